@@ -1,0 +1,21 @@
+"""Loader for tests/golden/golden.json.gz (reference outputs made by tests/golden/make_golden.py)."""
+import base64
+import gzip
+import json
+import os
+
+_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json.gz")
+MOTIFS = ["TTAGGG", "ttaggg", "TATATA", "AAAAAA", "CCCTAA", "TTAGGGTTAGGG", "ACGT", "TTNGGG"]
+TELOWIN = [["99.9", "0.4"], ["99.9", "0.1"], ["100"], ["95", "0.05"]]
+SDUST = [[], ["-w", "32", "-t", "15"], ["-t", "10"]]
+
+
+def load():
+    with gzip.open(_PATH, "rb") as f:
+        raw = json.load(f)
+
+    def dec(x):
+        if isinstance(x, dict):
+            return {k: dec(v) for k, v in x.items()}
+        return base64.b64decode(x)
+    return dec(raw)
