@@ -1,0 +1,363 @@
+// cornetto_b200/csrc/context.cu -- context, host/device batches, scratch, timing.
+#include <stdarg.h>
+
+#include "corn_internal.cuh"
+
+// --------------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------------
+int corn_set_err(corn_ctx *ctx, int code, const char *fmt, ...)
+{
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+extern "C" const char *corn_gpu_strerror(int status)
+{
+    switch (status) {
+    case CORN_OK: return "ok";
+    case CORN_E_NOGPU: return "no usable CUDA device (this build has no CPU fallback)";
+    case CORN_E_CUDA: return "CUDA runtime error";
+    case CORN_E_ARG: return "invalid argument";
+    case CORN_E_NOMEM: return "out of memory";
+    case CORN_E_LAYOUT: return "batch violates the CORN_ALIGN / zero-padding layout";
+    case CORN_E_TOOBIG: return "batch or record too large";
+    case CORN_E_STATE: return "call sequence error";
+    case CORN_E_INTERNAL: return "internal consistency check failed";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char *corn_gpu_last_error(const corn_ctx_t *ctx) { return ctx ? ctx->err : ""; }
+
+// --------------------------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------------------------
+extern "C" int corn_gpu_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return CORN_E_NOGPU; }
+    return n;
+}
+
+extern "C" int corn_gpu_init(int device, corn_ctx_t **out)
+{
+    if (!out) return CORN_E_ARG;
+    *out = NULL;
+    int n = corn_gpu_device_count();
+    if (n <= 0) return CORN_E_NOGPU;
+    if (device < 0) {
+        const char *e = getenv("CORNETTO_GPU");
+        device = e ? atoi(e) : 0;
+    }
+    if (device >= n) return CORN_E_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CORN_E_NOGPU;
+    if (prop.major < 10) return CORN_E_NOGPU;   // kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return CORN_E_NOGPU;
+
+    corn_ctx *ctx = (corn_ctx *)calloc(1, sizeof(corn_ctx));
+    if (!ctx) return CORN_E_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return CORN_E_CUDA; }
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 8; ++i)
+        if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { free(ctx); return CORN_E_CUDA; }
+    if (cudaMallocHost(&ctx->h_pinned_small, 4096) != cudaSuccess) { free(ctx); return CORN_E_NOMEM; }
+    *out = ctx;
+    return CORN_OK;
+}
+
+static void dbuf_free(corn_dbuf *b) { if (b->p) cudaFree(b->p); b->p = NULL; b->cap = 0; }
+
+extern "C" void corn_gpu_destroy(corn_ctx_t *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    corn_ctx_adopt(ctx, NULL);
+    corn_dbuf *bufs[] = { &ctx->cand, &ctx->tile_tab, &ctx->events, &ctx->runs, &ctx->misc, &ctx->scan_tmp,
+                          &ctx->bins, &ctx->bitmap, &ctx->wins, &ctx->sd_slots, &ctx->sd_out, &ctx->sd_tab };
+    for (size_t i = 0; i < sizeof bufs / sizeof bufs[0]; ++i) dbuf_free(bufs[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->own_stream);
+    cudaFreeHost(ctx->h_pinned_small);
+    free(ctx);
+}
+
+extern "C" int corn_gpu_set_stream(corn_ctx_t *ctx, void *s)
+{
+    if (!ctx) return CORN_E_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return CORN_OK;
+}
+
+int corn_dbuf_reserve(corn_ctx *ctx, corn_dbuf *b, size_t bytes)
+{
+    if (bytes <= b->cap) return CORN_OK;
+    CORN_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (b->p) {
+        CORN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(b->p);
+        b->p = NULL; b->cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;   // a little slack so steady-state calls do not reallocate
+    CORN_CUDA(ctx, cudaMalloc(&b->p, want));
+    b->cap = want;
+    return CORN_OK;
+}
+
+int corn_read_small(corn_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
+{
+    if (bytes > 4096) return corn_set_err(ctx, CORN_E_INTERNAL, "corn_read_small: %zu bytes", bytes);
+    CORN_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned_small, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CORN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(h_dst, ctx->h_pinned_small, bytes);
+    return CORN_OK;
+}
+
+void *corn_host_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (bytes == 0) bytes = 1;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    return p;
+}
+void corn_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int corn_gpu_last_timing(const corn_ctx_t *ctx, corn_timing_t *t)
+{
+    if (!ctx || !t) return CORN_E_ARG;
+    *t = ctx->timing;
+    return CORN_OK;
+}
+extern "C" uint64_t corn_gpu_total_launches(const corn_ctx_t *ctx) { return ctx ? ctx->total_launches : 0; }
+
+// --------------------------------------------------------------------------------------------
+// host batch builder (pinned)
+// --------------------------------------------------------------------------------------------
+struct corn_hbatch {
+    uint8_t  *seq;
+    uint64_t  cap, used;       // used is always a multiple of CORN_ALIGN
+    uint64_t *offset;
+    uint32_t *length;
+    uint32_t  n_rec, max_rec;
+    int       pinned;
+};
+
+static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int corn_hbatch_create(uint64_t capacity_bytes, uint32_t max_records, corn_hbatch_t **out)
+{
+    if (!out || max_records == 0) return CORN_E_ARG;
+    capacity_bytes = align_up(capacity_bytes < CORN_ALIGN ? CORN_ALIGN : capacity_bytes, CORN_ALIGN);
+    if (capacity_bytes > CORN_MAX_BATCH_BYTES) return CORN_E_TOOBIG;
+    corn_hbatch *hb = (corn_hbatch *)calloc(1, sizeof *hb);
+    if (!hb) return CORN_E_NOMEM;
+    // pinned when a CUDA device is present, plain memory otherwise (so that host-only logic
+    // -- parsing, layout -- can be unit-tested on a machine without a GPU)
+    void *p = NULL;
+    if (cudaMallocHost(&p, capacity_bytes) == cudaSuccess) hb->pinned = 1;
+    else { cudaGetLastError(); p = malloc(capacity_bytes); }
+    hb->seq = (uint8_t *)p;
+    hb->offset = (uint64_t *)malloc(sizeof(uint64_t) * max_records);
+    hb->length = (uint32_t *)malloc(sizeof(uint32_t) * max_records);
+    if (!hb->seq || !hb->offset || !hb->length) { corn_hbatch_destroy(hb); return CORN_E_NOMEM; }
+    hb->cap = capacity_bytes;
+    hb->max_rec = max_records;
+    *out = hb;
+    return CORN_OK;
+}
+
+extern "C" void corn_hbatch_destroy(corn_hbatch_t *hb)
+{
+    if (!hb) return;
+    if (hb->seq) { if (hb->pinned) cudaFreeHost(hb->seq); else free(hb->seq); }
+    free(hb->offset); free(hb->length); free(hb);
+}
+
+extern "C" void corn_hbatch_reset(corn_hbatch_t *hb) { hb->used = 0; hb->n_rec = 0; }
+
+extern "C" uint64_t corn_hbatch_room(const corn_hbatch_t *hb)
+{
+    if (hb->n_rec >= hb->max_rec || hb->used + CORN_ALIGN > hb->cap) return 0;
+    // a record of length L occupies align_up(L + 1, CORN_ALIGN) bytes
+    uint64_t left = hb->cap - hb->used;
+    uint64_t room = left - 1;
+    if (room > 0x7FFFFFFFull) room = 0x7FFFFFFFull;   // kseq records are < 2^31 (src/kseq.h:84,185)
+    return room;
+}
+
+extern "C" uint8_t *corn_hbatch_cursor(corn_hbatch_t *hb) { return hb->seq + hb->used; }
+
+extern "C" int corn_hbatch_commit(corn_hbatch_t *hb, uint64_t length)
+{
+    if (hb->n_rec >= hb->max_rec) return CORN_E_TOOBIG;
+    if (length > 0x7FFFFFFFull) return CORN_E_TOOBIG;
+    uint64_t span = align_up(length + 1, CORN_ALIGN);
+    if (hb->used + span > hb->cap) return CORN_E_TOOBIG;
+    memset(hb->seq + hb->used + length, 0, span - length);
+    hb->offset[hb->n_rec] = hb->used;
+    hb->length[hb->n_rec] = (uint32_t)length;
+    hb->n_rec++;
+    hb->used += span;
+    return CORN_OK;
+}
+
+extern "C" int corn_hbatch_add(corn_hbatch_t *hb, const void *bases, uint64_t length)
+{
+    if (length > corn_hbatch_room(hb) || (length == 0 && corn_hbatch_room(hb) == 0)) return CORN_E_TOOBIG;
+    if (length) memcpy(hb->seq + hb->used, bases, length);
+    return corn_hbatch_commit(hb, length);
+}
+
+extern "C" void corn_hbatch_view(const corn_hbatch_t *hb, corn_batch_t *v)
+{
+    v->seq = hb->seq; v->offset = hb->offset; v->length = hb->length;
+    v->n_rec = hb->n_rec; v->total_bytes = hb->used;
+}
+
+// --------------------------------------------------------------------------------------------
+// device batches
+// --------------------------------------------------------------------------------------------
+static int dbatch_new(corn_ctx *ctx, const uint64_t *offset, const uint32_t *length, uint32_t n_rec,
+                      uint64_t total_bytes, corn_dbatch **out)
+{
+    if (total_bytes % CORN_ALIGN) return corn_set_err(ctx, CORN_E_LAYOUT, "total_bytes %% %u != 0", CORN_ALIGN);
+    if (total_bytes > CORN_MAX_BATCH_BYTES) return corn_set_err(ctx, CORN_E_TOOBIG, "batch of %llu bytes", (unsigned long long)total_bytes);
+    corn_dbatch *db = (corn_dbatch *)calloc(1, sizeof *db);
+    if (!db) return CORN_E_NOMEM;
+    db->n_rec = n_rec;
+    db->total_bytes = total_bytes;
+    db->h_rec_off = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n_rec + 1));
+    db->h_rec_len = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n_rec + 1));
+    if (!db->h_rec_off || !db->h_rec_len) { free(db->h_rec_off); free(db->h_rec_len); free(db); return CORN_E_NOMEM; }
+    uint64_t prev_end = 0;
+    for (uint32_t i = 0; i < n_rec; ++i) {
+        uint64_t o = offset[i], l = length[i];
+        int bad = (o % CORN_ALIGN) || o < prev_end || o + l + 1 > total_bytes || l > 0x7FFFFFFFull;
+        if (bad) {
+            free(db->h_rec_off); free(db->h_rec_len); free(db);
+            return corn_set_err(ctx, CORN_E_LAYOUT, "record %u: offset %llu length %llu", i, (unsigned long long)o, (unsigned long long)l);
+        }
+        prev_end = o + l + 1;
+        db->h_rec_off[i] = (uint32_t)o;
+        db->h_rec_len[i] = (uint32_t)l;
+        db->n_bases += l;
+    }
+    db->h_rec_off[n_rec] = (uint32_t)total_bytes;
+    db->h_rec_len[n_rec] = 0;
+
+    cudaError_t e;
+    // round the data area up to whole tiles so the scan kernel never needs a bounds check
+    uint64_t tiles = (total_bytes + CORN_TILE_BYTES - 1) / CORN_TILE_BYTES;
+    db->alloc_bytes = CORN_GUARD_BYTES + tiles * CORN_TILE_BYTES + CORN_TAIL_BYTES;
+    e = cudaMalloc((void **)&db->d_base, db->alloc_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&db->d_rec_off, sizeof(uint32_t) * ((size_t)n_rec + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&db->d_rec_len, sizeof(uint32_t) * ((size_t)n_rec + 1));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        const unsigned long long want = db->alloc_bytes;
+        if (db->d_base) cudaFree(db->d_base);
+        if (db->d_rec_off) cudaFree(db->d_rec_off);
+        if (db->d_rec_len) cudaFree(db->d_rec_len);
+        free(db->h_rec_off); free(db->h_rec_len); free(db);
+        return corn_set_err(ctx, CORN_E_NOMEM, "cudaMalloc of %llu bytes: %s", want, cudaGetErrorString(e));
+    }
+    db->d_seq = db->d_base + CORN_GUARD_BYTES;
+    *out = db;
+    return CORN_OK;
+}
+
+extern "C" void corn_gpu_dbatch_free(corn_ctx_t *ctx, corn_dbatch_t *db)
+{
+    if (!db) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->last_db == db) ctx->last_db = NULL;
+    }
+    cudaFree(db->d_base); cudaFree(db->d_rec_off); cudaFree(db->d_rec_len);
+    free(db->h_rec_off); free(db->h_rec_len); free(db);
+}
+
+void corn_ctx_adopt(corn_ctx *ctx, corn_dbatch *db)
+{
+    if (ctx->owned_db && ctx->owned_db != db) corn_gpu_dbatch_free(ctx, ctx->owned_db);
+    ctx->owned_db = db;
+}
+
+extern "C" void *corn_gpu_dbatch_seq_ptr(const corn_dbatch_t *db) { return db ? db->d_seq : NULL; }
+extern "C" uint64_t corn_gpu_dbatch_bytes(const corn_dbatch_t *db) { return db ? db->total_bytes : 0; }
+
+static int dbatch_tables_to_device(corn_ctx *ctx, corn_dbatch *db)
+{
+    CORN_CUDA(ctx, cudaMemcpyAsync(db->d_rec_off, db->h_rec_off, sizeof(uint32_t) * ((size_t)db->n_rec + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CORN_CUDA(ctx, cudaMemcpyAsync(db->d_rec_len, db->h_rec_len, sizeof(uint32_t) * ((size_t)db->n_rec + 1), cudaMemcpyHostToDevice, ctx->stream));
+    return CORN_OK;
+}
+
+extern "C" int corn_gpu_upload(corn_ctx_t *ctx, const corn_batch_t *b, corn_dbatch_t **out)
+{
+    if (!ctx || !b || !out || (b->n_rec && (!b->offset || !b->length)) || (b->total_bytes && !b->seq)) return CORN_E_ARG;
+    CORN_CUDA(ctx, cudaSetDevice(ctx->device));
+    corn_dbatch *db = NULL;
+    CORN_TRY(dbatch_new(ctx, b->offset, b->length, b->n_rec, b->total_bytes, &db));
+    int r = CORN_OK;
+    cudaError_t e = cudaEventRecord(ctx->ev[0], ctx->stream);
+    // guard + tail (and the round-up-to-tile area) are zero; the record area is copied as is:
+    // the layout contract makes the caller responsible for the zero padding between records.
+    if (e == cudaSuccess) e = cudaMemsetAsync(db->d_base, 0, CORN_GUARD_BYTES, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(db->d_seq + b->total_bytes, 0, db->alloc_bytes - CORN_GUARD_BYTES - b->total_bytes, ctx->stream);
+    if (e == cudaSuccess && b->total_bytes) e = cudaMemcpyAsync(db->d_seq, b->seq, b->total_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) r = dbatch_tables_to_device(ctx, db);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess || r != CORN_OK) {
+        corn_gpu_dbatch_free(ctx, db);
+        return r != CORN_OK ? r : corn_set_err(ctx, CORN_E_CUDA, "upload: %s", cudaGetErrorString(e));
+    }
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    *out = db;
+    return CORN_OK;
+}
+
+extern "C" int corn_gpu_dbatch_alloc(corn_ctx_t *ctx, const uint32_t *length, uint32_t n_rec, corn_dbatch_t **out)
+{
+    if (!ctx || !out || (n_rec && !length)) return CORN_E_ARG;
+    CORN_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t *off = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)n_rec + 1));
+    if (!off) return CORN_E_NOMEM;
+    uint64_t used = 0;
+    for (uint32_t i = 0; i < n_rec; ++i) { off[i] = used; used += align_up((uint64_t)length[i] + 1, CORN_ALIGN); }
+    corn_dbatch *db = NULL;
+    int r = dbatch_new(ctx, off, length, n_rec, used, &db);
+    free(off);
+    if (r != CORN_OK) return r;
+    cudaError_t e = cudaMemsetAsync(db->d_base, 0, db->alloc_bytes, ctx->stream);
+    if (e == cudaSuccess) r = dbatch_tables_to_device(ctx, db);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess || r != CORN_OK) {
+        corn_gpu_dbatch_free(ctx, db);
+        return r != CORN_OK ? r : corn_set_err(ctx, CORN_E_CUDA, "dbatch_alloc: %s", cudaGetErrorString(e));
+    }
+    *out = db;
+    return CORN_OK;
+}
+
+extern "C" int corn_gpu_dbatch_download(corn_ctx_t *ctx, const corn_dbatch_t *db, uint32_t rec, uint8_t *dst)
+{
+    if (!ctx || !db || !dst || rec >= db->n_rec) return CORN_E_ARG;
+    CORN_CUDA(ctx, cudaSetDevice(ctx->device));
+    CORN_CUDA(ctx, cudaMemcpyAsync(dst, db->d_seq + db->h_rec_off[rec], db->h_rec_len[rec], cudaMemcpyDeviceToHost, ctx->stream));
+    CORN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CORN_OK;
+}

@@ -1,0 +1,187 @@
+// cornetto_b200/csrc/corn_internal.cuh -- context, device buffers and small device utilities
+// shared by the telofind / telowin / sdust translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/corn_gpu.h"
+
+// --------------------------------------------------------------------------------------------
+// HBM layout of a resident batch
+//   [ GUARD bytes of 0x00 ][ total_bytes of records+padding ][ TAIL bytes of 0x00 ]
+// GUARD lets the kernels look m bytes behind position 0, TAIL lets them read one tile row and
+// the sdust right halo past the end without bounds checks.
+// --------------------------------------------------------------------------------------------
+#define CORN_GUARD_BYTES 1024u
+#define CORN_TAIL_BYTES  4096u
+
+// telofind scan tiling: a chunk is the 32 bytes one lane owns per warp iteration, a row is the
+// 1 KiB a warp consumes per iteration, a tile is what a warp scans between two flushes of its
+// candidate list.
+#define CORN_CHUNK_BYTES  32u
+#define CORN_ROW_BYTES    1024u
+#define CORN_TILE_ROWS    32u
+#define CORN_TILE_CHUNKS  (CORN_TILE_ROWS * 32u)            // 1024 candidate slots per tile
+#define CORN_TILE_BYTES   (CORN_TILE_ROWS * CORN_ROW_BYTES) // 32 KiB
+
+struct corn_dbatch {
+    uint8_t  *d_base;      // allocation start (guard included)
+    uint8_t  *d_seq;       // d_base + CORN_GUARD_BYTES
+    uint64_t  total_bytes; // multiple of CORN_ALIGN
+    uint64_t  alloc_bytes;
+    uint32_t  n_rec;
+    uint32_t *d_rec_off;   // [n_rec+1] start of each record (buffer position); [n_rec] = total_bytes
+    uint32_t *d_rec_len;   // [n_rec]
+    uint32_t *h_rec_off;   // host copies
+    uint32_t *h_rec_len;
+    uint64_t  n_bases;     // sum of lengths
+};
+
+struct corn_dbuf {         // grow-only device scratch
+    void  *p;
+    size_t cap;
+};
+
+struct corn_ctx {
+    int          device;
+    int          sm_count;
+    cudaStream_t own_stream, stream;
+    cudaEvent_t  ev[8];
+    char         err[512];
+    corn_timing_t timing;
+    uint64_t     total_launches;
+
+    // scratch (grow-only, reused across calls)
+    corn_dbuf cand;        // telofind tile candidate lists
+    corn_dbuf tile_tab;    // per-tile counts / offsets
+    corn_dbuf events;      // ordered start/end position lists
+    corn_dbuf runs;        // final corn_run_t list of the last telofind
+    corn_dbuf misc;        // small per-call things (counters, totals, scan temporaries)
+    corn_dbuf scan_tmp;
+    corn_dbuf bins;        // telowin bin counters
+    corn_dbuf bitmap;      // telowin general path
+    corn_dbuf wins;        // telowin output
+    corn_dbuf sd_slots;    // sdust per-chunk interval slots
+    corn_dbuf sd_out;      // sdust compacted output
+    corn_dbuf sd_tab;      // sdust chunk tables
+
+    // batch uploaded by a host-buffer entry point; kept resident until the next such call so a
+    // fused telowin(hits == NULL) can still reach its record table
+    corn_dbatch *owned_db;
+
+    // state left by the last telofind for a fused telowin(hits == NULL)
+    const corn_dbatch *last_db;
+    uint64_t  last_n_run;
+    int       last_runs_disjoint;  // runs cannot overlap (border-free motif, no fwd/rev overlap)
+    int       last_motif_len;
+
+    void     *h_pinned_small;      // 4 KiB pinned scratch for small readbacks
+};
+
+// --------------------------------------------------------------------------------------------
+// error plumbing
+// --------------------------------------------------------------------------------------------
+int corn_set_err(corn_ctx *ctx, int code, const char *fmt, ...);
+
+#define CORN_CUDA(ctx, call)                                                                    \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return corn_set_err((ctx), e_ == cudaErrorMemoryAllocation ? CORN_E_NOMEM : CORN_E_CUDA, \
+                                "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define CORN_TRY(expr)                       \
+    do {                                     \
+        int r_ = (expr);                     \
+        if (r_ != CORN_OK) return r_;        \
+    } while (0)
+
+// replace the context-owned resident batch (frees the previous one)
+void corn_ctx_adopt(corn_ctx *ctx, corn_dbatch *db);
+
+// grow-only scratch; contents are NOT preserved on growth
+int corn_dbuf_reserve(corn_ctx *ctx, corn_dbuf *b, size_t bytes);
+
+// kernel launch bookkeeping (gpu_launches in bench.py comes from here)
+static inline void corn_count_launch(corn_ctx *ctx, unsigned n = 1)
+{
+    ctx->timing.launches += n;
+    ctx->total_launches += n;
+}
+
+#define CORN_LAUNCH_CHECK(ctx)                                                                  \
+    do {                                                                                        \
+        cudaError_t e_ = cudaGetLastError();                                                    \
+        if (e_ != cudaSuccess)                                                                  \
+            return corn_set_err((ctx), CORN_E_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, \
+                                cudaGetErrorString(e_));                                        \
+    } while (0)
+
+// --------------------------------------------------------------------------------------------
+// exclusive scans (scan.cu).  n may be 0.  total (device pointer, may be NULL) receives the sum.
+// --------------------------------------------------------------------------------------------
+int corn_scan_u32(corn_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, size_t n, uint32_t *d_total);
+int corn_scan_u32x4(corn_ctx *ctx, const uint4 *d_in, uint4 *d_out, size_t n, uint4 *d_total);
+
+// small synchronous readback through pinned scratch (<= 4 KiB)
+int corn_read_small(corn_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+
+// pinned host result blocks handed to the caller (freed by corn_gpu_*_free)
+void *corn_host_alloc(size_t bytes);
+void  corn_host_free(void *p);
+
+// --------------------------------------------------------------------------------------------
+// device helpers
+// --------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t corn_lanemask_lt()
+{
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ uint32_t corn_warp_sum(uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// inclusive warp scan
+__device__ __forceinline__ uint32_t corn_warp_iscan(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// first index i in [0,n) with a[i] > x   (upper bound); a ascending
+__device__ __forceinline__ uint32_t corn_upper_bound(const uint32_t *__restrict__ a, uint32_t n, uint32_t x)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// first index i in [0,n) with a[i] >= x  (lower bound)
+__device__ __forceinline__ uint32_t corn_lower_bound(const uint32_t *__restrict__ a, uint32_t n, uint32_t x)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+#endif

@@ -1,0 +1,130 @@
+// cornetto_b200/csrc/scan.cu -- exclusive prefix sums over the small tables of the sparse phase
+// (per-tile event counts, per-record chunk counts, per-block window counts).  These tables hold
+// 10^4..10^6 entries, so a plain reduce / scan-of-sums / scan three-kernel scheme is enough.
+#include "corn_internal.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS   = 8;
+constexpr int SCAN_BLOCK   = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t zero_of(uint32_t) { return 0u; }
+__device__ __forceinline__ uint4    zero_of(uint4)    { return make_uint4(0, 0, 0, 0); }
+__device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return a + b; }
+__device__ __forceinline__ uint4    add(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// exclusive scan of one value per thread across the block; returns the block total in *total
+template <typename T>
+__device__ T block_exclusive(T v, T *smem, T *total)
+{
+    const int tid = threadIdx.x;
+    smem[tid] = v;
+    __syncthreads();
+    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+        T t = zero_of(T());
+        if (tid >= o) t = smem[tid - o];
+        __syncthreads();
+        if (tid >= o) smem[tid] = add(smem[tid], t);
+        __syncthreads();
+    }
+    T incl = smem[tid];
+    *total = smem[SCAN_THREADS - 1];
+    T excl = tid ? smem[tid - 1] : zero_of(T());
+    __syncthreads();
+    (void)incl;
+    return excl;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_block_sums(const T *__restrict__ in, T *__restrict__ sums, size_t n)
+{
+    __shared__ T smem[SCAN_THREADS];
+    size_t base = (size_t)blockIdx.x * SCAN_BLOCK + (size_t)threadIdx.x * SCAN_ITEMS;
+    T s = zero_of(T());
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) s = add(s, in[base + i]);
+    T total;
+    block_exclusive(s, smem, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// out[i] = offset[block] + exclusive prefix inside the block.  offsets == NULL means 0.
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_block_scan(const T *in, T *out, size_t n,   // in == out allowed
+                                                             const T *offsets, T *total_out)
+{
+    __shared__ T smem[SCAN_THREADS];
+    size_t base = (size_t)blockIdx.x * SCAN_BLOCK + (size_t)threadIdx.x * SCAN_ITEMS;
+    T v[SCAN_ITEMS];
+    T s = zero_of(T());
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : zero_of(T());
+        s = add(s, v[i]);
+    }
+    T total;
+    T excl = block_exclusive(s, smem, &total);
+    T off = offsets ? offsets[blockIdx.x] : zero_of(T());
+    T run = add(off, excl);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run = add(run, v[i]);
+    }
+    if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total_out = add(off, total);
+}
+
+template <typename T>
+__global__ void k_zero_total(T *t) { *t = zero_of(T()); }
+
+template <typename T>
+int scan_impl(corn_ctx *ctx, const T *d_in, T *d_out, size_t n, T *d_total)
+{
+    if (n == 0) {
+        if (d_total) { k_zero_total<T><<<1, 1, 0, ctx->stream>>>(d_total); corn_count_launch(ctx); CORN_LAUNCH_CHECK(ctx); }
+        return CORN_OK;
+    }
+    size_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (nb == 1) {
+        k_block_scan<T><<<1, SCAN_THREADS, 0, ctx->stream>>>(d_in, d_out, n, (const T *)NULL, d_total);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+        return CORN_OK;
+    }
+    // two temporaries per level; levels shrink by 4096x so two levels cover 2^36 entries
+    size_t nb2 = (nb + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->scan_tmp, sizeof(T) * (nb + nb2 + 2)));
+    T *sums = (T *)ctx->scan_tmp.p, *sums2 = sums + nb;
+    k_block_sums<T><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(d_in, sums, n);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    if (nb2 == 1) {
+        k_block_scan<T><<<1, SCAN_THREADS, 0, ctx->stream>>>(sums, sums, nb, (const T *)NULL, (T *)NULL);
+        corn_count_launch(ctx);
+    } else {
+        k_block_sums<T><<<(unsigned)nb2, SCAN_THREADS, 0, ctx->stream>>>(sums, sums2, nb);
+        k_block_scan<T><<<1, SCAN_THREADS, 0, ctx->stream>>>(sums2, sums2, nb2, (const T *)NULL, (T *)NULL);
+        k_block_scan<T><<<(unsigned)nb2, SCAN_THREADS, 0, ctx->stream>>>(sums, sums, nb, sums2, (T *)NULL);
+        corn_count_launch(ctx, 3);
+        if (nb2 > SCAN_BLOCK) return corn_set_err(ctx, CORN_E_TOOBIG, "scan of %zu entries", n);
+    }
+    CORN_LAUNCH_CHECK(ctx);
+    k_block_scan<T><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(d_in, d_out, n, sums, d_total);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    return CORN_OK;
+}
+
+}  // namespace
+
+int corn_scan_u32(corn_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, size_t n, uint32_t *d_total)
+{
+    return scan_impl<uint32_t>(ctx, d_in, d_out, n, d_total);
+}
+
+int corn_scan_u32x4(corn_ctx *ctx, const uint4 *d_in, uint4 *d_out, size_t n, uint4 *d_total)
+{
+    return scan_impl<uint4>(ctx, d_in, d_out, n, d_total);
+}

@@ -1,0 +1,245 @@
+// cornetto_b200/csrc/sdust.cu -- symmetric DUST low-complexity masking on the GPU.
+//
+// Replaces sdust_core(), src/sdust/sdust.c:130-160.  The state machine is inherently serial
+// along a sequence, so the parallelism is across chunks: one THREAD per chunk of a record, with
+// the exact mid-record start and the seam merge described in sdust_core.cuh.  Per-thread state
+// (window ring, 2x64 counters, W slots) lives in shared memory, one 4-byte column per thread so
+// that data-dependent indices never cause bank conflicts.
+//
+// This kernel is instruction-issue / shared-memory bound, not HBM bound (about 60 instructions
+// and 10 shared-memory accesses per base against 1 byte of HBM traffic); DESIGN.md says so.
+#include "corn_internal.cuh"
+#include "sdust_core.cuh"
+
+namespace {
+
+constexpr int SD_BLOCK = 128;
+
+__global__ void k_sdust_nchunks(const uint32_t *__restrict__ rec_len, uint32_t *__restrict__ nch, uint32_t n_rec, uint32_t C)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rec) nch[r] = (rec_len[r] + C - 1) / C;
+}
+
+// byte stream over one record, 16 bytes per global load
+struct DevFetch {
+    const uint8_t *seq;
+    uint4 buf;
+    int blk;
+    __device__ __forceinline__ uint8_t operator()(int i)
+    {
+        const int b = i >> 4;
+        if (b != blk) { buf = __ldg((const uint4 *)(seq + ((size_t)b << 4))); blk = b; }
+        const int k = i & 15;
+        const uint32_t w = k < 8 ? (k < 4 ? buf.x : buf.y) : (k < 12 ? buf.z : buf.w);
+        return (uint8_t)(w >> ((k & 3) * 8));
+    }
+};
+
+struct SdParams {
+    const uint8_t  *seq;
+    const uint32_t *rec_off, *rec_len;
+    const uint32_t *chunk_base;     // [n_rec+1]
+    uint32_t n_rec, n_chunks;
+    int T, W, C;
+    uint32_t cap;
+    uint64_t *slots;                // n_chunks * cap
+    uint32_t *cnt;                  // [n_chunks]
+    uint32_t *err;
+};
+
+__global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
+{
+    extern __shared__ uint32_t smem[];
+    const uint32_t j = blockIdx.x * SD_BLOCK + threadIdx.x;
+    if (j >= P.n_chunks) return;
+    const uint32_t rec = corn_upper_bound(P.chunk_base, P.n_rec, j) - 1;
+    const uint32_t k = j - P.chunk_base[rec];
+    const int len = (int)P.rec_len[rec];
+    const int c0 = (int)k * P.C;
+    const int c1 = min(len, c0 + P.C);
+
+    // column layout: row r of this thread at smem[r * SD_BLOCK + tid]
+    const int ring_rows = (P.W + 3) >> 2;
+    uint8_t *col = (uint8_t *)(smem + threadIdx.x);
+    sd_mem m;
+    m.pitch = SD_BLOCK * 4;
+    m.ring = col;
+    m.cw   = col + (size_t)ring_rows * m.pitch;
+    m.cv   = m.cw + 16 * (size_t)m.pitch;
+    m.slot = (uint32_t *)(m.cv + 16 * (size_t)m.pitch);
+
+    sd_sink sink;
+    sd_sink_init(sink, P.slots + (size_t)j * P.cap, P.cap);
+    DevFetch fetch;
+    fetch.seq = P.seq + P.rec_off[rec];
+    fetch.blk = -1;
+    fetch.buf = make_uint4(0, 0, 0, 0);
+    sd_run_chunk(fetch, len, c0, c1, P.T, P.W, m, sink);
+    P.cnt[j] = sink.n;
+    if (sink.overflow) atomicAdd(P.err, 1u);
+}
+
+struct GatherParams {
+    const uint64_t *slots;
+    const uint32_t *cnt;
+    const uint32_t *chunk_base, *rec_len;
+    uint32_t n_rec, n_chunks, cap;
+    int C, W;
+    uint32_t *out_cnt;
+    const uint32_t *out_off;
+    uint64_t *out;
+};
+
+__global__ void __launch_bounds__(256) k_sdust_gather(const GatherParams P, int write)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n_chunks) return;
+    const uint32_t rec = corn_upper_bound(P.chunk_base, P.n_rec, j) - 1;
+    const uint32_t k = j - P.chunk_base[rec];
+    if (!write) { P.out_cnt[j] = sd_gather_count(P.slots, P.cnt, P.cap, j, k, P.C, P.W); return; }
+    const uint32_t nch = P.chunk_base[rec + 1] - P.chunk_base[rec];
+    sd_gather_write(P.slots, P.cnt, P.cap, j, k, nch, P.C, P.W, P.out + P.out_off[j]);
+}
+
+// rec_first[r] = offset of the first interval of record r; rec_first[n_rec] = total
+__global__ void k_sdust_rec_first(const uint32_t *__restrict__ chunk_base, const uint32_t *__restrict__ out_off,
+                                  const uint32_t *__restrict__ total, uint32_t n_rec, uint32_t n_chunks, uint64_t *rec_first)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rec) return;
+    const uint32_t cb = r < n_rec ? chunk_base[r] : n_chunks;
+    rec_first[r] = cb < n_chunks ? out_off[cb] : *total;
+}
+
+}  // namespace
+
+static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_intervals_t *out)
+{
+    if (W < 3 || W > SD_MAX_W) return corn_set_err(ctx, CORN_E_ARG, "sdust window %d outside [3,%d]", W, SD_MAX_W);
+    CORN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const float keep_h2d = ctx->timing.h2d_ms;
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    ctx->timing.h2d_ms = keep_h2d;
+    out->iv = NULL; out->rec_first = NULL; out->n_iv = 0; out->n_rec = db->n_rec; out->_owner = NULL;
+
+    int C = 4096;
+    if (const char *e = getenv("CORNETTO_SDUST_CHUNK")) { int v = atoi(e); if (v >= 16 && v <= (1 << 20)) C = v; }
+    const uint32_t n_rec = db->n_rec;
+    const uint32_t cap = (uint32_t)(C + 2 * W) / 4 + 2;
+
+    // tables: nch[n_rec+1] | chunk_base[n_rec+1] | (later) cnt[n_chunks] | out_cnt | out_off
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->misc, 4096));
+    uint32_t *d_tot = (uint32_t *)((uint8_t *)ctx->misc.p + 2048);
+    uint32_t *d_err = d_tot + 4;
+    CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 32, st));
+    // host-side chunk count (lengths are known on the host): sizes the tables without a readback
+    uint64_t n_chunks64 = 0;
+    for (uint32_t r = 0; r < n_rec; ++r) n_chunks64 += ((uint64_t)db->h_rec_len[r] + C - 1) / C;
+    if (n_chunks64 > 0xFFFFFFF0ull) return corn_set_err(ctx, CORN_E_TOOBIG, "too many sdust chunks");
+    const uint32_t n_chunks = (uint32_t)n_chunks64;
+    const size_t tab_words = 2 * ((size_t)n_rec + 1) + 3 * ((size_t)n_chunks + 1) + 16;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_tab, tab_words * sizeof(uint32_t)));
+    uint32_t *nch = (uint32_t *)ctx->sd_tab.p, *chunk_base = nch + n_rec + 1;
+    uint32_t *cnt = chunk_base + n_rec + 1, *out_cnt = cnt + n_chunks + 1, *out_off = out_cnt + n_chunks + 1;
+
+    uint64_t *h_first = (uint64_t *)corn_host_alloc(sizeof(uint64_t) * ((size_t)n_rec + 1));
+    if (!h_first) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc");
+    out->rec_first = h_first;
+    if (n_chunks == 0) {
+        for (uint32_t r = 0; r <= n_rec; ++r) h_first[r] = 0;
+        return CORN_OK;
+    }
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_slots, (size_t)n_chunks * cap * sizeof(uint64_t)));
+
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    k_sdust_nchunks<<<(n_rec + 255) / 256, 256, 0, st>>>(db->d_rec_len, nch, n_rec, (uint32_t)C);
+    corn_count_launch(ctx);
+    CORN_TRY(corn_scan_u32(ctx, nch, chunk_base, n_rec, chunk_base + n_rec));
+
+    SdParams sp;
+    sp.seq = db->d_seq; sp.rec_off = db->d_rec_off; sp.rec_len = db->d_rec_len; sp.chunk_base = chunk_base;
+    sp.n_rec = n_rec; sp.n_chunks = n_chunks; sp.T = T; sp.W = W; sp.C = C; sp.cap = cap;
+    sp.slots = (uint64_t *)ctx->sd_slots.p; sp.cnt = cnt; sp.err = d_err;
+    const int rows = ((W + 3) >> 2) + 32 + W;
+    const size_t smem = (size_t)rows * SD_BLOCK * 4;
+    CORN_CUDA(ctx, cudaFuncSetAttribute(k_sdust_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    k_sdust_scan<<<(n_chunks + SD_BLOCK - 1) / SD_BLOCK, SD_BLOCK, smem, st>>>(sp);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+
+    GatherParams gp;
+    gp.slots = sp.slots; gp.cnt = cnt; gp.chunk_base = chunk_base; gp.rec_len = db->d_rec_len;
+    gp.n_rec = n_rec; gp.n_chunks = n_chunks; gp.cap = cap; gp.C = C; gp.W = W;
+    gp.out_cnt = out_cnt; gp.out_off = out_off; gp.out = NULL;
+    k_sdust_gather<<<(n_chunks + 255) / 256, 256, 0, st>>>(gp, 0);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    CORN_TRY(corn_scan_u32(ctx, out_cnt, out_off, n_chunks, d_tot));
+    uint32_t hv[8];
+    CORN_TRY(corn_read_small(ctx, hv, d_tot, 32));
+    const uint32_t n_iv = hv[0];
+    if (hv[4]) return corn_set_err(ctx, CORN_E_INTERNAL, "sdust: %u chunks overflowed their interval slot", hv[4]);
+    uint64_t *d_first = NULL;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_out, ((size_t)n_iv + 1) * sizeof(uint64_t) + ((size_t)n_rec + 1) * sizeof(uint64_t)));
+    gp.out = (uint64_t *)ctx->sd_out.p;
+    d_first = gp.out + n_iv + 1;
+    if (n_iv) {
+        k_sdust_gather<<<(n_chunks + 255) / 256, 256, 0, st>>>(gp, 1);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+    }
+    k_sdust_rec_first<<<(n_rec + 1 + 255) / 256, 256, 0, st>>>(chunk_base, out_off, d_tot, n_rec, n_chunks, d_first);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+
+    out->n_iv = n_iv;
+    if (n_iv) {
+        out->iv = (uint64_t *)corn_host_alloc((size_t)n_iv * sizeof(uint64_t));
+        if (!out->iv) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc of %u intervals", n_iv);
+        CORN_CUDA(ctx, cudaMemcpyAsync(out->iv, gp.out, (size_t)n_iv * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    }
+    CORN_CUDA(ctx, cudaMemcpyAsync(h_first, d_first, ((size_t)n_rec + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+    CORN_CUDA(ctx, cudaStreamSynchronize(st));
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&ctx->timing.scan_ms, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&b, ctx->ev[4], ctx->ev[5]);
+    ctx->timing.post_ms = a + b;
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[5], ctx->ev[6]);
+    ctx->timing.out_bytes = (uint64_t)n_iv * 8;
+    return CORN_OK;
+}
+
+extern "C" int corn_gpu_sdust_dev(corn_ctx_t *ctx, const corn_dbatch_t *db, int T, int W, corn_intervals_t *out)
+{
+    if (!ctx || !db || !out) return CORN_E_ARG;
+    int r = sdust_run(ctx, db, T, W, out);
+    if (r != CORN_OK) corn_gpu_intervals_free(out);
+    return r;
+}
+
+extern "C" int corn_gpu_sdust(corn_ctx_t *ctx, const corn_batch_t *batch, int T, int W, corn_intervals_t *out)
+{
+    if (!ctx || !batch || !out) return CORN_E_ARG;
+    corn_dbatch_t *db = NULL;
+    CORN_TRY(corn_gpu_upload(ctx, batch, &db));
+    const float h2d = ctx->timing.h2d_ms;
+    corn_ctx_adopt(ctx, db);
+    ctx->last_db = NULL;            // the telofind state of this context no longer matches the resident batch
+    ctx->timing.h2d_ms = h2d;
+    return corn_gpu_sdust_dev(ctx, db, T, W, out);
+}
+
+extern "C" void corn_gpu_intervals_free(corn_intervals_t *iv)
+{
+    if (!iv) return;
+    corn_host_free(iv->iv);
+    corn_host_free(iv->rec_first);
+    iv->iv = NULL; iv->rec_first = NULL; iv->n_iv = 0; iv->_owner = NULL;
+}

@@ -1,0 +1,371 @@
+// cornetto_b200/csrc/sdust_core.cuh -- symmetric DUST state machine for one chunk of one record.
+//
+// Restates sdust_core() of src/sdust/sdust.c:130-160 (lh3/sdust 0.1-r2) in a form that fits a GPU
+// thread: bounded state, no heap, and a provably exact way to start in the middle of a record.
+// The same code compiles for the device (sdust.cu: one thread per chunk, state in shared memory)
+// and for the host (tests/sim/: a CPU simulation of the chunked execution, checked against the
+// oracle without a GPU).
+//
+// 1. Bounded perfect-interval list.  The reference keeps a list P of perfect intervals sorted
+//    by descending start (sdust.c:104-128) that can hold ~W^2/2 entries inside a long
+//    homopolymer.  Only two things are ever read from it:
+//      - the best score ratio among entries with start >= s (the j-loop, :113-117), and
+//      - for each start s, the entry inserted last (largest finish), which is the one saved
+//        when s leaves the window (:88-102); the others with the same start are contained in it.
+//    A later insertion with the same start always has a ratio >= the earlier ones (it had to
+//    beat them to be inserted) and a larger finish, so ONE slot per start position -- a ring of
+//    W slots holding (r, l, finish-start) -- reproduces every decision and every saved interval.
+//
+// 2. Starting mid-record.  The window state (w, cw, rw, L, cv, rv) is a pure function of the last
+//    W-2 emitted triplets, the slots only matter while their start is inside the window, and at
+//    any non-ACGT byte the reference flushes all of P (:152-156) but keeps the window (the "stale
+//    window" quirk).  Let a run be started fresh (empty window, no slots) at p0 < c0 and let tau0
+//    be the position at which it has emitted W-2 triplets.  From tau0 on its window equals the
+//    true one; any slot that differs from the true execution has start <= ws(tau0) + W-3 and
+//    finish <= start + W, and a differing decision can only create a slot whose start is <= that
+//    of a differing slot it contains (and sd_save may save/drop the slot one start to its right
+//    differently).  Hence every interval touching positions >= ws(tau0) + 2W - 2 is identical, and since ws(tau0) <= tau0 it suffices that
+//        c0 >= tau0 + 2W.
+//    sdust_warm_start() walks back from c0 - 2W until W triplet positions have been seen (W-2
+//    plus two for the run-length difference at p0) or the record start is reached (exact).
+//    For N-free sequence this is a 3W+2 = 194 byte warm-up; with Ns it stretches as needed.
+//    A chunk owns the save events that happen while positions [c0, c1) are processed; it stops at
+//    c1 (the next chunk re-creates the state there), so there is no right halo at all.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SD_HD __host__ __device__ __forceinline__
+#else
+#define SD_HD static inline
+#endif
+
+#define SD_MAX_W 128
+
+// seq_nt4_table, src/sdust/sdust.c:23-40: A/a C/c G/g T/t -> 0..3, bytes 0..3 -> 0..3, rest 4
+SD_HD int sd_nt4(uint8_t c)
+{
+    if (c < 4) return c;
+    const uint8_t u = c & 0xDF;
+    return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : 4;
+}
+
+// Per-thread state arrays live in shared memory on the device with one 4-byte wide column per
+// thread (so a thread always hits its own bank whatever index it uses).  pitch = bytes between
+// consecutive 4-byte rows of one thread's column; on the host pitch = 4 (a plain array).
+struct sd_mem {
+    uint8_t  *ring;    // W entries: triplet codes of the window deque
+    uint8_t  *cw;      // 64 window counters
+    uint8_t  *cv;      // 64 suffix counters
+    uint32_t *slot;    // W slots: valid:1 | flen:8 | l:8 | r:15
+    uint32_t  pitch;   // bytes
+};
+
+#define SD_U8(base, i)  (*((base) + ((uint32_t)(i) >> 2) * m.pitch + ((uint32_t)(i) & 3u)))
+#define SD_U32(base, i) (*(uint32_t *)((uint8_t *)(base) + (uint32_t)(i) * m.pitch))
+
+#define SD_SLOT_VALID 0x80000000u
+SD_HD uint32_t sd_slot_pack(int r, int l, int flen) { return SD_SLOT_VALID | ((uint32_t)flen << 23) | ((uint32_t)l << 15) | (uint32_t)r; }
+SD_HD int sd_slot_r(uint32_t s) { return (int)(s & 0x7FFFu); }
+SD_HD int sd_slot_l(uint32_t s) { return (int)((s >> 15) & 0xFFu); }
+SD_HD int sd_slot_flen(uint32_t s) { return (int)((s >> 23) & 0xFFu); }
+
+// interval sink = the reference's `res` vector for the save events this chunk owns.
+// save_masked_regions() appends an interval unless it starts at or before the finish of the
+// LAST saved one, in which case only that finish may grow (sdust.c:94-98).  After an N the
+// stale window can produce saves that are not in ascending order, and then this rule is not a
+// plain union (an earlier start is swallowed) -- so chunks own save EVENTS BY TIME (the input
+// position being processed when the save happens), fold them with this very rule, and the
+// per-chunk lists are folded again across seams (sd_gather_*) with the same rule.
+struct sd_sink {
+    uint64_t *out;
+    uint32_t  n, cap;
+    int       on;              // events before the chunk's first owned position are warm-up: ignored
+    int       cur_s, cur_f;    // last saved interval (cur_f < 0: none); written out when superseded
+    uint32_t  overflow;
+};
+
+SD_HD void sd_sink_init(sd_sink &k, uint64_t *out, uint32_t cap)
+{
+    k.out = out; k.n = 0; k.cap = cap; k.on = 0; k.cur_s = 0; k.cur_f = -1; k.overflow = 0;
+}
+SD_HD void sd_sink_close(sd_sink &k)
+{
+    if (k.cur_f >= 0) {
+        if (k.n < k.cap) k.out[k.n] = (uint64_t)(uint32_t)k.cur_s << 32 | (uint32_t)k.cur_f;
+        else k.overflow = 1;
+        ++k.n;
+        k.cur_f = -1;
+    }
+}
+SD_HD void sd_sink_put(sd_sink &k, int s, int f)
+{
+    if (!k.on) return;
+    if (k.cur_f >= 0 && s <= k.cur_f) { if (f > k.cur_f) k.cur_f = f; return; }
+    sd_sink_close(k);
+    k.cur_s = s; k.cur_f = f;
+}
+
+struct sd_state {
+    int wn, whead;       // deque size / index of its oldest element in the ring
+    int L, rw, rv;
+    int nslot;           // valid slots
+    int pstart;          // every valid slot has start >= pstart
+    int l;               // length of the current A/C/G/T run
+    unsigned t;          // current triplet
+};
+
+SD_HD void sd_reset(sd_state &s, const sd_mem &m, int W)
+{
+    s.wn = s.whead = s.L = s.rw = s.rv = s.nslot = s.pstart = s.l = 0;
+    s.t = 0;
+    for (int i = 0; i < 64; ++i) { SD_U8(m.cw, i) = 0; SD_U8(m.cv, i) = 0; }
+    for (int i = 0; i < W; ++i) SD_U32(m.slot, i) = 0;
+}
+
+SD_HD int sd_ring_idx(const sd_state &s, int i, int W)
+{
+    int k = s.whead + i;
+    return k >= W ? k - W : k;
+}
+
+// shift_window(): sdust.c:66-86
+SD_HD void sd_shift_window(sd_state &s, const sd_mem &m, int t, int T, int W)
+{
+    if (s.wn >= W - 2) {
+        const int x = SD_U8(m.ring, s.whead);
+        s.whead = s.whead + 1 >= W ? 0 : s.whead + 1;
+        --s.wn;
+        const int c = SD_U8(m.cw, x) - 1;
+        SD_U8(m.cw, x) = (uint8_t)c;
+        s.rw -= c;
+        if (s.L > s.wn) {
+            --s.L;
+            const int d = SD_U8(m.cv, x) - 1;
+            SD_U8(m.cv, x) = (uint8_t)d;
+            s.rv -= d;
+        }
+    }
+    SD_U8(m.ring, sd_ring_idx(s, s.wn, W)) = (uint8_t)t;
+    ++s.wn;
+    ++s.L;
+    {
+        const int c = SD_U8(m.cw, t);
+        s.rw += c;
+        SD_U8(m.cw, t) = (uint8_t)(c + 1);
+        const int d = SD_U8(m.cv, t);
+        s.rv += d;
+        SD_U8(m.cv, t) = (uint8_t)(d + 1);
+        if ((d + 1) * 10 > T << 1) {
+            int x;
+            do {
+                x = SD_U8(m.ring, sd_ring_idx(s, s.wn - s.L, W));
+                const int e = SD_U8(m.cv, x) - 1;
+                SD_U8(m.cv, x) = (uint8_t)e;
+                s.rv -= e;
+                --s.L;
+            } while (x != t);
+        }
+    }
+}
+
+// save_masked_regions(): sdust.c:88-102.  If the smallest start is below `start`, that ONE slot
+// is saved and every slot below `start` is dropped -- including, when `start` advanced by more
+// than one (it does by two at a flush with l >= W), slots that were never saved.  That loss is
+// reference behaviour and is reproduced here.
+SD_HD void sd_save(sd_state &s, const sd_mem &m, sd_sink &k, int start, int W)
+{
+    if (s.nslot == 0) { s.pstart = start; return; }
+    while (s.pstart < start && !(SD_U32(m.slot, (uint32_t)s.pstart % (uint32_t)W) & SD_SLOT_VALID)) ++s.pstart;
+    if (s.pstart >= start) return;                       // smallest start >= start: nothing to do
+    {
+        const uint32_t v = SD_U32(m.slot, (uint32_t)s.pstart % (uint32_t)W);
+        sd_sink_put(k, s.pstart, s.pstart + sd_slot_flen(v));
+    }
+    while (s.pstart < start) {
+        const uint32_t si = (uint32_t)s.pstart % (uint32_t)W;
+        if (SD_U32(m.slot, si) & SD_SLOT_VALID) {
+            SD_U32(m.slot, si) = 0;
+            if (--s.nslot == 0) { s.pstart = start; return; }
+        }
+        ++s.pstart;
+    }
+}
+
+// flush at a non-ACGT byte or at the end of the sequence: sdust.c:152-154
+//   start = max(l-W+1,0) + (i+1-l);  while (P.n) save_masked_regions(start++)
+SD_HD void sd_flush(sd_state &s, const sd_mem &m, sd_sink &k, int start, int W)
+{
+    while (s.nslot) sd_save(s, m, k, start++, W);
+}
+
+// find_perfect(): sdust.c:104-128 with the slot ring in place of P
+SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W)
+{
+    int r = s.rv, max_r = 0, max_l = 0;
+    const int i0 = s.wn - s.L - 1;
+    // entries whose start lies right of the first candidate also count for the maximum (the
+    // reference's j-loop always starts from the largest start, :113)
+    if (s.nslot)
+        for (int i = s.wn - 1; i > i0; --i) {
+            const uint32_t v = SD_U32(m.slot, (uint32_t)(i + start) % (uint32_t)W);
+            if (v & SD_SLOT_VALID) {
+                const int pr = sd_slot_r(v), pl = sd_slot_l(v);
+                if (max_r == 0 || pr * max_l > max_r * pl) { max_r = pr; max_l = pl; }
+            }
+        }
+    for (int i = i0; i >= 0; --i) {
+        const int t = SD_U8(m.ring, sd_ring_idx(s, i, W));
+        const int c = SD_U8(m.cv, t);
+        r += c;
+        SD_U8(m.cv, t) = (uint8_t)(c + 1);          // temporary; undone below (the reference copies cv)
+        const int new_r = r, new_l = s.wn - i - 1;
+        const uint32_t si = (uint32_t)(i + start) % (uint32_t)W;
+        const uint32_t v = SD_U32(m.slot, si);
+        if (v & SD_SLOT_VALID) {                      // entries with this start join the running maximum
+            const int pr = sd_slot_r(v), pl = sd_slot_l(v);
+            if (max_r == 0 || pr * max_l > max_r * pl) { max_r = pr; max_l = pl; }
+        }
+        if (new_r * 10 > T * new_l) {
+            if (max_r == 0 || new_r * max_l >= max_r * new_l) {
+                max_r = new_r; max_l = new_l;
+                if (!(v & SD_SLOT_VALID)) ++s.nslot;
+                SD_U32(m.slot, si) = sd_slot_pack(new_r, new_l, s.wn + 2 - i);
+            }
+        }
+    }
+    for (int i = i0; i >= 0; --i) {
+        const int t = SD_U8(m.ring, sd_ring_idx(s, i, W));
+        SD_U8(m.cv, t) = (uint8_t)(SD_U8(m.cv, t) - 1);
+    }
+}
+
+// one input position (i == l_seq is the virtual end-of-sequence byte, b = 4).
+// Returns the window start of an emitting step, INT32_MAX after a flush (every slot resolved),
+// or -1 for an A/C/G/T byte that does not complete a triplet.
+SD_HD int sd_step(sd_state &s, const sd_mem &m, sd_sink &k, int i, int b, int T, int W)
+{
+    if (b < 4) {
+        ++s.l;
+        s.t = (s.t << 2 | (unsigned)b) & 63u;
+        if (s.l < 3) return -1;
+        const int start = (s.l - W > 0 ? s.l - W : 0) + (i + 1 - s.l);
+        sd_save(s, m, k, start, W);
+        sd_shift_window(s, m, (int)s.t, T, W);
+        if (s.rw * 10 > s.L * T) sd_find_perfect(s, m, T, start, W);
+        return start;
+    }
+    sd_flush(s, m, k, (s.l - W + 1 > 0 ? s.l - W + 1 : 0) + (i + 1 - s.l), W);
+    s.l = 0; s.t = 0;
+    return 0x7fffffff;
+}
+
+// Where to start so that everything from c0 on is exact (see the header comment).
+// fetch(i) returns byte i of the record.
+template <class Fetch>
+SD_HD int sd_warm_start(Fetch &fetch, int c0, int W)
+{
+    int p = c0 - 2 * W;
+    if (p <= 0) return 0;
+    int need = W, run = 0;
+    // walk left until W triplet-completing positions have been passed: a maximal ACGT run of
+    // length n holds n-2 of them (two more than the W-2 needed, for the run cut at p0)
+    while (p > 0 && need > 0) {
+        --p;
+        if (sd_nt4(fetch(p)) < 4) { if (++run >= 3) --need; }
+        else run = 0;
+    }
+    return p;
+}
+
+// Runs the state machine from the warm start and records the save events that happen while
+// processing positions [c0, c1) of a record of length l_seq (c1 >= l_seq: last chunk, which also
+// owns the reference's final i == l_seq flush).
+template <class Fetch>
+SD_HD void sd_run_chunk(Fetch &fetch, int l_seq, int c0, int c1, int T, int W, const sd_mem &m, sd_sink &k)
+{
+    sd_state s;
+    sd_reset(s, m, W);
+    const int p0 = sd_warm_start(fetch, c0, W);
+    s.pstart = p0;
+    const int stop = c1 < l_seq ? c1 : l_seq;
+    for (int i = p0; i < stop; ++i) {
+        if (i == c0) k.on = 1;
+        sd_step(s, m, k, i, sd_nt4(fetch(i)), T, W);
+    }
+    if (c1 >= l_seq) { k.on = 1; sd_step(s, m, k, l_seq, 4, T, W); }
+    sd_sink_close(k);
+}
+
+// --------------------------------------------------------------------------------------------
+// Seam fold.  Chunk j (k-th chunk of its record, covering positions [k*C, ...)) left its list
+// R_j in slots[j*cap .. j*cap+n[j]).  The record's result is the fold of R_0, R_1, ... with the
+// reference's rule (start <= last.finish: only the finish grows; else append).
+//
+// A save at time i has start in [i-W, i+W) and finish <= i+W.  So (a) the finish of the interval
+// that is `last` when chunk j begins matters only if it is >= c0-W, which is decided by saves in
+// [c0-2W, c0), and (b) those saves fold the same way whatever happened before c0-4W.  Folding
+// the lists of the chunks that start in [c0-4W, c0) from an empty state therefore yields the
+// finish that chunk j's leading intervals are tested against.
+// --------------------------------------------------------------------------------------------
+#define SD_IV_START(x)  ((int)((x) >> 32))
+#define SD_IV_FINISH(x) ((int)(uint32_t)(x))
+
+// finish of the reference's last saved interval when chunk j (k-th of its record) begins; -1 = none that matters
+SD_HD int sd_incoming_finish(const uint64_t *slots, const uint32_t *n, uint32_t cap, uint32_t j, uint32_t k, int C, int W)
+{
+    uint32_t back = (uint32_t)((4 * W + C - 1) / C);
+    if (back > k) back = k;
+    int F = -1;
+    for (uint32_t jj = j - back; jj < j; ++jj)
+        for (uint32_t a = 0; a < n[jj]; ++a) {
+            const uint64_t iv = slots[(uint64_t)jj * cap + a];
+            if (F >= 0 && SD_IV_START(iv) <= F) { if (SD_IV_FINISH(iv) > F) F = SD_IV_FINISH(iv); }
+            else F = SD_IV_FINISH(iv);
+        }
+    return F;
+}
+
+// number of leading intervals of R_j swallowed by the incoming last interval
+SD_HD uint32_t sd_absorbed(const uint64_t *slots, const uint32_t *n, uint32_t cap, uint32_t j, uint32_t k, int C, int W)
+{
+    int F = sd_incoming_finish(slots, n, cap, j, k, C, W);
+    uint32_t a = 0;
+    while (a < n[j] && F >= 0 && SD_IV_START(slots[(uint64_t)j * cap + a]) <= F) {
+        const int f = SD_IV_FINISH(slots[(uint64_t)j * cap + a]);
+        if (f > F) F = f;
+        ++a;
+    }
+    return a;
+}
+
+SD_HD uint32_t sd_gather_count(const uint64_t *slots, const uint32_t *n, uint32_t cap, uint32_t j, uint32_t k, int C, int W)
+{
+    return n[j] - sd_absorbed(slots, n, cap, j, k, C, W);
+}
+
+// writes the intervals chunk j contributes; its last one keeps growing through the following
+// chunks of the record for as long as their leading intervals are swallowed by it.
+SD_HD void sd_gather_write(const uint64_t *slots, const uint32_t *n, uint32_t cap, uint32_t j, uint32_t k,
+                           uint32_t n_chunks_rec, int C, int W, uint64_t *dst)
+{
+    const uint32_t a0 = sd_absorbed(slots, n, cap, j, k, C, W);
+    for (uint32_t a = a0; a < n[j]; ++a) {
+        uint64_t iv = slots[(uint64_t)j * cap + a];
+        if (a == n[j] - 1) {
+            int F = SD_IV_FINISH(iv);
+            int open = 1;
+            for (uint32_t kk = k + 1; open && kk < n_chunks_rec; ++kk) {
+                if (F < (int)kk * C - W) break;                 // nothing later can start at or before F
+                const uint32_t jj = j + (kk - k);
+                for (uint32_t b = 0; b < n[jj]; ++b) {
+                    const uint64_t nx = slots[(uint64_t)jj * cap + b];
+                    if (SD_IV_START(nx) <= F) { if (SD_IV_FINISH(nx) > F) F = SD_IV_FINISH(nx); }
+                    else { open = 0; break; }
+                }
+            }
+            iv = (uint64_t)(uint32_t)SD_IV_START(iv) << 32 | (uint32_t)F;
+        }
+        *dst++ = iv;
+    }
+}

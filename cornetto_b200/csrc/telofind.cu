@@ -1,0 +1,516 @@
+// cornetto_b200/csrc/telofind.cu -- telomere motif scan on the GPU.
+//
+// Replaces disambiguate()+find()+rc(), src/find_telomere.c:24-81: for every record, the maximal
+// tandem runs of the motif (strand 0) and then of its reverse complement (strand 1).
+//
+// Pipeline (all on one stream, no host round trip except two 16-byte readbacks for sizing):
+//   k_telofind_scan      HOT: one pass over the sequence bytes.  A warp owns a 32 KiB tile; each
+//                        lane turns its 32 bytes into two bit planes, a shift-AND chain yields
+//                        candidate occurrence masks for both strands, and the (rare) non-zero
+//                        masks are appended in position order to the tile's candidate list with
+//                        a ballot/popc rank.  At the end of the tile the same warp verifies the
+//                        candidates byte-exactly (lane per candidate chunk) and classifies every
+//                        occurrence as run start (no occurrence m bytes before) and/or run end
+//                        (none m bytes after) by looking at the bytes themselves -- so tiles,
+//                        warps and GPUs never exchange state.
+//   scan (scan.cu)       exclusive prefix of the per-tile start/end counts.
+//   k_telofind_scatter   writes the four ordered position lists (fwd/rev x start/end).
+//   k_telofind_assemble  k-th start pairs with k-th end (per strand); runs are written in the
+//                        reference's print order: per record all strand-0 runs, then strand-1.
+//   Motifs that can overlap themselves (e.g. AAAAAA, TATATA) need the reference's greedy
+//   left-to-right semantics (src/find_telomere.c:49-58): the scan then emits every occurrence
+//   and k_telofind_greedy_* walks them per (record, strand).
+#include "corn_internal.cuh"
+#include "telofind_core.cuh"
+
+namespace {
+
+struct ScanParams {
+    const uint8_t *seq;        // d_seq (position 0 of the batch)
+    uint32_t       n_tiles;
+    uint32_t      *tile_counter;
+    // tile candidate lists, SoA, n_tiles * CORN_TILE_CHUNKS entries each
+    uint32_t *c_idx;           // global chunk index (byte position / 32)
+    uint32_t *c_a, *c_b;       // scan: candidate masks fwd / rev.  after classification: start masks fwd / rev
+    uint32_t *c_c, *c_d;       // after classification: end masks fwd / rev
+    uint4    *tile_cnt;        // per tile: #start_f, #end_f, #start_r, #end_r
+    uint32_t *tile_ncand;
+    const uint8_t *pat;        // device: fwd[256] then rev[256]
+    uint64_t fc, rc;           // packed 2-bit codes (plane matcher)
+    int      m;
+    int      bordered;         // emit every occurrence as a "start", no ends
+};
+
+__device__ __forceinline__ void ld256(const uint8_t *p, uint32_t w[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+}
+
+__device__ __forceinline__ bool occ_dev(const uint8_t *p, const uint8_t *__restrict__ pat, int m)
+{
+    for (int d = 0; d < m; ++d)
+        if (corn_fold(__ldg(p + d)) != __ldg(pat + d)) return false;
+    return true;
+}
+
+// Verify + classify the candidates of one tile.  Called by the warp that scanned the tile.
+__device__ void classify_tile(const ScanParams &P, uint32_t tile, uint32_t cnt, int lane)
+{
+    const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
+    const int m = P.m;
+    uint32_t n_sf = 0, n_ef = 0, n_sr = 0, n_er = 0;
+    for (uint32_t e = lane; e < cnt; e += 32) {
+        const uint32_t idx = __ldcg(P.c_idx + base + e);
+        uint32_t cf = __ldcg(P.c_a + base + e), cr = __ldcg(P.c_b + base + e);
+        const uint8_t *chunk = P.seq + (size_t)idx * CORN_CHUNK_BYTES;
+        uint32_t sf = 0, ef = 0, sr = 0, er = 0;
+        while (cf) {
+            const int b = __ffs(cf) - 1;
+            cf &= cf - 1;
+            const uint8_t *p = chunk + b;
+            if (!occ_dev(p, P.pat, m)) continue;
+            if (P.bordered) { sf |= 1u << b; continue; }
+            if (!occ_dev(p - m, P.pat, m)) sf |= 1u << b;
+            if (!occ_dev(p + m, P.pat, m)) ef |= 1u << b;
+        }
+        while (cr) {
+            const int b = __ffs(cr) - 1;
+            cr &= cr - 1;
+            const uint8_t *p = chunk + b;
+            if (!occ_dev(p, P.pat + 256, m)) continue;
+            if (P.bordered) { sr |= 1u << b; continue; }
+            if (!occ_dev(p - m, P.pat + 256, m)) sr |= 1u << b;
+            if (!occ_dev(p + m, P.pat + 256, m)) er |= 1u << b;
+        }
+        P.c_a[base + e] = sf; P.c_b[base + e] = sr;
+        P.c_c[base + e] = ef; P.c_d[base + e] = er;
+        n_sf += __popc(sf); n_ef += __popc(ef); n_sr += __popc(sr); n_er += __popc(er);
+    }
+    n_sf = corn_warp_sum(n_sf); n_ef = corn_warp_sum(n_ef);
+    n_sr = corn_warp_sum(n_sr); n_er = corn_warp_sum(n_er);
+    if (lane == 0) {
+        P.tile_cnt[tile] = make_uint4(n_sf, n_ef, n_sr, n_er);
+        P.tile_ncand[tile] = cnt;
+    }
+}
+
+// ordered append of the lanes' non-zero masks to the tile list
+__device__ __forceinline__ void push_candidates(const ScanParams &P, size_t base, uint32_t &cnt, uint32_t chunk_idx,
+                                                uint32_t mf, uint32_t mr, int lane)
+{
+    const bool has = (mf | mr) != 0;
+    const uint32_t any = __ballot_sync(0xffffffffu, has);
+    if (any) {
+        if (has) {
+            const uint32_t slot = cnt + __popc(any & corn_lanemask_lt());
+            P.c_idx[base + slot] = chunk_idx;
+            P.c_a[base + slot] = mf;
+            P.c_b[base + slot] = mr;
+        }
+        cnt += __popc(any);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// HOT KERNEL: plane matcher.  M_CT > 0 fixes the motif length at compile time (the default
+// 6-mer); the packed codes stay run-time values in uniform registers.
+// -------------------------------------------------------------------------------------------
+constexpr uint64_t pack_codes(const char *s, int i = 0)
+{
+    return s[i] ? ((uint64_t)(s[i] == 'A' ? 0 : s[i] == 'C' ? 1 : s[i] == 'T' ? 2 : 3) << (2 * i)) | pack_codes(s, i + 1) : 0;
+}
+constexpr uint64_t FC_TTAGGG = pack_codes("TTAGGG"), RC_TTAGGG = pack_codes("CCCTAA");
+
+// M_CT > 0: motif length AND codes (FC_CT/RC_CT) are compile-time, so the class selects fold
+// into the LOP3 truth tables.  M_CT == 0: run-time motif (length P.m, codes P.fc/P.rc).
+template <int M_CT, uint64_t FC_CT, uint64_t RC_CT>
+__global__ void __launch_bounds__(256, 4) k_telofind_scan(const ScanParams P)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= P.n_tiles) break;
+
+        const uint8_t *lane_ptr = P.seq + (size_t)tile * CORN_TILE_BYTES + (size_t)lane * CORN_CHUNK_BYTES;
+        const size_t   base = (size_t)tile * CORN_TILE_CHUNKS;
+        const uint32_t chunk0 = tile * CORN_TILE_CHUNKS + lane;
+        uint32_t cnt = 0;
+
+        uint32_t cur[8], nxt[8];
+        ld256(lane_ptr, cur);
+        ld256(lane_ptr + CORN_ROW_BYTES, nxt);
+        uint32_t pp1, pp2;
+        corn_planes32(cur, pp1, pp2);
+#pragma unroll 1
+        for (uint32_t row = 1; row <= CORN_TILE_ROWS; ++row) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            // prefetch row+1 (the row after the tile's last one is the next tile's first row;
+            // the one after that is still inside the allocation thanks to CORN_TAIL_BYTES)
+            ld256(lane_ptr + (size_t)(row + 1) * CORN_ROW_BYTES, nxt);
+            uint32_t c1, c2;
+            corn_planes32(cur, c1, c2);
+            // lane i needs the planes of the 32 bytes that follow its chunk of row-1:
+            // lane i+1's previous planes, or (lane 31) lane 0's current planes.
+            const uint32_t n1 = __shfl_sync(0xffffffffu, lane == 0 ? c1 : pp1, (lane + 1) & 31);
+            const uint32_t n2 = __shfl_sync(0xffffffffu, lane == 0 ? c2 : pp2, (lane + 1) & 31);
+            uint32_t mf, mr;
+            corn_match32<M_CT>(pp1, pp2, n1, n2, M_CT ? FC_CT : P.fc, M_CT ? RC_CT : P.rc, P.m, mf, mr);
+            push_candidates(P, base, cnt, chunk0 + (row - 1) * 32u, mf, mr, lane);
+            pp1 = c1; pp2 = c2;
+        }
+        __syncwarp();
+        classify_tile(P, tile, cnt, lane);
+        __syncwarp();
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Generic matcher for motifs with characters outside {A,C,G,T} or longer than 32: plain
+// byte compare of every position.  Same tile/candidate machinery, exact masks.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_telofind_scan_generic(const ScanParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int m = P.m;
+    const uint8_t f0 = __ldg(P.pat), r0 = __ldg(P.pat + 256);
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= P.n_tiles) break;
+        const uint8_t *lane_ptr = P.seq + (size_t)tile * CORN_TILE_BYTES + (size_t)lane * CORN_CHUNK_BYTES;
+        const size_t   base = (size_t)tile * CORN_TILE_CHUNKS;
+        const uint32_t chunk0 = tile * CORN_TILE_CHUNKS + lane;
+        uint32_t cnt = 0;
+        for (uint32_t row = 0; row < CORN_TILE_ROWS; ++row) {
+            const uint8_t *p = lane_ptr + (size_t)row * CORN_ROW_BYTES;
+            uint32_t mf = 0, mr = 0;
+            for (int b = 0; b < 32; ++b) {
+                const uint8_t c = corn_fold(__ldg(p + b));
+                if (c == f0 && occ_dev(p + b, P.pat, m)) mf |= 1u << b;
+                if (c == r0 && occ_dev(p + b, P.pat + 256, m)) mr |= 1u << b;
+            }
+            push_candidates(P, base, cnt, chunk0 + row * 32u, mf, mr, lane);
+        }
+        __syncwarp();
+        classify_tile(P, tile, cnt, lane);
+        __syncwarp();
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// ordered position lists.  One warp per tile.
+// -------------------------------------------------------------------------------------------
+struct ScatterParams {
+    const uint32_t *c_idx, *c_a, *c_b, *c_c, *c_d;
+    const uint4    *tile_off;
+    const uint32_t *tile_ncand;
+    uint32_t n_tiles;
+    uint32_t *start_f, *end_f, *start_r, *end_r;   // global byte positions
+    int m;
+};
+
+__device__ __forceinline__ void emit_bits(uint32_t mask, uint32_t *dst, uint32_t pos0)
+{
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        *dst++ = pos0 + b;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_telofind_scatter(const ScatterParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= P.n_tiles) return;
+    const uint32_t cnt = P.tile_ncand[tile];
+    if (cnt == 0) return;
+    uint4 off = P.tile_off[tile];
+    const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
+    for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        uint32_t idx = 0, sf = 0, sr = 0, ef = 0, er = 0;
+        if (e < cnt) {
+            idx = P.c_idx[base + e];
+            sf = P.c_a[base + e]; sr = P.c_b[base + e];
+            ef = P.c_c[base + e]; er = P.c_d[base + e];
+        }
+        const uint32_t pos0 = idx * CORN_CHUNK_BYTES;
+        const uint32_t k_sf = __popc(sf), k_ef = __popc(ef), k_sr = __popc(sr), k_er = __popc(er);
+        const uint32_t i_sf = corn_warp_iscan(k_sf, lane), i_ef = corn_warp_iscan(k_ef, lane);
+        const uint32_t i_sr = corn_warp_iscan(k_sr, lane), i_er = corn_warp_iscan(k_er, lane);
+        emit_bits(sf, P.start_f + off.x + i_sf - k_sf, pos0);
+        emit_bits(ef, P.end_f + off.y + i_ef - k_ef, pos0 + P.m);
+        emit_bits(sr, P.start_r + off.z + i_sr - k_sr, pos0);
+        emit_bits(er, P.end_r + off.w + i_er - k_er, pos0 + P.m);
+        off.x += __shfl_sync(0xffffffffu, i_sf, 31);
+        off.y += __shfl_sync(0xffffffffu, i_ef, 31);
+        off.z += __shfl_sync(0xffffffffu, i_sr, 31);
+        off.w += __shfl_sync(0xffffffffu, i_er, 31);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// run assembly, border-free motifs.  Thread k < n_f handles forward run k, thread n_f + k reverse
+// run k.  Output slot: the reference prints, per record, all strand-0 runs then all strand-1
+// runs (src/find_telomere.c:49-72), so
+//   fwd run k of record r  ->  k + #rev runs in records < r
+//   rev run k of record r  ->  k + #fwd runs in records <= r
+// -------------------------------------------------------------------------------------------
+struct AssembleParams {
+    const uint32_t *start_f, *end_f, *start_r, *end_r;
+    uint32_t n_f, n_r;
+    const uint32_t *rec_off;   // [n_rec+1]
+    uint32_t n_rec;
+    corn_run_t *out;
+    uint32_t *err;
+};
+
+__global__ void __launch_bounds__(256) k_telofind_assemble(const AssembleParams P)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n_f + P.n_r) return;
+    const bool rev = t >= P.n_f;
+    const uint32_t k = rev ? t - P.n_f : t;
+    const uint32_t s = rev ? P.start_r[k] : P.start_f[k];
+    const uint32_t e = rev ? P.end_r[k] : P.end_f[k];
+    const uint32_t rec = corn_upper_bound(P.rec_off, P.n_rec, s) - 1;   // rec_off[rec] <= s
+    const uint32_t r0 = P.rec_off[rec];
+    uint32_t slot;
+    if (!rev) slot = k + corn_lower_bound(P.start_r, P.n_r, r0);
+    else      slot = k + corn_lower_bound(P.start_f, P.n_f, P.rec_off[rec + 1]);
+    if (e <= s || e > P.rec_off[rec + 1]) atomicAdd(P.err, 1u);       // would mean a start/end mismatch
+    corn_run_t r;
+    r.rec = rec; r.strand = rev ? 1u : 0u; r.start = s - r0; r.end = e - r0;
+    P.out[slot] = r;
+}
+
+// -------------------------------------------------------------------------------------------
+// greedy run assembly for self-overlapping motifs: thread per (record, strand), two passes
+// (count, then write at the scanned offset).  occ lists hold EVERY occurrence, ascending.
+//   pos = 0; loop: p = first occurrence >= pos; q = p; while occurrence at q: q += m;
+//   emit [p,q); pos = q + 1            (src/find_telomere.c:49-58)
+// -------------------------------------------------------------------------------------------
+struct GreedyParams {
+    const uint32_t *occ_f, *occ_r;
+    uint32_t n_f, n_r;
+    const uint32_t *rec_off;
+    uint32_t n_rec;
+    int m;
+    uint32_t *cnt;          // [2*n_rec]  order: rec0 fwd, rec0 rev, rec1 fwd, ...
+    const uint32_t *off;    // exclusive scan of cnt
+    corn_run_t *out;        // NULL in the counting pass
+};
+
+__global__ void __launch_bounds__(128) k_telofind_greedy(const GreedyParams P)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2u * P.n_rec) return;
+    const uint32_t rec = t >> 1, strand = t & 1u;
+    const uint32_t *occ = strand ? P.occ_r : P.occ_f;
+    const uint32_t n = strand ? P.n_r : P.n_f;
+    const uint32_t r0 = P.rec_off[rec], r1 = P.rec_off[rec + 1];
+    uint32_t i = corn_lower_bound(occ, n, r0);
+    const uint32_t hi = corn_lower_bound(occ, n, r1);
+    uint32_t k = 0;
+    corn_run_t *out = P.out ? P.out + P.off[t] : NULL;
+    while (i < hi) {
+        const uint32_t p = occ[i];
+        uint32_t q = p + P.m;
+        uint32_t j = i + 1;
+        // extend while there is an occurrence exactly at q
+        for (;;) {
+            while (j < hi && occ[j] < q) ++j;
+            if (j < hi && occ[j] == q) { q += P.m; ++j; } else break;
+        }
+        if (out) { corn_run_t r; r.rec = rec; r.strand = strand; r.start = p - r0; r.end = q - r0; out[k] = r; }
+        ++k;
+        // resume at q + 1 (an occurrence at q is impossible here)
+        i = j;
+        while (i < hi && occ[i] <= q) ++i;
+    }
+    if (!P.out) P.cnt[t] = k;
+}
+
+__global__ void k_reset_counter(uint32_t *p, int n) { if ((int)threadIdx.x < n) p[threadIdx.x] = 0; }
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif, corn_hits_t *out)
+{
+    if (!motif || !motif[0]) return corn_set_err(ctx, CORN_E_ARG, "empty motif");
+    if (strlen(motif) > 255) return corn_set_err(ctx, CORN_E_ARG, "motif longer than 255");
+    CORN_CUDA(ctx, cudaSetDevice(ctx->device));
+    corn_motif_info mi;
+    corn_analyse_motif(motif, &mi);
+    cudaStream_t st = ctx->stream;
+    const float keep_h2d = ctx->timing.h2d_ms;
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    ctx->timing.h2d_ms = keep_h2d;
+
+    const uint32_t n_tiles = (uint32_t)((db->total_bytes + CORN_TILE_BYTES - 1) / CORN_TILE_BYTES);
+    const size_t n_slots = (size_t)n_tiles * CORN_TILE_CHUNKS;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->cand, 5 * n_slots * sizeof(uint32_t) + 256));
+    // tile_tab: counts (uint4) | offsets (uint4) | ncand (u32) ; misc: totals uint4, counter, err, pattern
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->tile_tab, (size_t)n_tiles * (2 * sizeof(uint4) + sizeof(uint32_t)) + 256));
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->misc, 4096));
+
+    uint32_t *cand = (uint32_t *)ctx->cand.p;
+    ScanParams sp;
+    sp.seq = db->d_seq;
+    sp.n_tiles = n_tiles;
+    sp.c_idx = cand; sp.c_a = cand + n_slots; sp.c_b = cand + 2 * n_slots; sp.c_c = cand + 3 * n_slots; sp.c_d = cand + 4 * n_slots;
+    sp.tile_cnt = (uint4 *)ctx->tile_tab.p;
+    uint4 *tile_off = sp.tile_cnt + n_tiles;
+    sp.tile_ncand = (uint32_t *)(tile_off + n_tiles);
+    uint8_t *misc = (uint8_t *)ctx->misc.p;
+    uint4 *d_totals = (uint4 *)misc;                    // 16 B
+    sp.tile_counter = (uint32_t *)(misc + 16);          // [0] tile counter, [1] error counter
+    uint32_t *d_err = sp.tile_counter + 1;
+    uint8_t *d_pat = misc + 64;                         // 512 B
+    sp.pat = d_pat;
+    sp.fc = mi.fc; sp.rc = mi.rc; sp.m = mi.m; sp.bordered = mi.bordered;
+
+    // pattern upload (pageable -> staged by the runtime; 512 bytes)
+    uint8_t hpat[512];
+    memset(hpat, 0, sizeof hpat);
+    memcpy(hpat, mi.fwd, mi.m); memcpy(hpat + 256, mi.rev, mi.m);
+    memcpy(ctx->h_pinned_small, hpat, 512);
+    CORN_CUDA(ctx, cudaMemcpyAsync(d_pat, ctx->h_pinned_small, 512, cudaMemcpyHostToDevice, st));
+    k_reset_counter<<<1, 32, 0, st>>>(sp.tile_counter, 2);
+    corn_count_launch(ctx);
+
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    if (n_tiles) {
+        // persistent grid: 4 CTAs of 8 warps per SM
+        const int grid = ctx->sm_count * 4;
+        if (mi.acgt && mi.m <= CORN_MAX_FAST_MOTIF) {
+            if (mi.m == 6 && mi.fc == FC_TTAGGG && mi.rc == RC_TTAGGG)
+                k_telofind_scan<6, FC_TTAGGG, RC_TTAGGG><<<grid, 256, 0, st>>>(sp);
+            else
+                k_telofind_scan<0, 0, 0><<<grid, 256, 0, st>>>(sp);
+        } else {
+            k_telofind_scan_generic<<<grid, 256, 0, st>>>(sp);
+        }
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+    }
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+
+    CORN_TRY(corn_scan_u32x4(ctx, sp.tile_cnt, tile_off, n_tiles, d_totals));
+    uint32_t tot[4];
+    CORN_TRY(corn_read_small(ctx, tot, d_totals, 16));
+    const uint32_t n_sf = tot[0], n_ef = tot[1], n_sr = tot[2], n_er = tot[3];
+    if (!mi.bordered && (n_sf != n_ef || n_sr != n_er))
+        return corn_set_err(ctx, CORN_E_INTERNAL, "start/end counts differ: %u/%u %u/%u", n_sf, n_ef, n_sr, n_er);
+
+    const size_t n_ev = (size_t)n_sf + n_ef + n_sr + n_er;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, (n_ev + 4) * sizeof(uint32_t)));
+    uint32_t *ev = (uint32_t *)ctx->events.p;
+    ScatterParams sc;
+    sc.c_idx = sp.c_idx; sc.c_a = sp.c_a; sc.c_b = sp.c_b; sc.c_c = sp.c_c; sc.c_d = sp.c_d;
+    sc.tile_off = tile_off; sc.tile_ncand = sp.tile_ncand; sc.n_tiles = n_tiles;
+    sc.start_f = ev; sc.end_f = ev + n_sf; sc.start_r = sc.end_f + n_ef; sc.end_r = sc.start_r + n_sr;
+    sc.m = mi.m;
+    if (n_tiles && n_ev) {
+        k_telofind_scatter<<<(n_tiles + 7) / 8, 256, 0, st>>>(sc);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+    }
+
+    uint64_t n_run = 0;
+    if (!mi.bordered) {
+        n_run = (uint64_t)n_sf + n_sr;
+        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->runs, (n_run + 1) * sizeof(corn_run_t)));
+        if (n_run) {
+            AssembleParams ap;
+            ap.start_f = sc.start_f; ap.end_f = sc.end_f; ap.start_r = sc.start_r; ap.end_r = sc.end_r;
+            ap.n_f = n_sf; ap.n_r = n_sr; ap.rec_off = db->d_rec_off; ap.n_rec = db->n_rec;
+            ap.out = (corn_run_t *)ctx->runs.p; ap.err = d_err;
+            k_telofind_assemble<<<(unsigned)((n_run + 255) / 256), 256, 0, st>>>(ap);
+            corn_count_launch(ctx);
+            CORN_LAUNCH_CHECK(ctx);
+        }
+    } else if (db->n_rec) {
+        const size_t n2 = 2 * (size_t)db->n_rec;
+        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (2 * n2 + 8) * sizeof(uint32_t)));   // borrowed as a temporary
+        GreedyParams gp;
+        gp.occ_f = sc.start_f; gp.occ_r = sc.start_r; gp.n_f = n_sf; gp.n_r = n_sr;
+        gp.rec_off = db->d_rec_off; gp.n_rec = db->n_rec; gp.m = mi.m;
+        gp.cnt = (uint32_t *)ctx->bins.p; uint32_t *goff = gp.cnt + n2; gp.off = goff; gp.out = NULL;
+        k_telofind_greedy<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>(gp);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+        uint32_t *d_tot = (uint32_t *)d_totals;
+        CORN_TRY(corn_scan_u32(ctx, gp.cnt, goff, n2, d_tot));
+        uint32_t t32 = 0;
+        CORN_TRY(corn_read_small(ctx, &t32, d_tot, 4));
+        n_run = t32;
+        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->runs, (n_run + 1) * sizeof(corn_run_t)));
+        gp.out = (corn_run_t *)ctx->runs.p;
+        k_telofind_greedy<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>(gp);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+    }
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+
+    ctx->last_db = db;
+    ctx->last_n_run = n_run;
+    ctx->last_runs_disjoint = !mi.bordered && !mi.strands_overlap;
+    ctx->last_motif_len = mi.m;
+    ctx->timing.out_bytes = n_run * sizeof(corn_run_t);
+
+    if (out) {
+        out->run = NULL; out->n_run = n_run; out->_owner = NULL;
+        if (n_run) {
+            out->run = (corn_run_t *)corn_host_alloc(n_run * sizeof(corn_run_t));
+            if (!out->run) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc of %llu runs", (unsigned long long)n_run);
+            out->_owner = out->run;
+            CORN_CUDA(ctx, cudaMemcpyAsync(out->run, ctx->runs.p, n_run * sizeof(corn_run_t), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    CORN_CUDA(ctx, cudaStreamSynchronize(st));
+    uint32_t herr = 0;
+    CORN_TRY(corn_read_small(ctx, &herr, d_err, 4));
+    if (herr) return corn_set_err(ctx, CORN_E_INTERNAL, "%u runs failed the start/end consistency check", herr);
+    float all_ms = 0;
+    cudaEventElapsedTime(&ctx->timing.scan_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&all_ms, ctx->ev[3], ctx->ev[4]);
+    ctx->timing.post_ms = all_ms;
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[4], ctx->ev[5]);
+    return CORN_OK;
+}
+
+extern "C" int corn_gpu_telofind_dev(corn_ctx_t *ctx, const corn_dbatch_t *db, const char *motif, corn_hits_t *out)
+{
+    if (!ctx || !db) return CORN_E_ARG;
+    return telofind_run(ctx, db, motif, out);
+}
+
+extern "C" int corn_gpu_telofind(corn_ctx_t *ctx, const corn_batch_t *batch, const char *motif, corn_hits_t *out)
+{
+    if (!ctx || !batch || !out) return CORN_E_ARG;
+    corn_dbatch_t *db = NULL;
+    CORN_TRY(corn_gpu_upload(ctx, batch, &db));
+    const float h2d = ctx->timing.h2d_ms;
+    corn_ctx_adopt(ctx, db);   // stays resident for a fused corn_gpu_telowin(hits == NULL)
+    ctx->timing.h2d_ms = h2d;
+    return telofind_run(ctx, db, motif, out);
+}
+
+extern "C" void corn_gpu_hits_free(corn_hits_t *hits)
+{
+    if (!hits) return;
+    corn_host_free(hits->_owner);
+    hits->run = NULL; hits->n_run = 0; hits->_owner = NULL;
+}

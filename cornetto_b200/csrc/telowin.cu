@@ -1,0 +1,301 @@
+// cornetto_b200/csrc/telowin.cu -- windowed telomere density on the GPU.
+//
+// Replaces the paint loop and process_scaffold() of src/telomere_windows.c:28-43,75-79.
+// The reference paints one byte per base and re-reads 1000 bytes for each 200-bp step; here
+// the marked bases are counted once per 200-bp bin (a byte per bin, <= 200), a window is the
+// sum of five consecutive bins, and the double-precision test
+//        (double)car / den >= threshold_adj                       (src/telomere_windows.c:37)
+// is evaluated with the same IEEE division on the device.
+//
+// Two ways to fill the bins:
+//   disjoint runs  (runs left on the device by telofind for a border-free motif whose strands
+//                   cannot overlap): every run adds its overlap with each bin it touches;
+//   general        (runs given by the caller, any order, overlaps allowed -- the text-driven
+//                   `cornetto telowin` path): paint a 1-bit-per-base map with atomicOr (union
+//                   semantics, exactly the reference's byte map), then popcount per bin.
+#include "corn_internal.cuh"
+
+namespace {
+
+// per-record tables: bin_base[r] = first bin of record r in the bin array (each record owns
+// nbins(r) + 4 zero bins so a window can always read five), n_win[r] = number of windows the
+// reference evaluates: i = 0,200,... until i + 1000 >= len  (src/telomere_windows.c:31,40-41).
+struct WinTables {
+    const uint32_t *rec_len;
+    uint32_t       *bin_base;   // [n_rec+1]
+    uint32_t        n_rec;
+};
+
+__host__ __device__ inline uint32_t nbins_of(uint32_t len) { return (len + 199u) / 200u + 4u; }
+__host__ __device__ inline uint32_t nwin_of(uint32_t len)
+{
+    if (len == 0) return 0;                       // den == 0 -> NaN compare, never printed
+    if (len <= 1000) return 1;
+    return (len - 1000u + 199u) / 200u + 1u;      // last i is the first multiple of 200 with i+1000 >= len
+}
+
+__global__ void k_bin_counts(const uint32_t *__restrict__ rec_len, uint32_t *__restrict__ nb, uint32_t n_rec)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rec) nb[r] = nbins_of(rec_len[r]);
+}
+
+__device__ __forceinline__ void bin_add(uint8_t *bins, uint32_t bin, uint32_t amount)
+{
+    // bins are bytes; total per bin <= 200, so adding into the containing word never carries
+    uint32_t *w = (uint32_t *)(bins + (bin & ~3u));
+    atomicAdd(w, amount << (8u * (bin & 3u)));
+}
+
+// disjoint runs -> bins.  One thread per run.
+__global__ void __launch_bounds__(256) k_bins_from_runs(const corn_run_t *__restrict__ runs, uint64_t n_run,
+                                                        const uint32_t *__restrict__ bin_base, uint8_t *bins)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_run) return;
+    const corn_run_t r = runs[t];
+    const uint32_t b0 = bin_base[r.rec];
+    uint32_t s = r.start;
+    while (s < r.end) {
+        const uint32_t bin = s / 200u;
+        const uint32_t lim = min(r.end, (bin + 1u) * 200u);
+        bin_add(bins, b0 + bin, lim - s);
+        s = lim;
+    }
+}
+
+// general path: paint bits.  bit_base[r] = first bit (multiple of 32) of record r.  One warp per run.
+__global__ void __launch_bounds__(256) k_paint_runs(const corn_run_t *__restrict__ runs, uint64_t n_run,
+                                                    const uint32_t *__restrict__ rec_len,
+                                                    const uint64_t *__restrict__ bit_base, uint32_t n_rec, uint32_t *bitmap)
+{
+    const uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= n_run) return;
+    const corn_run_t r = runs[wid];
+    if (r.rec >= n_rec) return;
+    const uint32_t len = rec_len[r.rec];
+    const uint32_t s = r.start, e = min(r.end, len);     // the reference would write out of bounds past len
+    if (s >= e) return;
+    uint32_t *bm = bitmap + (bit_base[r.rec] >> 5);
+    const uint32_t w0 = s >> 5, w1 = (e - 1) >> 5;
+    for (uint32_t w = w0 + lane; w <= w1; w += 32) {
+        uint32_t m = 0xffffffffu;
+        if (w == w0) m &= 0xffffffffu << (s & 31);
+        if (w == w1) m &= 0xffffffffu >> (31 - ((e - 1) & 31));
+        atomicOr(bm + w, m);
+    }
+}
+
+// bitmap -> bins.  One thread per bin (pad bins stay 0).
+__global__ void __launch_bounds__(256) k_bins_from_bitmap(const uint32_t *__restrict__ bitmap, const uint64_t *__restrict__ bit_base,
+                                                          const uint32_t *__restrict__ bin_base, const uint32_t *__restrict__ rec_len,
+                                                          uint32_t n_rec, uint32_t n_bins_total, uint8_t *bins)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_bins_total) return;
+    const uint32_t rec = corn_upper_bound(bin_base, n_rec, g) - 1;
+    const uint32_t k = g - bin_base[rec];
+    const uint32_t len = rec_len[rec];
+    const uint32_t s = k * 200u;
+    if (s >= len) { bins[g] = 0; return; }
+    const uint32_t e = min(len, s + 200u);
+    const uint32_t *bm = bitmap + (bit_base[rec] >> 5);
+    uint32_t cnt = 0;
+    for (uint32_t w = s >> 5; w <= (e - 1) >> 5; ++w) {
+        uint32_t m = 0xffffffffu;
+        if (w == (s >> 5)) m &= 0xffffffffu << (s & 31);
+        if (w == ((e - 1) >> 5)) m &= 0xffffffffu >> (31 - ((e - 1) & 31));
+        cnt += __popc(__ldg(bm + w) & m);
+    }
+    bins[g] = (uint8_t)cnt;
+}
+
+// windows.  One thread per bin index g; bin k of record r is window i = 200k when k < n_win(r).
+// Pass 1 (out == NULL) counts passing windows per block; pass 2 writes them at the scanned offset
+// in ascending (record, i) order.
+__global__ void __launch_bounds__(256) k_windows(const uint8_t *__restrict__ bins, const uint32_t *__restrict__ bin_base,
+                                                 const uint32_t *__restrict__ rec_len, uint32_t n_rec, uint32_t n_bins_total,
+                                                 double thr, uint32_t *blk_cnt, const uint32_t *blk_off, corn_window_t *out)
+{
+    __shared__ uint32_t warp_cnt[8];
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool pass = false;
+    corn_window_t w;
+    w.rec = w.start = w.end = w.car = 0;
+    if (g < n_bins_total) {
+        const uint32_t rec = corn_upper_bound(bin_base, n_rec, g) - 1;
+        const uint32_t k = g - bin_base[rec];
+        const uint32_t len = rec_len[rec];
+        if (k < nwin_of(len)) {
+            const uint8_t *b = bins + g;
+            const uint32_t car = (uint32_t)b[0] + b[1] + b[2] + b[3] + b[4];
+            const uint32_t i = k * 200u;
+            const uint32_t den = (i + 1000u < len) ? 1000u : len - i;
+            pass = ((double)car / (double)den) >= thr;
+            w.rec = rec; w.start = i; w.end = i + den; w.car = car;
+        }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    if (!out) {
+        if (threadIdx.x == 0) {
+            uint32_t s = 0;
+            for (int i = 0; i < 8; ++i) s += warp_cnt[i];
+            blk_cnt[blockIdx.x] = s;
+        }
+        return;
+    }
+    if (pass) {
+        uint32_t off = blk_off[blockIdx.x];
+        for (int i = 0; i < warp; ++i) off += warp_cnt[i];
+        out[off + __popc(bal & corn_lanemask_lt())] = w;
+    }
+}
+
+__global__ void k_bit_bases(const uint32_t *__restrict__ rec_len, uint32_t *__restrict__ words, uint32_t n_rec)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rec) words[r] = (rec_len[r] + 31u) / 32u + 1u;   // 32-bit words per record
+}
+
+__global__ void k_words_to_bits(const uint32_t *__restrict__ word_base, uint64_t *__restrict__ bit_base, uint32_t n)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) bit_base[r] = (uint64_t)word_base[r] * 32u;
+}
+
+}  // namespace
+
+extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const corn_contigs_t *contigs,
+                                double thr, corn_windows_t *out)
+{
+    if (!ctx || !out) return CORN_E_ARG;
+    CORN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    out->win = NULL; out->n_win = 0; out->_owner = NULL;
+
+    // ---- record lengths on the device --------------------------------------------------------
+    uint32_t n_rec = 0;
+    const uint32_t *d_len = NULL;
+    uint64_t n_run = 0;
+    const corn_run_t *d_runs = NULL;
+    int disjoint = 0;
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    if (!hits) {
+        if (!ctx->last_db) return corn_set_err(ctx, CORN_E_STATE, "telowin(hits == NULL) needs a preceding telofind on this context");
+        if (contigs && contigs->n != ctx->last_db->n_rec) return corn_set_err(ctx, CORN_E_ARG, "contigs->n != records of the last telofind");
+        n_rec = ctx->last_db->n_rec;
+        d_len = ctx->last_db->d_rec_len;
+        n_run = ctx->last_n_run;
+        d_runs = (const corn_run_t *)ctx->runs.p;
+        disjoint = ctx->last_runs_disjoint;
+    } else {
+        if (!contigs || (contigs->n && !contigs->length) || (hits->n_run && !hits->run)) return CORN_E_ARG;
+        n_rec = contigs->n;
+        n_run = hits->n_run;
+        const size_t need = sizeof(uint32_t) * ((size_t)n_rec + 1) + sizeof(corn_run_t) * (n_run + 1) + 64;
+        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_tab, need));     // borrowed for the uploads
+        uint32_t *dl = (uint32_t *)ctx->sd_tab.p;
+        corn_run_t *dr = (corn_run_t *)((uint8_t *)ctx->sd_tab.p + ((sizeof(uint32_t) * ((size_t)n_rec + 1) + 15) & ~(size_t)15));
+        if (n_rec) CORN_CUDA(ctx, cudaMemcpyAsync(dl, contigs->length, sizeof(uint32_t) * n_rec, cudaMemcpyHostToDevice, st));
+        if (n_run) CORN_CUDA(ctx, cudaMemcpyAsync(dr, hits->run, sizeof(corn_run_t) * n_run, cudaMemcpyHostToDevice, st));
+        d_len = dl; d_runs = dr;
+        disjoint = 0;
+    }
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    if (n_rec == 0) { CORN_CUDA(ctx, cudaStreamSynchronize(st)); return CORN_OK; }
+
+    // ---- tables ---------------------------------------------------------------------------------
+    // misc: [0..16) totals ; tile_tab is free after telofind's scatter: reuse for per-record tables
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->misc, 4096));
+    uint32_t *d_tot = (uint32_t *)((uint8_t *)ctx->misc.p + 1024);
+    const size_t tab_bytes = ((size_t)n_rec + 2) * (2 * sizeof(uint32_t) + sizeof(uint64_t) + sizeof(uint32_t)) + 256;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->wins, tab_bytes));   // head of `wins` holds the tables until the output is sized
+    // (the output itself is written into ctx->bitmap's sibling buffer below)
+    uint32_t *nb = (uint32_t *)ctx->wins.p;              // [n_rec]   bins per record
+    uint32_t *bin_base = nb + (n_rec + 1);               // [n_rec+1]
+    const unsigned gr = (n_rec + 255) / 256;
+    k_bin_counts<<<gr, 256, 0, st>>>(d_len, nb, n_rec);
+    corn_count_launch(ctx);
+    CORN_TRY(corn_scan_u32(ctx, nb, bin_base, n_rec, d_tot));
+    uint32_t n_bins_total = 0;
+    CORN_TRY(corn_read_small(ctx, &n_bins_total, d_tot, 4));
+    // bin_base[n_rec] = total, so upper_bound over n_rec entries is enough; keep the total on the host
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (size_t)n_bins_total + 64));
+    uint8_t *bins = (uint8_t *)ctx->bins.p;
+
+    if (disjoint) {
+        CORN_CUDA(ctx, cudaMemsetAsync(bins, 0, (size_t)n_bins_total + 8, st));
+        if (n_run) {
+            k_bins_from_runs<<<(unsigned)((n_run + 255) / 256), 256, 0, st>>>(d_runs, n_run, bin_base, bins);
+            corn_count_launch(ctx);
+            CORN_LAUNCH_CHECK(ctx);
+        }
+    } else {
+        // 1 bit per base, records word aligned
+        uint32_t *words = bin_base + (n_rec + 1);                         // [n_rec] then scanned in place
+        uint64_t *bit_base = (uint64_t *)(((uintptr_t)(words + n_rec + 1) + 7) & ~(uintptr_t)7);
+        k_bit_bases<<<gr, 256, 0, st>>>(d_len, words, n_rec);
+        corn_count_launch(ctx);
+        CORN_TRY(corn_scan_u32(ctx, words, words, n_rec, d_tot + 1));
+        uint32_t n_words = 0;
+        CORN_TRY(corn_read_small(ctx, &n_words, d_tot + 1, 4));
+        k_words_to_bits<<<gr, 256, 0, st>>>(words, bit_base, n_rec);
+        corn_count_launch(ctx);
+        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bitmap, ((size_t)n_words + 2) * sizeof(uint32_t)));
+        CORN_CUDA(ctx, cudaMemsetAsync(ctx->bitmap.p, 0, ((size_t)n_words + 2) * sizeof(uint32_t), st));
+        if (n_run) {
+            const uint64_t threads = n_run * 32;
+            k_paint_runs<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_runs, n_run, d_len, bit_base, n_rec, (uint32_t *)ctx->bitmap.p);
+            corn_count_launch(ctx);
+            CORN_LAUNCH_CHECK(ctx);
+        }
+        k_bins_from_bitmap<<<(n_bins_total + 255) / 256, 256, 0, st>>>((const uint32_t *)ctx->bitmap.p, bit_base, bin_base, d_len, n_rec, n_bins_total, bins);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+    }
+
+    // ---- windows: count, scan, write -----------------------------------------------------------
+    const uint32_t n_blk = (n_bins_total + 255) / 256;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->tile_tab, ((size_t)n_blk + 1) * 2 * sizeof(uint32_t) + 64));
+    uint32_t *blk_cnt = (uint32_t *)ctx->tile_tab.p, *blk_off = blk_cnt + n_blk + 1;
+    k_windows<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, blk_cnt, NULL, NULL);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    CORN_TRY(corn_scan_u32(ctx, blk_cnt, blk_off, n_blk, d_tot + 2));
+    uint32_t n_win = 0;
+    CORN_TRY(corn_read_small(ctx, &n_win, d_tot + 2, 4));
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, ((size_t)n_win + 1) * sizeof(corn_window_t)));   // events list is dead by now
+    corn_window_t *d_out = (corn_window_t *)ctx->events.p;
+    if (n_win) {
+        k_windows<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, blk_cnt, blk_off, d_out);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+    }
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    out->n_win = n_win;
+    if (n_win) {
+        out->win = (corn_window_t *)corn_host_alloc((size_t)n_win * sizeof(corn_window_t));
+        if (!out->win) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc of %u windows", n_win);
+        out->_owner = out->win;
+        CORN_CUDA(ctx, cudaMemcpyAsync(out->win, d_out, (size_t)n_win * sizeof(corn_window_t), cudaMemcpyDeviceToHost, st));
+    }
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    CORN_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.post_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    ctx->timing.out_bytes = (uint64_t)n_win * sizeof(corn_window_t);
+    return CORN_OK;
+}
+
+extern "C" void corn_gpu_windows_free(corn_windows_t *w)
+{
+    if (!w) return;
+    corn_host_free(w->_owner);
+    w->win = NULL; w->n_win = 0; w->_owner = NULL;
+}

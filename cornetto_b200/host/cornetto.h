@@ -1,0 +1,87 @@
+/* cornetto_b200/host/cornetto.h -- shared declarations of the drop-in `cornetto` host program.
+ *
+ * The host side keeps the reference's operator interface for the hot path: the same four
+ * `int xxx_main(int argc, char *argv[])` entry points (src/main.c:45-48,111-122), the same
+ * arguments, stdout text, stderr messages and exit codes -- with the inner loops replaced by
+ * calls into the CUDA library (include/corn_gpu.h). */
+#ifndef CORNETTO_HOST_H
+#define CORNETTO_HOST_H
+
+#include <errno.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "corn_gpu.h"
+
+#define CORNETTO_VERSION "0.2.0"
+
+/* message style of the reference (src/error.h:54-119) */
+#define CORN_ERROR(msg, ...) \
+    fprintf(stderr, "[%s::ERROR]\033[1;31m " msg "\033[0m At %s:%d\n", __func__, __VA_ARGS__, __FILE__, __LINE__ - 1)
+#define CORN_F_CHK(ret, file) \
+    do { if ((ret) == NULL) { CORN_ERROR("Could not to open file %s: %s", file, strerror(errno)); exit(EXIT_FAILURE); } } while (0)
+#define CORN_MALLOC_CHK(ret) \
+    do { if ((ret) == NULL) { CORN_ERROR("Failed to allocate memory: %s", strerror(errno)); exit(EXIT_FAILURE); } } while (0)
+
+int find_telomere_main(int argc, char *argv[]);
+int telomere_windows_main(int argc, char *argv[]);
+int telomere_breaks_main(int argc, char *argv[]);
+int sdust_main(int argc, char *argv[]);
+int assbed_main(int argc, char *argv[]);
+
+/* misc.c */
+double realtime(void);
+double cputime(void);
+long   peakrss(void);
+
+/* GPU context shared by the sub-commands: created on first use; exits with the reference's
+ * ERROR style when no device is usable (there is no CPU fallback). */
+corn_ctx_t *cornetto_gpu(void);
+void        cornetto_gpu_release(void);
+/* prints the library error and exits */
+void        cornetto_gpu_die(const char *what, int status);
+
+/* ---- FASTA/FASTQ reader with kseq_read() semantics (src/kseq.h:184-224) -------------------- */
+typedef struct fastx fastx_t;
+fastx_t *fastx_open(const char *path);        /* "-" = stdin; plain or gzip; NULL if it cannot be opened */
+void     fastx_close(fastx_t *fx);
+/* Advances to the next record header.  1 = a record begins (fastx_name() valid), 0 = end of input. */
+int      fastx_next(fastx_t *fx);
+const char *fastx_name(const fastx_t *fx);
+/* Appends sequence bytes of the current record to dst (at most cap).  Returns the number of
+ * bytes written; *done becomes 1 once the sequence part of the record is complete. */
+size_t   fastx_seq(fastx_t *fx, uint8_t *dst, size_t cap, int *done);
+/* After the sequence is complete: consumes a FASTQ quality block if there is one.
+ * 0 = record valid; -2 = truncated/mismatching quality (the reference stops reading there). */
+int      fastx_finish(fastx_t *fx);
+
+/* ---- record batches: names + pinned sequence bytes in the CORN_ALIGN layout ------------------ */
+typedef struct {
+    corn_hbatch_t *hb;
+    char   **name;        /* [n] strdup'ed */
+    uint32_t n, max_rec;
+    int      eof;         /* input exhausted (or stopped at a malformed FASTQ record) */
+} rec_batch_t;
+
+rec_batch_t *rec_batch_create(uint64_t capacity_bytes, uint32_t max_rec);
+void         rec_batch_destroy(rec_batch_t *b);
+/* Fills the batch with as many whole records as fit.  A record that does not fit into an EMPTY
+ * batch makes the batch grow.  Returns the number of records now in the batch. */
+uint32_t     rec_batch_fill(rec_batch_t *b, fastx_t *fx);
+
+/* ---- buffered text output ------------------------------------------------------------------- */
+typedef struct { char *buf; size_t n, cap; FILE *fp; } outbuf_t;
+void outbuf_init(outbuf_t *o, FILE *fp);
+void outbuf_flush(outbuf_t *o);
+void outbuf_free(outbuf_t *o);
+void outbuf_str(outbuf_t *o, const char *s, size_t len);
+void outbuf_u64(outbuf_t *o, uint64_t v);
+void outbuf_i32(outbuf_t *o, int32_t v);
+void outbuf_chr(outbuf_t *o, char c);
+
+/* ---- khash iteration order (src/khash.h:230-348,395-400), for telobreaks' output order -------- */
+size_t khash_str_order(const char *const *names, size_t n, size_t *order);
+
+#endif

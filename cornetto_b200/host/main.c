@@ -1,0 +1,52 @@
+/* cornetto_b200/host/main.c -- command dispatcher of the drop-in binary.
+ *
+ * Same behaviour as the reference's main() (src/main.c:95-152) for the hot-path commands:
+ * dispatch on argv[1], --version / --help, and the Version / CMD / time / RSS footer on stderr.
+ * Commands outside the sequence-scan path are not part of this build (scope). */
+#include "cornetto.h"
+
+static int print_usage(FILE *fp)
+{
+    fprintf(fp, "Usage: cornetto <command> [options]\n\n");
+    fprintf(fp, "commands (B200 build: the sequence-scan path):\n");
+    fprintf(fp, "   telo:\n");
+    fprintf(fp, "       telowin         analyse telomere windows in a fasta file\n");
+    fprintf(fp, "       telobreaks      find telomere breaks in a fasta file\n");
+    fprintf(fp, "       telofind        find telomere sequences in a fasta file\n");
+    fprintf(fp, "       sdust           symmetric DUST (https://github.com/lh3/sdust)\n");
+    fprintf(fp, "   misc:\n");
+    fprintf(fp, "       fa2bed          create a bed file with assembly contig lengths\n");
+    fprintf(fp, "\n");
+    fprintf(fp, "       --help, -h      print this help message\n");
+    fprintf(fp, "       --version, -V   print version information\n");
+    return fp == stdout ? EXIT_SUCCESS : EXIT_FAILURE;
+}
+
+int main(int argc, char *argv[])
+{
+    double realtime0 = realtime();
+    int ret = 1;
+
+    if (argc < 2) return print_usage(stderr);
+    else if (strcmp(argv[1], "telowin") == 0) ret = telomere_windows_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "telobreaks") == 0) ret = telomere_breaks_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "telofind") == 0) ret = find_telomere_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "sdust") == 0) ret = sdust_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "fa2bed") == 0) ret = assbed_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "--version") == 0 || strcmp(argv[1], "-V") == 0) {
+        fprintf(stdout, "cornetto %s\n", CORNETTO_VERSION);
+        exit(EXIT_SUCCESS);
+    } else if (strcmp(argv[1], "--help") == 0 || strcmp(argv[1], "-h") == 0) return print_usage(stdout);
+    else {
+        fprintf(stderr, "[cornetto] Unrecognised command %s\n", argv[1]);
+        return print_usage(stderr);
+    }
+    cornetto_gpu_release();
+
+    fprintf(stderr, "[%s] Version: %s\n", __func__, CORNETTO_VERSION);
+    fprintf(stderr, "[%s] CMD:", __func__);
+    for (int i = 0; i < argc; ++i) fprintf(stderr, " %s", argv[i]);
+    fprintf(stderr, "\n[%s] Real time: %.3f sec; CPU time: %.3f sec; Peak RAM: %.3f GB\n\n", __func__,
+            realtime() - realtime0, cputime(), (double)peakrss() / 1024.0 / 1024.0 / 1024.0);
+    return ret;
+}

@@ -1,0 +1,81 @@
+/* cornetto_b200/host/misc.c -- timing helpers for the stderr footer (reference: src/misc.c:48-70),
+ * the shared GPU context, and buffered text output. */
+#include <sys/resource.h>
+#include <sys/time.h>
+
+#include "cornetto.h"
+
+double realtime(void)
+{
+    struct timeval tp;
+    gettimeofday(&tp, NULL);
+    return (double)tp.tv_sec + (double)tp.tv_usec * 1e-6;
+}
+
+double cputime(void)
+{
+    struct rusage r;
+    getrusage(RUSAGE_SELF, &r);
+    return (double)(r.ru_utime.tv_sec + r.ru_stime.tv_sec) + 1e-6 * (double)(r.ru_utime.tv_usec + r.ru_stime.tv_usec);
+}
+
+long peakrss(void)
+{
+    struct rusage r;
+    getrusage(RUSAGE_SELF, &r);
+    return r.ru_maxrss * 1024;
+}
+
+static corn_ctx_t *g_ctx;
+
+void cornetto_gpu_die(const char *what, int status)
+{
+    CORN_ERROR("%s: %s (%s)", what, corn_gpu_strerror(status), g_ctx ? corn_gpu_last_error(g_ctx) : "");
+    exit(EXIT_FAILURE);
+}
+
+corn_ctx_t *cornetto_gpu(void)
+{
+    if (!g_ctx) {
+        int r = corn_gpu_init(-1, &g_ctx);
+        if (r != CORN_OK) cornetto_gpu_die("cannot initialise the GPU", r);
+    }
+    return g_ctx;
+}
+
+void cornetto_gpu_release(void)
+{
+    if (g_ctx) corn_gpu_destroy(g_ctx);
+    g_ctx = NULL;
+}
+
+/* ---- output ------------------------------------------------------------------------------------ */
+void outbuf_init(outbuf_t *o, FILE *fp)
+{
+    o->cap = 1 << 20; o->n = 0; o->fp = fp;
+    o->buf = (char *)malloc(o->cap);
+    CORN_MALLOC_CHK(o->buf);
+}
+void outbuf_flush(outbuf_t *o) { if (o->n) fwrite(o->buf, 1, o->n, o->fp); o->n = 0; }
+void outbuf_free(outbuf_t *o) { outbuf_flush(o); fflush(o->fp); free(o->buf); o->buf = NULL; }
+static inline void need(outbuf_t *o, size_t k) { if (o->n + k > o->cap) outbuf_flush(o); }
+void outbuf_str(outbuf_t *o, const char *s, size_t len)
+{
+    if (len > o->cap / 2) { outbuf_flush(o); fwrite(s, 1, len, o->fp); return; }
+    need(o, len);
+    memcpy(o->buf + o->n, s, len);
+    o->n += len;
+}
+void outbuf_chr(outbuf_t *o, char c) { need(o, 1); o->buf[o->n++] = c; }
+void outbuf_u64(outbuf_t *o, uint64_t v)
+{
+    char t[24]; int k = 0;
+    do { t[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    need(o, (size_t)k);
+    while (k) o->buf[o->n++] = t[--k];
+}
+void outbuf_i32(outbuf_t *o, int32_t v)
+{
+    if (v < 0) { outbuf_chr(o, '-'); outbuf_u64(o, (uint64_t)(-(int64_t)v)); }
+    else outbuf_u64(o, (uint64_t)v);
+}

@@ -1,0 +1,74 @@
+/* cornetto_b200/host/sdust_main.c -- `cornetto sdust [-w 64] [-t 20] <in.fa|->`.
+ *
+ * Same contract as sdust_main(), src/sdust/sdust.c:179-207: ketopt-style short options "w:t:"
+ * that may also follow the file name (permutation), "-" reads stdin, usage + exit(1) when no
+ * input is given, one line  name \t start \t end  per masked interval.  sdust_core() is
+ * replaced by corn_gpu_sdust() on batches of records. */
+#include "cornetto.h"
+
+uint64_t cornetto_batch_capacity(const char *path);
+
+int sdust_main(int argc, char *argv[])
+{
+    int W = 64, T = 20;
+    const char *file = NULL;
+    /* option scan equivalent to ketopt(&o, argc, argv, 1, "w:t:", 0) (src/sdust/ketopt.h:57-118):
+     * arguments not starting with '-' (and a bare "-") are operands wherever they stand */
+    int i = 1;
+    while (i < argc) {
+        const char *a = argv[i];
+        if (a[0] != '-' || a[1] == 0) { if (!file) file = a; ++i; continue; }
+        if (a[1] == '-') {                 /* "--" ends the options; "--long" is unknown ('?') and skipped */
+            if (a[2] == 0) { for (++i; i < argc; ++i) if (!file) file = argv[i]; break; }
+            ++i; continue;
+        }
+        int pos = 1, next = i + 1;
+        while (a[pos]) {
+            const int c = a[pos++];
+            if (c == 'w' || c == 't') {
+                const char *arg = NULL;
+                if (a[pos]) arg = a + pos;
+                else if (i < argc - 1) { arg = argv[i + 1]; next = i + 2; }
+                if (arg) { if (c == 'w') W = atoi(arg); else T = atoi(arg); }
+                break;
+            }
+        }
+        i = next;
+    }
+    if (!file) {
+        fprintf(stderr, "Usage: sdust [-w %d] [-t %d] <in.fa>\n", W, T);
+        exit(1);
+    }
+    fastx_t *fx = fastx_open(file);
+    if (!fx) return 0;     /* the reference reads nothing from an unopenable file and returns 0 */
+    corn_ctx_t *ctx = cornetto_gpu();
+
+    const uint64_t cap = cornetto_batch_capacity(file);
+    uint64_t max_rec = cap / 64 + 16;
+    if (max_rec > (1u << 23)) max_rec = 1u << 23;
+    rec_batch_t *b = rec_batch_create(cap, (uint32_t)max_rec);
+    outbuf_t ob;
+    outbuf_init(&ob, stdout);
+    while (rec_batch_fill(b, fx) > 0) {
+        corn_batch_t view;
+        corn_hbatch_view(b->hb, &view);
+        corn_intervals_t iv;
+        int r = corn_gpu_sdust(ctx, &view, T, W, &iv);
+        if (r != CORN_OK) cornetto_gpu_die("sdust", r);
+        for (uint32_t rec = 0; rec < iv.n_rec; ++rec) {
+            const char *name = b->name[rec];
+            const size_t nl = strlen(name);
+            for (uint64_t k = iv.rec_first[rec]; k < iv.rec_first[rec + 1]; ++k) {
+                outbuf_str(&ob, name, nl);
+                outbuf_chr(&ob, '\t'); outbuf_i32(&ob, (int32_t)(iv.iv[k] >> 32));
+                outbuf_chr(&ob, '\t'); outbuf_i32(&ob, (int32_t)iv.iv[k]);
+                outbuf_chr(&ob, '\n');
+            }
+        }
+        corn_gpu_intervals_free(&iv);
+    }
+    outbuf_free(&ob);
+    rec_batch_destroy(b);
+    fastx_close(fx);
+    return 0;
+}

@@ -1,0 +1,107 @@
+/* cornetto_b200/host/telofind_main.c -- `cornetto telofind <fasta|fastq[.gz]> [MOTIF]`.
+ *
+ * Same contract as find_telomere_main(), src/find_telomere.c:83-111: usage text and exit(1)
+ * when the file argument is missing, motif = argv[2] or "TTAGGG" (used as given, never folded),
+ * one line  name \t len \t strand \t start \t end \t end-start  per maximal tandem run, strand 0
+ * runs of a record before its strand 1 runs.  The per-record toupper()/strstr() scan is replaced
+ * by corn_gpu_telofind() on batches of records. */
+#include <sys/stat.h>
+
+#include "cornetto.h"
+
+uint64_t cornetto_batch_capacity(const char *path)
+{
+    uint64_t cap = 1ull << 30;
+    const char *e = getenv("CORNETTO_BATCH_MB"), *eb = getenv("CORNETTO_BATCH_BYTES");
+    if (eb && atoll(eb) > 0) cap = (uint64_t)atoll(eb);
+    else if (e && atoll(e) > 0) cap = (uint64_t)atoll(e) << 20;
+    else {
+        struct stat st;
+        size_t n = strlen(path);
+        int gz = n > 3 && strcmp(path + n - 3, ".gz") == 0;
+        if (!gz && strcmp(path, "-") != 0 && stat(path, &st) == 0 && S_ISREG(st.st_mode)) {
+            uint64_t want = (uint64_t)st.st_size + (1u << 16);
+            if (want < cap) cap = want;
+        }
+    }
+    if (cap > CORN_MAX_BATCH_BYTES) cap = CORN_MAX_BATCH_BYTES;
+    return cap;
+}
+
+int find_telomere_main(int argc, char *argv[])
+{
+    if (argc < 2) {
+        fprintf(stderr, "Error: invalid number of parameters\n");
+        fprintf(stderr, "Usage: find <input fasta> [optional sequence to search for, default is vertebrate TTAGGG]\n");
+        exit(EXIT_FAILURE);
+    }
+    const char *fasta = argv[1];
+    const char *query = (argc >= 3 ? argv[2] : "TTAGGG");
+
+    fastx_t *fx = fastx_open(fasta);
+    CORN_F_CHK(fx, fasta);
+    corn_ctx_t *ctx = cornetto_gpu();
+
+    const uint64_t cap = cornetto_batch_capacity(fasta);
+    uint64_t max_rec = cap / 64 + 16;
+    if (max_rec > (1u << 23)) max_rec = 1u << 23;
+    rec_batch_t *b = rec_batch_create(cap, (uint32_t)max_rec);
+    outbuf_t ob;
+    outbuf_init(&ob, stdout);
+
+    if (query[0] == 0) {
+        /* the reference spins forever on an empty motif (strstr always matches); refuse instead */
+        CORN_ERROR("%s", "empty motif");
+        exit(EXIT_FAILURE);
+    }
+    while (rec_batch_fill(b, fx) > 0) {
+        corn_batch_t view;
+        corn_hbatch_view(b->hb, &view);
+        corn_hits_t hits;
+        int r = corn_gpu_telofind(ctx, &view, query, &hits);
+        if (r != CORN_OK) cornetto_gpu_die("telofind", r);
+        for (uint64_t i = 0; i < hits.n_run; ++i) {
+            const corn_run_t *h = &hits.run[i];
+            const char *name = b->name[h->rec];
+            outbuf_str(&ob, name, strlen(name));
+            outbuf_chr(&ob, '\t'); outbuf_u64(&ob, view.length[h->rec]);
+            outbuf_chr(&ob, '\t'); outbuf_u64(&ob, h->strand);
+            outbuf_chr(&ob, '\t'); outbuf_u64(&ob, h->start);
+            outbuf_chr(&ob, '\t'); outbuf_u64(&ob, h->end);
+            outbuf_chr(&ob, '\t'); outbuf_u64(&ob, h->end - h->start);
+            outbuf_chr(&ob, '\n');
+        }
+        corn_gpu_hits_free(&hits);
+    }
+    outbuf_free(&ob);
+    rec_batch_destroy(b);
+    fastx_close(fx);
+    return EXIT_SUCCESS;
+}
+
+/* `cornetto fa2bed <fasta>`: name \t 0 \t len per record (src/assbed.c:97-100); a by-product of
+ * the reader, needed by scripts/telostats.sh:36 for the .lens file. */
+int assbed_main(int argc, char *argv[])
+{
+    if (argc != 2 || strcmp(argv[1], "-h") == 0 || strcmp(argv[1], "--help") == 0) {
+        FILE *fp = (argc == 2) ? stdout : stderr;
+        fprintf(fp, "Usage: cornetto fa2bed <assembly.fa>\n");
+        exit(fp == stdout ? EXIT_SUCCESS : EXIT_FAILURE);
+    }
+    fastx_t *fx = fastx_open(argv[1]);
+    CORN_F_CHK(fx, argv[1]);
+    uint8_t *scratch = (uint8_t *)malloc(1 << 20);
+    CORN_MALLOC_CHK(scratch);
+    while (fastx_next(fx)) {
+        char *name = strdup(fastx_name(fx));
+        uint64_t len = 0;
+        int done = 0;
+        while (!done) len += fastx_seq(fx, scratch, 1 << 20, &done);
+        if (fastx_finish(fx) != 0) { free(name); break; }
+        fprintf(stdout, "%s\t%d\t%d\n", name, 0, (int)len);
+        free(name);
+    }
+    free(scratch);
+    fastx_close(fx);
+    return 0;
+}

@@ -1,0 +1,179 @@
+/* include/corn_gpu.h -- C ABI of the B200-native cornetto sequence-scan path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no C++/torch types.
+ * The reference (hasindu2008/cornetto, C99) has no device boundary at all -- its four hot
+ * sub-commands do their arithmetic inline in
+ *     find_telomere_main      src/find_telomere.c:83-111   (disambiguate :76-81, find :44-74, rc :24-42)
+ *     telomere_windows_main   src/telomere_windows.c:45-86 (process_scaffold :28-43)
+ *     telomere_breaks_main    src/telomere_breaks.c:47-172
+ *     sdust_main / sdust()    src/sdust/sdust.c:162-207    (sdust_core :130-160), API src/sdust/sdust.h:16-21
+ * A maintainer replaces those inline loops by the calls below (INTEGRATION.md shows the patch);
+ * cornetto_b200/host/ is that host side written out in C with the CLI and text formats unchanged.
+ *
+ * Conventions
+ *   - every function returns CORN_OK (0) or a negative corn_status; nothing here prints or exits
+ *     (the host wrappers own stdout/stderr/exit so the reference's text stays byte-identical);
+ *   - there is NO CPU fallback: without a usable sm_100 device corn_gpu_init() fails with
+ *     CORN_E_NOGPU and every other entry point needs a context;
+ *   - result arrays are owned by the library (pinned host memory) until the matching *_free;
+ *   - one context per GPU; a context may be used by one host thread at a time.
+ */
+#ifndef CORN_GPU_H
+#define CORN_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CORN_GPU_ABI_VERSION 1
+
+/* HBM sequence layout: records are concatenated; every record starts at a multiple of
+ * CORN_ALIGN bytes, is followed by at least one 0x00 byte, and all bytes outside records are
+ * 0x00.  (0x00 never matches a motif byte, so no occurrence can span two records.) */
+#define CORN_ALIGN 32u
+/* Largest batch (bytes incl. padding): hit positions are 32-bit inside the kernels. */
+#define CORN_MAX_BATCH_BYTES 0xFFF00000ull
+
+typedef enum corn_status {
+    CORN_OK          =  0,
+    CORN_E_NOGPU     = -1,  /* no CUDA device / not sm_100 / driver missing */
+    CORN_E_CUDA      = -2,  /* a CUDA runtime call failed; see corn_gpu_last_error() */
+    CORN_E_ARG       = -3,  /* invalid argument (NULL, empty motif, W out of range, ...) */
+    CORN_E_NOMEM     = -4,  /* host or device allocation failed */
+    CORN_E_LAYOUT    = -5,  /* batch violates the layout contract above */
+    CORN_E_TOOBIG    = -6,  /* batch larger than CORN_MAX_BATCH_BYTES or record >= 2^31 */
+    CORN_E_STATE     = -7,  /* call sequence error (e.g. telowin(NULL hits) without a prior telofind) */
+    CORN_E_INTERNAL  = -8   /* device-side consistency check failed */
+} corn_status;
+
+typedef struct corn_ctx corn_ctx_t;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int         corn_gpu_device_count(void);                 /* >=0, or negative corn_status */
+/* device < 0: take $CORNETTO_GPU if set, else device 0. */
+int         corn_gpu_init(int device, corn_ctx_t **ctx);
+void        corn_gpu_destroy(corn_ctx_t *ctx);
+const char *corn_gpu_strerror(int status);
+const char *corn_gpu_last_error(const corn_ctx_t *ctx);  /* detail of the last failure ("" if none) */
+/* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*).
+ * NULL restores the context's own stream. */
+int         corn_gpu_set_stream(corn_ctx_t *ctx, void *cuda_stream);
+
+/* ---- host batches ------------------------------------------------------------------------- */
+typedef struct corn_batch {
+    const uint8_t  *seq;          /* total_bytes bytes in the layout described above */
+    const uint64_t *offset;       /* [n_rec] start of each record in seq (multiple of CORN_ALIGN) */
+    const uint32_t *length;       /* [n_rec] record length in bytes (kseq's seq.l) */
+    uint32_t        n_rec;
+    uint64_t        total_bytes;  /* multiple of CORN_ALIGN, <= CORN_MAX_BATCH_BYTES */
+} corn_batch_t;
+
+/* Builder for a batch in PINNED host memory (what the kseq-style reader fills directly, so the
+ * H2D copy runs at full PCIe rate).  Replaces the per-record kstring_t buffer that
+ * kseq_read() grows with realloc (src/kseq.h:201-211). */
+typedef struct corn_hbatch corn_hbatch_t;
+int      corn_hbatch_create(uint64_t capacity_bytes, uint32_t max_records, corn_hbatch_t **hb);
+void     corn_hbatch_destroy(corn_hbatch_t *hb);
+void     corn_hbatch_reset(corn_hbatch_t *hb);
+/* Space left for ONE more record (bytes of sequence), 0 if the record table is full. */
+uint64_t corn_hbatch_room(const corn_hbatch_t *hb);
+/* Zero-copy fill: returns where the next record's bytes go (up to corn_hbatch_room()). */
+uint8_t *corn_hbatch_cursor(corn_hbatch_t *hb);
+/* Seals the record written at the cursor (length bytes), zero-fills its padding. */
+int      corn_hbatch_commit(corn_hbatch_t *hb, uint64_t length);
+/* Convenience: copy a record in.  CORN_E_TOOBIG if it does not fit. */
+int      corn_hbatch_add(corn_hbatch_t *hb, const void *bases, uint64_t length);
+void     corn_hbatch_view(const corn_hbatch_t *hb, corn_batch_t *view);
+
+/* ---- device-resident batches -------------------------------------------------------------- */
+typedef struct corn_dbatch corn_dbatch_t;
+int  corn_gpu_upload(corn_ctx_t *ctx, const corn_batch_t *batch, corn_dbatch_t **db);
+void corn_gpu_dbatch_free(corn_ctx_t *ctx, corn_dbatch_t *db);
+/* Device address of the sequence bytes (for in-place synthetic generation in bench.py). */
+void *corn_gpu_dbatch_seq_ptr(const corn_dbatch_t *db);
+uint64_t corn_gpu_dbatch_bytes(const corn_dbatch_t *db);
+/* Allocates a device batch with the given record lengths WITHOUT uploading bytes: the
+ * sequence area is zeroed and the caller (bench synthetic generator) fills the records. */
+int  corn_gpu_dbatch_alloc(corn_ctx_t *ctx, const uint32_t *length, uint32_t n_rec, corn_dbatch_t **db);
+int  corn_gpu_dbatch_download(corn_ctx_t *ctx, const corn_dbatch_t *db, uint32_t rec, uint8_t *dst);
+
+/* ---- telofind: replaces disambiguate()+find(), src/find_telomere.c:44-81 ------------------- */
+typedef struct corn_run {       /* one printed line: name \t len \t strand \t start \t end \t end-start */
+    uint32_t rec;               /* record index inside the batch */
+    uint32_t strand;            /* 0 = motif, 1 = rc(motif)  (src/find_telomere.c:51,65) */
+    uint32_t start, end;        /* [start,end) on the record */
+} corn_run_t;
+
+typedef struct corn_hits {
+    corn_run_t *run;            /* in the reference's print order: per record, strand 0 runs then strand 1 */
+    uint64_t    n_run;
+    void       *_owner;
+} corn_hits_t;
+
+/* Host-buffer entry point (H2D + kernels + D2H). */
+int  corn_gpu_telofind(corn_ctx_t *ctx, const corn_batch_t *batch, const char *motif, corn_hits_t *out);
+/* Same on a resident batch.  out may be NULL: the runs then stay on the device only (they are
+ * always kept there for a following corn_gpu_telowin(hits == NULL)). */
+int  corn_gpu_telofind_dev(corn_ctx_t *ctx, const corn_dbatch_t *db, const char *motif, corn_hits_t *out);
+void corn_gpu_hits_free(corn_hits_t *hits);
+
+/* ---- telowin: replaces the paint loop + process_scaffold(), src/telomere_windows.c:28-43,75-79 */
+typedef struct corn_contigs {
+    const uint32_t *length;     /* [n] contig lengths (atoi(col2), src/telomere_windows.c:72) */
+    uint32_t        n;
+} corn_contigs_t;
+
+typedef struct corn_window {    /* "Window\tname\tlen\tstart\tend\t%.3g(car/(end-start))" */
+    uint32_t rec;
+    uint32_t start, end;        /* i, i+den */
+    uint32_t car;               /* marked bases in [start,end) */
+} corn_window_t;
+
+typedef struct corn_windows {
+    corn_window_t *win;
+    uint64_t       n_win;
+    void          *_owner;
+} corn_windows_t;
+
+/* threshold_adj = thr * pow(identity/100, 6), computed by the caller in double exactly as
+ * src/telomere_windows.c:53-54 does.
+ * hits == NULL : use the runs left on the device by the last corn_gpu_telofind*() of this
+ *                context (fused telofind+telowin; contigs may be NULL = the batch's records).
+ * hits != NULL : paint these runs (any order, overlaps allowed; rec indexes contigs[]). */
+int  corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const corn_contigs_t *contigs,
+                      double threshold_adj, corn_windows_t *out);
+void corn_gpu_windows_free(corn_windows_t *w);
+
+/* ---- sdust: replaces sdust_core(), src/sdust/sdust.c:130-160 ------------------------------- */
+typedef struct corn_intervals {
+    uint64_t *iv;               /* start<<32 | finish, exactly the reference's encoding (sdust.c:99) */
+    uint64_t *rec_first;        /* [n_rec+1] iv[rec_first[r] .. rec_first[r+1]) belong to record r */
+    uint64_t  n_iv;
+    uint32_t  n_rec;
+    void     *_owner;
+} corn_intervals_t;
+
+/* 3 <= W <= 128 (default 64), any T (default 20). */
+int  corn_gpu_sdust(corn_ctx_t *ctx, const corn_batch_t *batch, int T, int W, corn_intervals_t *out);
+int  corn_gpu_sdust_dev(corn_ctx_t *ctx, const corn_dbatch_t *db, int T, int W, corn_intervals_t *out);
+void corn_gpu_intervals_free(corn_intervals_t *iv);
+
+/* ---- measurement hooks (CUDA events on the context's stream; bench.py reads them) ---------- */
+typedef struct corn_timing {
+    float h2d_ms;       /* host->device copies of the last call */
+    float scan_ms;      /* dominant kernel: telofind_scan / sdust_scan */
+    float post_ms;      /* every other kernel of the call (ordering, run assembly, bins, windows) */
+    float d2h_ms;       /* device->host copies of the results */
+    uint32_t launches;  /* kernels launched by the last call */
+    uint64_t out_bytes; /* result bytes produced on the device */
+} corn_timing_t;
+int  corn_gpu_last_timing(const corn_ctx_t *ctx, corn_timing_t *t);
+uint64_t corn_gpu_total_launches(const corn_ctx_t *ctx);   /* since corn_gpu_init */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CORN_GPU_H */

@@ -1,0 +1,229 @@
+"""GPU parity tests proper (run on the B200 box with `-m gpu`).
+
+Everything here goes through the product: either the drop-in `cornetto` binary (host C +
+C ABI + CUDA) or the C ABI itself via ctypes.  The checkers are the committed golden vectors
+(reference outputs, tests/golden/) and the oracle (oracle/, CPU restatement).  Integer/byte work:
+the bar is bit-exact.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util
+import synth
+from util import ROOT, run, write, retab_telomere, lens_from_fa2bed
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(ROOT, "cornetto_b200", "bin", "cornetto")
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from cornetto_b200 import capi as m
+    from cornetto_b200.build import ensure_built
+    ensure_built()
+    m.load()
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(capi):
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def cornetto(args, stdin=None, env=None, check=True):
+    e = dict(os.environ)
+    if env:
+        e.update(env)
+    return run([BIN] + args, stdin=stdin, env=e, check=check)
+
+
+# ---------------------------------------------------------------------------------------------
+# 1. drop-in binary vs the golden vectors made by the unmodified reference
+# ---------------------------------------------------------------------------------------------
+def test_cli_matches_golden(tmp_path):
+    g = golden_util.load()
+    for name, c in g.items():
+        fa = write(str(tmp_path / name), c["input"])
+        for m in golden_util.MOTIFS:
+            out, _, _ = cornetto(["telofind", fa, m])
+            assert out == c["telofind"][m], ("telofind", name, m)
+        out, _, _ = cornetto(["telofind", fa])
+        assert out == c["telofind"]["TTAGGG"], ("telofind default motif", name)
+        out, _, _ = cornetto(["fa2bed", fa])
+        assert out == c["fa2bed"], ("fa2bed", name)
+        tf = write(str(tmp_path / (name + ".telomere")), retab_telomere(c["telofind"]["TTAGGG"]))
+        lf = write(str(tmp_path / (name + ".lens")), lens_from_fa2bed(c["fa2bed"]))
+        for a in golden_util.TELOWIN:
+            out, _, _ = cornetto(["telowin", tf] + a)
+            assert out == c["telowin"][" ".join(a)], ("telowin", name, a)
+        for a in golden_util.SDUST:
+            out, _, _ = cornetto(["sdust"] + a + [fa])
+            assert out == c["sdust"][" ".join(a)], ("sdust", name, a)
+        sf = write(str(tmp_path / (name + ".sdust")), c["sdust"][""])
+        out, _, _ = cornetto(["telobreaks", lf, sf, tf])
+        assert out == c["telobreaks"], ("telobreaks", name)
+
+
+def test_cli_small_batches_and_chunks(tmp_path, oracle_bin):
+    """Record batches of a few KiB and 64..193-base sdust chunks: every seam type is crossed."""
+    recs = synth.assembly(11, [40_000, 9_000, 999, 1000, 1200, 7, 3_000], n_gaps=4, iupac_per_mb=200.0,
+                          microsat_per_mb=2000.0, telo=(20, 200))
+    fa = write(str(tmp_path / "a.fa"), synth.fasta_bytes(recs))
+    want_t, _, _ = run([oracle_bin, "telofind", fa])
+    want_s, _, _ = run([oracle_bin, "sdust", fa])
+    for bb in ("4096", "20000", "70000"):
+        out, _, _ = cornetto(["telofind", fa], env={"CORNETTO_BATCH_BYTES": bb})
+        assert out == want_t, bb
+        for ch in ("64", "101", "193", "1024"):
+            out, _, _ = cornetto(["sdust", fa], env={"CORNETTO_BATCH_BYTES": bb, "CORNETTO_SDUST_CHUNK": ch})
+            assert out == want_s, (bb, ch)
+
+
+def test_cli_stdin_gz_and_options(tmp_path, oracle_bin):
+    recs = synth.assembly(12, [30_000, 5_000], n_gaps=1)
+    data = synth.fasta_bytes(recs)
+    fa = write(str(tmp_path / "b.fa"), data)
+    want, _, _ = run([oracle_bin, "sdust", fa])
+    out, _, _ = cornetto(["sdust", "-"], stdin=data)
+    assert out == want
+    want2, _, _ = run([oracle_bin, "sdust", "-w", "32", "-t", "15", fa])
+    out, _, _ = cornetto(["sdust", fa, "-w", "32", "-t", "15"])      # options after the operand (ketopt permutes)
+    assert out == want2
+    out, _, _ = cornetto(["sdust", "-w32", "-t15", fa])
+    assert out == want2
+    import gzip
+    gz = write(str(tmp_path / "b.fa.gz"), gzip.compress(data))
+    want_t, _, _ = run([oracle_bin, "telofind", fa])
+    out, _, _ = cornetto(["telofind", gz])
+    assert out == want_t
+
+
+def test_cli_errors(tmp_path):
+    _, err, rc = cornetto(["telofind"], check=False)
+    assert rc == 1 and b"Usage: find <input fasta>" in err
+    _, err, rc = cornetto(["telofind", str(tmp_path / "nope.fa")], check=False)
+    assert rc == 1 and b"Could not to open file" in err
+    _, err, rc = cornetto(["sdust"], check=False)
+    assert rc == 1 and err.startswith(b"Usage: sdust [-w 64] [-t 20] <in.fa>")
+    _, err, rc = cornetto(["telowin", "x"], check=False)
+    assert rc == 1 and b"Usage: cornetto telowin" in err
+    out, err, rc = cornetto(["--version"])
+    assert out == b"cornetto 0.2.0\n"
+
+
+# ---------------------------------------------------------------------------------------------
+# 2. C ABI vs the oracle on seeded inputs
+# ---------------------------------------------------------------------------------------------
+def _oracle_lib():
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    L = C.CDLL(path)
+
+    class Run(C.Structure):
+        _fields_ = [("strand", C.c_uint32), ("start", C.c_uint64), ("end", C.c_uint64)]
+    L.orc_telofind.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.POINTER(C.POINTER(Run))]
+    L.orc_telofind.restype = C.c_size_t
+    L.orc_sdust.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.orc_sdust.restype = C.POINTER(C.c_uint64)
+    return L, Run
+
+
+def oracle_telofind(records, motif):
+    import ctypes as C
+    L, Run = _oracle_lib()
+    out = []
+    for i, r in enumerate(records):
+        p = C.POINTER(Run)()
+        b = bytes(r)
+        n = L.orc_telofind(b, len(b), motif.encode(), C.byref(p))
+        out += [(i, p[k].strand, p[k].start, p[k].end) for k in range(n)]
+    return np.array(out, dtype=np.uint64).reshape(-1, 4)
+
+
+def oracle_sdust(records, T, W):
+    import ctypes as C
+    L, _ = _oracle_lib()
+    ivs, first = [], [0]
+    for r in records:
+        b = bytes(r)
+        n = C.c_int()
+        p = L.orc_sdust(b, len(b), T, W, C.byref(n))
+        ivs += [p[k] for k in range(n.value)]
+        first.append(len(ivs))
+    return np.array(ivs, dtype=np.uint64), np.array(first, dtype=np.uint64)
+
+
+def as_rows(runs):
+    return np.stack([runs["rec"], runs["strand"], runs["start"], runs["end"]], axis=1).astype(np.uint64).reshape(-1, 4)
+
+
+@pytest.mark.parametrize("motif", ["TTAGGG", "TTTAGGG", "AAAAAA", "TATATA", "TTNGGG", "ACGTACGTACGTACGTACGTACGTACGTACGTACGT"])
+def test_abi_telofind(ctx, capi, motif):
+    rng = np.random.default_rng(21)
+    recs = [synth.make_contig(rng, int(L), n_gaps=2, iupac_per_mb=300.0, telo=(30, 300)) for L in (70_000, 33, 0, 5, 6, 120_001, 1024, 31, 32, 64)]
+    recs.append(np.frombuffer(b"TTAGGG" * 2000, dtype=np.uint8))           # one run across many tiles' worth of chunks
+    recs.append(np.frombuffer((b"TTAGGGA" * 3000), dtype=np.uint8))        # dense start/end events
+    hb = capi.HostBatch(recs)
+    got = as_rows(ctx.telofind(hb, motif))
+    want = oracle_telofind(recs, motif)
+    assert got.shape == want.shape and (got == want).all()
+
+
+def test_abi_telofind_telowin_fused(ctx, capi, oracle_bin, tmp_path):
+    recs = synth.assembly(31, [400_000, 150_000, 999, 1000, 1200, 1400, 2000, 1, 0], telo=(200, 900))
+    hb = capi.HostBatch([s for _, s in recs])
+    runs = ctx.telofind(hb, "TTAGGG")
+    for thr_in, ident in ((0.4, 99.9), (0.1, 99.9), (0.05, 95.0), (0.0, 100.0)):
+        thr = thr_in * (ident / 100) ** 6
+        fused = ctx.telowin(thr)
+        general = ctx.telowin(thr, runs=runs, lengths=hb.lengths)
+        assert (fused == general).all() and len(fused) == len(general)
+        # text check against the oracle CLI
+        tsv = b"".join(b"%s\t%d\t%d\t%d\t%d\t%d\n" % (recs[r["rec"]][0].encode(), hb.lengths[r["rec"]], r["strand"], r["start"], r["end"], r["end"] - r["start"]) for r in runs)
+        tf = write(str(tmp_path / "f.telomere"), tsv)
+        want, _, _ = run([oracle_bin, "telowin", tf, repr(ident), repr(thr_in)])
+        got = b"".join(b"Window\t%s\t%d\t%d\t%d\t%s\n" % (recs[w["rec"]][0].encode(), hb.lengths[w["rec"]], w["start"], w["end"],
+                                                       (b"%.3g" % (float(w["car"]) / float(int(w["end"]) - int(w["start"])))))
+                       for w in fused if True)
+        # contigs without any run never reach the reference's text path (scripts/telostats.sh pipes telofind output)
+        names_with_runs = {recs[r["rec"]][0].encode() for r in runs}
+        got = b"".join(l + b"\n" for l in got.splitlines() if l.split(b"\t")[1] in names_with_runs)
+        assert got == want, (thr_in, ident)
+
+
+@pytest.mark.parametrize("tw", [(20, 64), (15, 32), (10, 64), (25, 100), (8, 20)])
+def test_abi_sdust(ctx, capi, tw):
+    T, W = tw
+    rng = np.random.default_rng(41)
+    recs = [synth.make_contig(rng, int(L), telo=None, n_its=0, microsat_per_mb=3000.0, n_gaps=g, gap_len=(1, gl), p_lower=0.1, iupac_per_mb=500.0)
+            for L, g, gl in ((90_000, 6, 400), (5000, 30, 3), (4097, 0, 1), (4096, 1, 60), (1, 0, 1), (0, 0, 1), (2, 0, 1), (130_000, 40, 60))]
+    recs.append(np.frombuffer(b"A" * 100 + b"N" + b"AAAAA", dtype=np.uint8))   # interval past the end of the record
+    recs.append(np.frombuffer(b"A" * 20_000, dtype=np.uint8))                  # one interval across many chunks
+    hb = capi.HostBatch(recs)
+    iv, first = ctx.sdust(hb, T, W)
+    wiv, wfirst = oracle_sdust(recs, T, W)
+    assert (first == wfirst).all()
+    assert len(iv) == len(wiv) and (iv == wiv).all()
+
+
+def test_abi_errors(ctx, capi):
+    hb = capi.HostBatch([b"ACGT"])
+    with pytest.raises(capi.CornError):
+        ctx.telofind(hb, "")
+    with pytest.raises(capi.CornError):
+        ctx.sdust(hb, 20, 2)
+    with pytest.raises(capi.CornError):
+        ctx.sdust(hb, 20, 500)
+    # empty batch is fine
+    e = capi.HostBatch([])
+    assert len(ctx.telofind(e)) == 0
+    iv, first = ctx.sdust(e)
+    assert len(iv) == 0 and list(first) == [0]
