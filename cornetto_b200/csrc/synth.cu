@@ -34,15 +34,18 @@ __global__ void __launch_bounds__(256) k_fill_random(uint8_t *seq, uint64_t n_bl
     *(uint4 *)(seq + pos) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(256) k_apply_feature(uint8_t *seq, const uint32_t *__restrict__ rec_off,
-                                                       const uint32_t *__restrict__ rec_len, uint32_t n_rec, corn_feature_t f)
+// one block per feature
+__global__ void __launch_bounds__(128) k_apply_features(uint8_t *seq, const uint32_t *__restrict__ rec_off,
+                                                        const uint32_t *__restrict__ rec_len, uint32_t n_rec,
+                                                        const corn_feature_t *__restrict__ feats)
 {
+    const corn_feature_t f = feats[blockIdx.x];
     if (f.rec >= n_rec) return;
     const uint32_t len = rec_len[f.rec];
     if (f.start >= len) return;
     const uint32_t n = min(f.len, len - f.start);
     uint8_t *p = seq + rec_off[f.rec] + f.start;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         if (f.kind == CORN_FEAT_NGAP) p[i] = 'N';
         else if (f.kind == CORN_FEAT_LOWER) { uint8_t b = p[i]; if (b >= 'A' && b <= 'Z') p[i] = b + 32; }
         else {
@@ -78,13 +81,15 @@ extern "C" int corn_bench_fill_random(corn_ctx_t *ctx, corn_dbatch_t *db, uint64
 extern "C" int corn_bench_apply_features(corn_ctx_t *ctx, corn_dbatch_t *db, const corn_feature_t *feat, uint32_t n_feat)
 {
     if (!ctx || !db || (n_feat && !feat)) return CORN_E_ARG;
+    if (n_feat == 0) return CORN_OK;
     CORN_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (uint32_t i = 0; i < n_feat; ++i) {
-        const corn_feature_t f = feat[i];
-        if (f.kind == CORN_FEAT_TANDEM && (f.period == 0 || f.period > 8)) return corn_set_err(ctx, CORN_E_ARG, "feature %u: period %u", i, f.period);
-        const unsigned blocks = f.len > (1u << 16) ? 64 : 1;
-        k_apply_feature<<<blocks, 256, 0, ctx->stream>>>(db->d_seq, db->d_rec_off, db->d_rec_len, db->n_rec, f);
-    }
+    for (uint32_t i = 0; i < n_feat; ++i)
+        if (feat[i].kind == CORN_FEAT_TANDEM && (feat[i].period == 0 || feat[i].period > 8))
+            return corn_set_err(ctx, CORN_E_ARG, "feature %u: period %u", i, feat[i].period);
+    // features of one call may run concurrently: callers pass non-overlapping ones per call
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->wins, (size_t)n_feat * sizeof(corn_feature_t)));
+    CORN_CUDA(ctx, cudaMemcpyAsync(ctx->wins.p, feat, (size_t)n_feat * sizeof(corn_feature_t), cudaMemcpyHostToDevice, ctx->stream));
+    k_apply_features<<<n_feat, 128, 0, ctx->stream>>>(db->d_seq, db->d_rec_off, db->d_rec_len, db->n_rec, (const corn_feature_t *)ctx->wins.p);
     CORN_LAUNCH_CHECK(ctx);
     CORN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CORN_OK;

@@ -28,7 +28,8 @@ typedef struct corn_feature {
 /* every base of every record <- uniform A/C/G/T from a counter-based generator keyed by
  * (seed, byte position in the batch); padding stays 0x00. */
 int corn_bench_fill_random(corn_ctx_t *ctx, corn_dbatch_t *db, uint64_t seed);
-/* overlays features in array order (later features overwrite earlier ones) */
+/* overlays features; the features of ONE call are applied concurrently (overlapping ones race,
+ * any outcome being a valid sequence); successive calls are ordered. */
 int corn_bench_apply_features(corn_ctx_t *ctx, corn_dbatch_t *db, const corn_feature_t *feat, uint32_t n_feat);
 /* copies the whole padded sequence area (corn_gpu_dbatch_bytes() bytes) to host memory */
 int corn_bench_download_all(corn_ctx_t *ctx, const corn_dbatch_t *db, uint8_t *dst);

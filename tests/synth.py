@@ -65,11 +65,11 @@ def make_contig(rng, length: int, *, telo=(500, 2500), p_variant=0.02, p_lower=0
         p = int(rng.integers(0, length - g))
         s[p:p + g] = ord("N")
     n_iu = int(iupac_per_mb * length / 1e6)
-    if n_iu:
+    if n_iu and length > 0:
         codes = np.frombuffer(b"RYKMSWBDHVNU", dtype=np.uint8)
         pos = rng.integers(0, length, size=n_iu)
         s[pos] = codes[rng.integers(0, len(codes), size=n_iu)]
-    if p_lower > 0:
+    if p_lower > 0 and length > 0:
         # soft-masked stretches rather than isolated bases
         n_blk = max(1, int(p_lower * length / 200))
         for _ in range(n_blk):

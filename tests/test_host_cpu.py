@@ -1,0 +1,177 @@
+"""CPU-only checks of the host side and of the device-side algorithms compiled for the host.
+
+ - the streaming FASTA/FASTQ reader (cornetto_b200/host/fastx.c) against the oracle's kseq
+   restatement, also across tiny batch capacities (carry / grow paths);
+ - `cornetto telobreaks` and `cornetto fa2bed` (no GPU involved) against the golden vectors;
+ - tests/sim: the kernels' host/device arithmetic (bit-plane matcher, chunked sdust with exact
+   warm start and seam fold) against the oracle;
+ - without a GPU the scan commands fail loudly instead of falling back.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util
+import synth
+from util import ROOT, run, write, retab_telomere, lens_from_fa2bed
+
+BIN = os.path.join(ROOT, "cornetto_b200", "bin", "cornetto")
+INC = os.path.join(ROOT, "include")
+LIBDIR = os.path.join(ROOT, "cornetto_b200", "lib")
+
+
+@pytest.fixture(scope="session")
+def built():
+    from cornetto_b200.build import ensure_built
+    ensure_built()
+    return True
+
+
+@pytest.fixture(scope="session")
+def sim_bin(tmp_path_factory, oracle_bin):
+    out = str(tmp_path_factory.mktemp("sim") / "sim")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", out, "-x", "c++", os.path.join(ROOT, "tests", "sim", "sim_main.cpp"),
+                           "-x", "c", os.path.join(ROOT, "oracle", "oracle.c"), "-lz", "-lm"], stderr=subprocess.DEVNULL)
+    return out
+
+
+@pytest.fixture(scope="session")
+def reader_dump(tmp_path_factory, built):
+    out = str(tmp_path_factory.mktemp("rd") / "reader_dump")
+    host = os.path.join(ROOT, "cornetto_b200", "host")
+    subprocess.check_call(["gcc", "-O2", "-std=c99", "-D_GNU_SOURCE", "-I" + INC, "-o", out, os.path.join(ROOT, "tests", "sim", "reader_dump.c"),
+                           os.path.join(host, "fastx.c"), os.path.join(host, "misc.c"), "-L" + LIBDIR, "-lcorn_gpu",
+                           "-Wl,-rpath," + LIBDIR, "-lz", "-lm"])
+    return out
+
+
+def oracle_records(path):
+    L = C.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle.so"))
+
+    class Rec(C.Structure):
+        _fields_ = [("name", C.c_char_p), ("seq", C.POINTER(C.c_ubyte)), ("len", C.c_size_t)]
+    L.orc_read_fastx.argtypes = [C.c_char_p, C.POINTER(C.POINTER(Rec)), C.POINTER(C.c_size_t)]
+    recs, n = C.POINTER(Rec)(), C.c_size_t()
+    assert L.orc_read_fastx(path.encode(), C.byref(recs), C.byref(n)) == 0
+    return b"".join(recs[i].name + b"\t%d\t" % recs[i].len + bytes(recs[i].seq[:recs[i].len]).hex().encode() + b"\n" for i in range(n.value))
+
+
+EDGE_FILES = {
+    "eof_cr.fa": b">a\nACGT\r", "eof_cr2.fa": b">a\nACGT\n\r", "hdr_only.fa": b">a", "hdr_only2.fa": b">a\n",
+    "junk_before.fa": b"junk\n>a b c\nAC\nGT\n>b\n\n\n>c\nA", "plus.fa": b">a\nACGT\n+\nIIII\n>b\nAC\n",
+    "fq_noqual.fq": b"@a\nACGT\n+\n", "fq_at_in_qual.fq": b"@a\nACGT\n+\n@III\n@b\nGG\n+\n>I\n",
+    "win.fq": b"@a\r\nACGT\r\n+\r\nIIII\r\n@b\r\nAC\r\n+\r\nII\r\n", "empty.fa": b"", "cr_first.fa": b">x\r\n\r\nAC\r\n",
+}
+
+
+def test_reader_matches_oracle(reader_dump, oracle_bin, tmp_path):
+    cases = {k: c["input"] for k, c in golden_util.load().items()}
+    cases.update(EDGE_FILES)
+    for name, data in cases.items():
+        p = write(str(tmp_path / name), data)
+        want = oracle_records(p)
+        for cap in ("64", "4096", str(1 << 20)):
+            got, _, _ = run([reader_dump, p, cap])
+            assert got == want, (name, cap)
+            assert b"BADPAD" not in got and b"BADALIGN" not in got
+
+
+def test_telobreaks_and_fa2bed_match_golden(built, tmp_path):
+    for name, c in golden_util.load().items():
+        fa = write(str(tmp_path / name), c["input"])
+        out, _, _ = run([BIN, "fa2bed", fa])
+        assert out == c["fa2bed"], name
+        tf = write(str(tmp_path / (name + ".telomere")), retab_telomere(c["telofind"]["TTAGGG"]))
+        lf = write(str(tmp_path / (name + ".lens")), lens_from_fa2bed(c["fa2bed"]))
+        sf = write(str(tmp_path / (name + ".sdust")), c["sdust"][""])
+        out, _, _ = run([BIN, "telobreaks", lf, sf, tf])
+        assert out == c["telobreaks"], name
+
+
+def test_telobreaks_many_contigs(built, oracle_bin, tmp_path):
+    """khash bucket order with resizes (>16 contigs), run clamping at both contig ends, the
+    99 / 100 bp flank, matched length 18 vs 24, names missing from the lens file, duplicates."""
+    rng = np.random.default_rng(5)
+    names = [f"h{i % 7}tg{i * 37 % 1000:06d}l_{'MAT' if i % 2 else 'PAT'}" for i in range(300)]
+    lens = [int(rng.integers(2000, 9000)) for _ in names]
+    lens_txt = "".join(f"{n}\t{l}\n" for n, l in zip(names, lens)) + f"{names[3]}\t{lens[3]}\n"
+    sd, tl = [], []
+    for n, l in zip(names, lens):
+        sd.append(f"{n}\t0\t{int(rng.integers(300, 900))}\n")
+        sd.append(f"{n}\t{l - int(rng.integers(300, 900))}\t{l + 40}\n")
+        mid = int(rng.integers(1000, l - 1000))
+        sd.append(f"{n}\t{mid}\t{mid + 260}\n")
+        sd.append(f"{n}\t{mid + 260}\t{mid + 300}\n")          # adjacent: fuses with the previous
+        tl.append(f"{n}\t{l}\t1\t0\t{int(rng.choice([18, 24, 120]))}\t{int(rng.choice([18, 24, 120]))}\n")
+        tl.append(f"{n}\t{l}\t0\t{l - 60}\t{l}\t60\n")
+        tl.append(f"{n}\t{l}\t0\t{mid + int(rng.choice([99, 100, 101]))}\t{mid + 130}\t30\n")
+    sd.append("absent\t0\t100\n")
+    tl.append("absent\t500\t0\t0\t60\t60\n")
+    lf = write(str(tmp_path / "x.lens"), lens_txt.encode())
+    sf = write(str(tmp_path / "x.sdust"), "".join(sd).encode())
+    tf = write(str(tmp_path / "x.telomere"), "".join(tl).encode())
+    want, _, _ = run([oracle_bin, "telobreaks", lf, sf, tf])
+    got, _, _ = run([BIN, "telobreaks", lf, sf, tf])
+    assert got == want and len(want) > 1000
+
+
+def test_sim_core_primitives(sim_bin):
+    out, _, _ = run([sim_bin, "coretest"])
+    assert b"coretest ok" in out
+
+
+def test_sim_matches_oracle(sim_bin, oracle_bin, tmp_path):
+    """The device algorithms, compiled for the host, on the quirk corpus + an N-rich assembly."""
+    files = dict(synth.quirk_corpus())
+    files["asm.fa"] = synth.fasta_bytes(synth.assembly(1, [120_000, 30_000, 999, 1000, 7], n_gaps=6, iupac_per_mb=100.0, microsat_per_mb=1500.0))
+    for name, data in files.items():
+        if name.endswith(".gz"):
+            continue
+        p = write(str(tmp_path / name), data)
+        for motif in ("TTAGGG", "TATATA", "AAAAAA", "TTNGGG", "TTAGGGTTAGGG"):
+            a, _, _ = run([sim_bin, "telofind", p, motif])
+            b, _, _ = run([oracle_bin, "telofind", p, motif])
+            assert a == b, (name, motif)
+        for opts in ([], ["-w", "32", "-t", "15"], ["-t", "8"], ["-w", "100", "-t", "25"]):
+            b, _, _ = run([oracle_bin, "sdust"] + opts + [p])
+            for chunk in ("64", "101", "4096"):
+                a, _, _ = run([sim_bin, "sdust"] + opts + ["-c", chunk, p])
+                assert a == b, (name, opts, chunk)
+
+
+def test_sim_sdust_n_fuzz(sim_bin, oracle_bin, tmp_path):
+    """Differential fuzz of the chunked sdust (exact warm start + seam fold) on N-rich input."""
+    for seed in range(6):
+        rng = np.random.default_rng(1000 + seed)
+        recs = []
+        for k in range(8):
+            L = int(rng.integers(100, 20000))
+            recs.append((f"f{k}", synth.make_contig(rng, L, telo=None, n_its=0, microsat_per_mb=float(rng.choice([50, 3000, 20000])),
+                                                     n_gaps=int(rng.integers(0, 40)), gap_len=(1, int(rng.choice([3, 60, 400]))),
+                                                     p_lower=0.1, iupac_per_mb=float(rng.choice([0, 2000])))))
+        p = write(str(tmp_path / f"fz{seed}.fa"), synth.fasta_bytes(recs))
+        for opts in ([], ["-w", "32", "-t", "15"]):
+            b, _, _ = run([oracle_bin, "sdust"] + opts + [p])
+            for chunk in ("64", "101", "193"):
+                a, _, _ = run([sim_bin, "sdust"] + opts + ["-c", chunk, p])
+                assert a == b, (seed, opts, chunk)
+
+
+def test_scan_commands_fail_loudly_without_gpu(built, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    fa = write(str(tmp_path / "a.fa"), b">a\nTTAGGGTTAGGG\n")
+    for cmd in (["telofind", fa], ["sdust", fa]):
+        out, err, rc = run([BIN] + cmd, check=False)
+        assert rc == 1 and out == b"" and b"no usable CUDA device" in err
+    # argument errors are reported before any GPU work, exactly like the reference
+    _, err, rc = run([BIN, "telofind"], check=False)
+    assert rc == 1 and b"Usage: find <input fasta>" in err
+    _, err, rc = run([BIN, "sdust"], check=False)
+    assert rc == 1 and err.startswith(b"Usage: sdust [-w 64] [-t 20] <in.fa>")
+    _, err, rc = run([BIN, "telobreaks", "a", "b"], check=False)
+    assert rc == 1 and b"Usage: telobreaks" in err
