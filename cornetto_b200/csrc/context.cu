@@ -1,4 +1,5 @@
 // cornetto_b200/csrc/context.cu -- context, host/device batches, scratch, timing.
+#include <pthread.h>
 #include <stdarg.h>
 
 #include "corn_internal.cuh"
@@ -83,6 +84,7 @@ extern "C" void corn_gpu_destroy(corn_ctx_t *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     corn_ctx_adopt(ctx, NULL);
+    if (ctx->spare_base) cudaFree(ctx->spare_base);
     corn_dbuf *bufs[] = { &ctx->cand, &ctx->tile_tab, &ctx->events, &ctx->runs, &ctx->misc, &ctx->scan_tmp,
                           &ctx->bins, &ctx->bitmap, &ctx->wins, &ctx->sd_slots, &ctx->sd_out, &ctx->sd_tab };
     for (size_t i = 0; i < sizeof bufs / sizeof bufs[0]; ++i) dbuf_free(bufs[i]);
@@ -123,14 +125,55 @@ int corn_read_small(corn_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
     return CORN_OK;
 }
 
+// Pinned result blocks are recycled through a small process-wide pool: cudaMallocHost /
+// cudaFreeHost cost far more than the copies they serve when a caller loops over batches.
+namespace {
+struct HostBlock { void *p; size_t bytes; };
+constexpr int POOL_SLOTS = 8;
+HostBlock g_pool[POOL_SLOTS];        // free blocks
+HostBlock g_live[64];                // handed out (size lookup on free)
+pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
+}
+
 void *corn_host_alloc(size_t bytes)
 {
-    void *p = NULL;
     if (bytes == 0) bytes = 1;
-    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    void *p = NULL;
+    size_t got = 0;
+    pthread_mutex_lock(&g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < POOL_SLOTS; ++i)
+        if (g_pool[i].p && g_pool[i].bytes >= bytes && (best < 0 || g_pool[i].bytes < g_pool[best].bytes)) best = i;
+    if (best >= 0) { p = g_pool[best].p; got = g_pool[best].bytes; g_pool[best].p = NULL; }
+    pthread_mutex_unlock(&g_pool_mu);
+    if (!p) {
+        got = bytes + bytes / 4;
+        if (cudaMallocHost(&p, got) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    }
+    pthread_mutex_lock(&g_pool_mu);
+    for (int i = 0; i < 64; ++i) if (!g_live[i].p) { g_live[i].p = p; g_live[i].bytes = got; break; }
+    pthread_mutex_unlock(&g_pool_mu);
     return p;
 }
-void corn_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void corn_host_free(void *p)
+{
+    if (!p) return;
+    size_t bytes = 0;
+    pthread_mutex_lock(&g_pool_mu);
+    for (int i = 0; i < 64; ++i) if (g_live[i].p == p) { bytes = g_live[i].bytes; g_live[i].p = NULL; break; }
+    if (bytes) {
+        int slot = -1;
+        for (int i = 0; i < POOL_SLOTS; ++i) if (!g_pool[i].p) { slot = i; break; }
+        if (slot < 0) {                      // pool full: evict the smallest block if this one is bigger
+            int small = 0;
+            for (int i = 1; i < POOL_SLOTS; ++i) if (g_pool[i].bytes < g_pool[small].bytes) small = i;
+            if (g_pool[small].bytes < bytes) { void *old = g_pool[small].p; g_pool[small].p = p; g_pool[small].bytes = bytes; p = old; }
+        } else { g_pool[slot].p = p; g_pool[slot].bytes = bytes; p = NULL; }
+    }
+    pthread_mutex_unlock(&g_pool_mu);
+    if (p) cudaFreeHost(p);
+}
 
 extern "C" int corn_gpu_last_timing(const corn_ctx_t *ctx, corn_timing_t *t)
 {
@@ -259,7 +302,14 @@ static int dbatch_new(corn_ctx *ctx, const uint64_t *offset, const uint32_t *len
     // round the data area up to whole tiles so the scan kernel never needs a bounds check
     uint64_t tiles = (total_bytes + CORN_TILE_BYTES - 1) / CORN_TILE_BYTES;
     db->alloc_bytes = CORN_GUARD_BYTES + tiles * CORN_TILE_BYTES + CORN_TAIL_BYTES;
-    e = cudaMalloc((void **)&db->d_base, db->alloc_bytes);
+    db->span_bytes = db->alloc_bytes;
+    if (ctx->spare_base && ctx->spare_bytes >= db->alloc_bytes) {
+        db->d_base = ctx->spare_base; db->alloc_bytes = ctx->spare_bytes;
+        ctx->spare_base = NULL; ctx->spare_bytes = 0;
+        e = cudaSuccess;
+    } else {
+        e = cudaMalloc((void **)&db->d_base, db->alloc_bytes);
+    }
     if (e == cudaSuccess) e = cudaMalloc((void **)&db->d_rec_off, sizeof(uint32_t) * ((size_t)n_rec + 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&db->d_rec_len, sizeof(uint32_t) * ((size_t)n_rec + 1));
     if (e != cudaSuccess) {
@@ -283,8 +333,14 @@ extern "C" void corn_gpu_dbatch_free(corn_ctx_t *ctx, corn_dbatch_t *db)
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         if (ctx->last_db == db) ctx->last_db = NULL;
+        if (db->alloc_bytes > ctx->spare_bytes) {            // keep the larger buffer for the next upload
+            uint8_t *old = ctx->spare_base;
+            ctx->spare_base = db->d_base; ctx->spare_bytes = db->alloc_bytes;
+            db->d_base = old;
+        }
     }
-    cudaFree(db->d_base); cudaFree(db->d_rec_off); cudaFree(db->d_rec_len);
+    if (db->d_base) cudaFree(db->d_base);
+    cudaFree(db->d_rec_off); cudaFree(db->d_rec_len);
     free(db->h_rec_off); free(db->h_rec_len); free(db);
 }
 
@@ -315,7 +371,7 @@ extern "C" int corn_gpu_upload(corn_ctx_t *ctx, const corn_batch_t *b, corn_dbat
     // guard + tail (and the round-up-to-tile area) are zero; the record area is copied as is:
     // the layout contract makes the caller responsible for the zero padding between records.
     if (e == cudaSuccess) e = cudaMemsetAsync(db->d_base, 0, CORN_GUARD_BYTES, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(db->d_seq + b->total_bytes, 0, db->alloc_bytes - CORN_GUARD_BYTES - b->total_bytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(db->d_seq + b->total_bytes, 0, db->span_bytes - CORN_GUARD_BYTES - b->total_bytes, ctx->stream);
     if (e == cudaSuccess && b->total_bytes) e = cudaMemcpyAsync(db->d_seq, b->seq, b->total_bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) r = dbatch_tables_to_device(ctx, db);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[1], ctx->stream);
@@ -342,7 +398,7 @@ extern "C" int corn_gpu_dbatch_alloc(corn_ctx_t *ctx, const uint32_t *length, ui
     int r = dbatch_new(ctx, off, length, n_rec, used, &db);
     free(off);
     if (r != CORN_OK) return r;
-    cudaError_t e = cudaMemsetAsync(db->d_base, 0, db->alloc_bytes, ctx->stream);
+    cudaError_t e = cudaMemsetAsync(db->d_base, 0, db->span_bytes, ctx->stream);
     if (e == cudaSuccess) r = dbatch_tables_to_device(ctx, db);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess || r != CORN_OK) {

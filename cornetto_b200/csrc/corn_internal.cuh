@@ -32,7 +32,8 @@ struct corn_dbatch {
     uint8_t  *d_base;      // allocation start (guard included)
     uint8_t  *d_seq;       // d_base + CORN_GUARD_BYTES
     uint64_t  total_bytes; // multiple of CORN_ALIGN
-    uint64_t  alloc_bytes;
+    uint64_t  alloc_bytes; // size of the allocation (may exceed span_bytes when a retired buffer is reused)
+    uint64_t  span_bytes;  // guard + whole tiles + tail actually used by this batch
     uint32_t  n_rec;
     uint32_t *d_rec_off;   // [n_rec+1] start of each record (buffer position); [n_rec] = total_bytes
     uint32_t *d_rec_len;   // [n_rec]
@@ -68,6 +69,10 @@ struct corn_ctx {
     corn_dbuf sd_slots;    // sdust per-chunk interval slots
     corn_dbuf sd_out;      // sdust compacted output
     corn_dbuf sd_tab;      // sdust chunk tables
+
+    // one retired sequence buffer kept for the next upload (cudaMalloc/cudaFree of GBs cost milliseconds)
+    uint8_t *spare_base;
+    uint64_t spare_bytes;
 
     // batch uploaded by a host-buffer entry point; kept resident until the next such call so a
     // fused telowin(hits == NULL) can still reach its record table

@@ -228,6 +228,7 @@ extern "C" int corn_gpu_sdust(corn_ctx_t *ctx, const corn_batch_t *batch, int T,
 {
     if (!ctx || !batch || !out) return CORN_E_ARG;
     corn_dbatch_t *db = NULL;
+    corn_ctx_adopt(ctx, NULL);   // retire the previous resident batch first: its buffer is reused by the upload
     CORN_TRY(corn_gpu_upload(ctx, batch, &db));
     const float h2d = ctx->timing.h2d_ms;
     corn_ctx_adopt(ctx, db);

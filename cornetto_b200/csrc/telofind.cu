@@ -126,7 +126,7 @@ constexpr uint64_t FC_TTAGGG = pack_codes("TTAGGG"), RC_TTAGGG = pack_codes("CCC
 // M_CT > 0: motif length AND codes (FC_CT/RC_CT) are compile-time, so the class selects fold
 // into the LOP3 truth tables.  M_CT == 0: run-time motif (length P.m, codes P.fc/P.rc).
 template <int M_CT, uint64_t FC_CT, uint64_t RC_CT>
-__global__ void __launch_bounds__(256, 4) k_telofind_scan(const ScanParams P)
+__global__ void __launch_bounds__(256, 5) k_telofind_scan(const ScanParams P)
 {
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -139,30 +139,41 @@ __global__ void __launch_bounds__(256, 4) k_telofind_scan(const ScanParams P)
         const size_t   base = (size_t)tile * CORN_TILE_CHUNKS;
         const uint32_t chunk0 = tile * CORN_TILE_CHUNKS + lane;
         uint32_t cnt = 0;
+        uint32_t pp1 = 0, pp2 = 0;
 
-        uint32_t cur[8], nxt[8];
-        ld256(lane_ptr, cur);
-        ld256(lane_ptr + CORN_ROW_BYTES, nxt);
-        uint32_t pp1, pp2;
-        corn_planes32(cur, pp1, pp2);
-#pragma unroll 1
-        for (uint32_t row = 1; row <= CORN_TILE_ROWS; ++row) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-            // prefetch row+1 (the row after the tile's last one is the next tile's first row;
-            // the one after that is still inside the allocation thanks to CORN_TAIL_BYTES)
-            ld256(lane_ptr + (size_t)(row + 1) * CORN_ROW_BYTES, nxt);
-            uint32_t c1, c2;
-            corn_planes32(cur, c1, c2);
-            // lane i needs the planes of the 32 bytes that follow its chunk of row-1:
-            // lane i+1's previous planes, or (lane 31) lane 0's current planes.
-            const uint32_t n1 = __shfl_sync(0xffffffffu, lane == 0 ? c1 : pp1, (lane + 1) & 31);
-            const uint32_t n2 = __shfl_sync(0xffffffffu, lane == 0 ? c2 : pp2, (lane + 1) & 31);
-            uint32_t mf, mr;
-            corn_match32<M_CT>(pp1, pp2, n1, n2, M_CT ? FC_CT : P.fc, M_CT ? RC_CT : P.rc, P.m, mf, mr);
-            push_candidates(P, base, cnt, chunk0 + (row - 1) * 32u, mf, mr, lane);
-            pp1 = c1; pp2 = c2;
+        // Rows 0..CORN_TILE_ROWS (the extra one is the next tile's first row: only its planes are
+        // needed, for lane 31 of the last row).  Three register buffers rotate so that two rows
+        // (2 KiB per warp) are always in flight behind the one being processed.
+        uint32_t b0[8], b1[8], b2[8];
+        ld256(lane_ptr, b0);
+        ld256(lane_ptr + CORN_ROW_BYTES, b1);
+        ld256(lane_ptr + 2 * CORN_ROW_BYTES, b2);
+
+        // planes of `buf` (row r); candidates of row r-1 from (pp, planes); then refill buf with row r+3
+#define CORN_ROW_STEP(buf, r)                                                                                   \
+        {                                                                                                       \
+            uint32_t c1, c2;                                                                                    \
+            corn_planes32(buf, c1, c2);                                                                         \
+            if ((r) + 3 <= CORN_TILE_ROWS) ld256(lane_ptr + (size_t)((r) + 3) * CORN_ROW_BYTES, buf);           \
+            if ((r) > 0) {                                                                                      \
+                /* lane i needs the planes of the 32 bytes after its chunk of row r-1: lane i+1's previous  */ \
+                /* planes, or (lane 31) lane 0's current planes                                              */ \
+                const uint32_t n1 = __shfl_sync(0xffffffffu, lane == 0 ? c1 : pp1, (lane + 1) & 31);            \
+                const uint32_t n2 = __shfl_sync(0xffffffffu, lane == 0 ? c2 : pp2, (lane + 1) & 31);            \
+                uint32_t mf, mr;                                                                                \
+                corn_match32<M_CT>(pp1, pp2, n1, n2, M_CT ? FC_CT : P.fc, M_CT ? RC_CT : P.rc, P.m, mf, mr);    \
+                push_candidates(P, base, cnt, chunk0 + ((r) - 1) * 32u, mf, mr, lane);                          \
+            }                                                                                                   \
+            pp1 = c1; pp2 = c2;                                                                                 \
         }
+        static_assert((CORN_TILE_ROWS + 1) % 3 == 0, "row loop is unrolled by three");
+#pragma unroll 1
+        for (uint32_t row = 0; row <= CORN_TILE_ROWS; row += 3) {
+            CORN_ROW_STEP(b0, row)
+            CORN_ROW_STEP(b1, row + 1)
+            CORN_ROW_STEP(b2, row + 2)
+        }
+#undef CORN_ROW_STEP
         __syncwarp();
         classify_tile(P, tile, cnt, lane);
         __syncwarp();
@@ -211,7 +222,9 @@ struct ScatterParams {
     const uint4    *tile_off;
     const uint32_t *tile_ncand;
     uint32_t n_tiles;
-    uint32_t *start_f, *end_f, *start_r, *end_r;   // global byte positions
+    uint32_t *ev;              // event lists, laid out [start_f | end_f | start_r | end_r] from the totals
+    const uint4 *totals;       // device: #start_f, #end_f, #start_r, #end_r
+    uint32_t capacity;         // entries available in ev
     int m;
 };
 
@@ -231,6 +244,9 @@ __global__ void __launch_bounds__(256) k_telofind_scatter(const ScatterParams P)
     if (tile >= P.n_tiles) return;
     const uint32_t cnt = P.tile_ncand[tile];
     if (cnt == 0) return;
+    const uint4 tot = *P.totals;
+    if ((uint64_t)tot.x + tot.y + tot.z + tot.w > P.capacity) return;     // host grows the buffer and relaunches
+    uint32_t *start_f = P.ev, *end_f = start_f + tot.x, *start_r = end_f + tot.y, *end_r = start_r + tot.z;
     uint4 off = P.tile_off[tile];
     const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
     for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
@@ -245,10 +261,10 @@ __global__ void __launch_bounds__(256) k_telofind_scatter(const ScatterParams P)
         const uint32_t k_sf = __popc(sf), k_ef = __popc(ef), k_sr = __popc(sr), k_er = __popc(er);
         const uint32_t i_sf = corn_warp_iscan(k_sf, lane), i_ef = corn_warp_iscan(k_ef, lane);
         const uint32_t i_sr = corn_warp_iscan(k_sr, lane), i_er = corn_warp_iscan(k_er, lane);
-        emit_bits(sf, P.start_f + off.x + i_sf - k_sf, pos0);
-        emit_bits(ef, P.end_f + off.y + i_ef - k_ef, pos0 + P.m);
-        emit_bits(sr, P.start_r + off.z + i_sr - k_sr, pos0);
-        emit_bits(er, P.end_r + off.w + i_er - k_er, pos0 + P.m);
+        emit_bits(sf, start_f + off.x + i_sf - k_sf, pos0);
+        emit_bits(ef, end_f + off.y + i_ef - k_ef, pos0 + P.m);
+        emit_bits(sr, start_r + off.z + i_sr - k_sr, pos0);
+        emit_bits(er, end_r + off.w + i_er - k_er, pos0 + P.m);
         off.x += __shfl_sync(0xffffffffu, i_sf, 31);
         off.y += __shfl_sync(0xffffffffu, i_ef, 31);
         off.z += __shfl_sync(0xffffffffu, i_sr, 31);
@@ -264,31 +280,48 @@ __global__ void __launch_bounds__(256) k_telofind_scatter(const ScatterParams P)
 //   rev run k of record r  ->  k + #fwd runs in records <= r
 // -------------------------------------------------------------------------------------------
 struct AssembleParams {
-    const uint32_t *start_f, *end_f, *start_r, *end_r;
-    uint32_t n_f, n_r;
+    const uint32_t *ev;        // [start_f | end_f | start_r | end_r]
+    const uint4 *totals;
+    uint32_t ev_capacity, run_capacity;
     const uint32_t *rec_off;   // [n_rec+1]
     uint32_t n_rec;
+    uint32_t *rank_f, *rank_r; // [n_rec+1]: number of fwd / rev runs that start before record r
     corn_run_t *out;
     uint32_t *err;
 };
 
+// rank_f[r] = #forward starts < rec_off[r]  (r = 0..n_rec), same for reverse: one thread per record
+__global__ void __launch_bounds__(256) k_telofind_ranks(const AssembleParams P)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > P.n_rec) return;
+    const uint4 tot = *P.totals;
+    if ((uint64_t)tot.x + tot.y + tot.z + tot.w > P.ev_capacity) return;
+    const uint32_t *start_f = P.ev, *start_r = P.ev + tot.x + tot.y;
+    const uint32_t pos = P.rec_off[r];
+    P.rank_f[r] = corn_lower_bound(start_f, tot.x, pos);
+    P.rank_r[r] = corn_lower_bound(start_r, tot.z, pos);
+}
+
 __global__ void __launch_bounds__(256) k_telofind_assemble(const AssembleParams P)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.n_f + P.n_r) return;
-    const bool rev = t >= P.n_f;
-    const uint32_t k = rev ? t - P.n_f : t;
-    const uint32_t s = rev ? P.start_r[k] : P.start_f[k];
-    const uint32_t e = rev ? P.end_r[k] : P.end_f[k];
-    const uint32_t rec = corn_upper_bound(P.rec_off, P.n_rec, s) - 1;   // rec_off[rec] <= s
-    const uint32_t r0 = P.rec_off[rec];
-    uint32_t slot;
-    if (!rev) slot = k + corn_lower_bound(P.start_r, P.n_r, r0);
-    else      slot = k + corn_lower_bound(P.start_f, P.n_f, P.rec_off[rec + 1]);
-    if (e <= s || e > P.rec_off[rec + 1]) atomicAdd(P.err, 1u);       // would mean a start/end mismatch
-    corn_run_t r;
-    r.rec = rec; r.strand = rev ? 1u : 0u; r.start = s - r0; r.end = e - r0;
-    P.out[slot] = r;
+    const uint4 tot = *P.totals;
+    const uint32_t n_f = tot.x, n_r = tot.z;
+    if ((uint64_t)tot.x + tot.y + tot.z + tot.w > P.ev_capacity || (uint64_t)n_f + n_r > P.run_capacity) return;
+    const uint32_t *start_f = P.ev, *end_f = start_f + tot.x, *start_r = end_f + tot.y, *end_r = start_r + tot.z;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_f + n_r; t += gridDim.x * blockDim.x) {
+        const bool rev = t >= n_f;
+        const uint32_t k = rev ? t - n_f : t;
+        const uint32_t s = rev ? start_r[k] : start_f[k];
+        const uint32_t e = rev ? end_r[k] : end_f[k];
+        const uint32_t rec = corn_upper_bound(P.rec_off, P.n_rec, s) - 1;   // rec_off[rec] <= s
+        const uint32_t r0 = P.rec_off[rec];
+        const uint32_t slot = rev ? k + P.rank_f[rec + 1] : k + P.rank_r[rec];
+        if (e <= s || e > P.rec_off[rec + 1]) atomicAdd(P.err, 1u);        // would mean a start/end mismatch
+        corn_run_t r;
+        r.rec = rec; r.strand = rev ? 1u : 0u; r.start = s - r0; r.end = e - r0;
+        P.out[slot] = r;
+    }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -345,6 +378,15 @@ __global__ void k_reset_counter(uint32_t *p, int n) { if ((int)threadIdx.x < n) 
 // --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
+template <typename K>
+static int scan_grid(corn_ctx *ctx, K kernel)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
+    if (const char *e = getenv("CORNETTO_SCAN_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= per_sm) per_sm = v; }
+    return ctx->sm_count * per_sm;
+}
+
 static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif, corn_hits_t *out)
 {
     if (!motif || !motif[0]) return corn_set_err(ctx, CORN_E_ARG, "empty motif");
@@ -391,15 +433,15 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
 
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     if (n_tiles) {
-        // persistent grid: 4 CTAs of 8 warps per SM
-        const int grid = ctx->sm_count * 4;
+        // persistent grid: every SM filled to the occupancy limit (a partial last wave would leave
+        // whole SMs without a CTA: the block scheduler packs, it does not balance)
         if (mi.acgt && mi.m <= CORN_MAX_FAST_MOTIF) {
             if (mi.m == 6 && mi.fc == FC_TTAGGG && mi.rc == RC_TTAGGG)
-                k_telofind_scan<6, FC_TTAGGG, RC_TTAGGG><<<grid, 256, 0, st>>>(sp);
+                k_telofind_scan<6, FC_TTAGGG, RC_TTAGGG><<<scan_grid(ctx, k_telofind_scan<6, FC_TTAGGG, RC_TTAGGG>), 256, 0, st>>>(sp);
             else
-                k_telofind_scan<0, 0, 0><<<grid, 256, 0, st>>>(sp);
+                k_telofind_scan<0, 0, 0><<<scan_grid(ctx, k_telofind_scan<0, 0, 0>), 256, 0, st>>>(sp);
         } else {
-            k_telofind_scan_generic<<<grid, 256, 0, st>>>(sp);
+            k_telofind_scan_generic<<<scan_grid(ctx, k_telofind_scan_generic), 256, 0, st>>>(sp);
         }
         corn_count_launch(ctx);
         CORN_LAUNCH_CHECK(ctx);
@@ -407,61 +449,83 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
 
     CORN_TRY(corn_scan_u32x4(ctx, sp.tile_cnt, tile_off, n_tiles, d_totals));
-    uint32_t tot[4];
-    CORN_TRY(corn_read_small(ctx, tot, d_totals, 16));
-    const uint32_t n_sf = tot[0], n_ef = tot[1], n_sr = tot[2], n_er = tot[3];
-    if (!mi.bordered && (n_sf != n_ef || n_sr != n_er))
-        return corn_set_err(ctx, CORN_E_INTERNAL, "start/end counts differ: %u/%u %u/%u", n_sf, n_ef, n_sr, n_er);
 
-    const size_t n_ev = (size_t)n_sf + n_ef + n_sr + n_er;
-    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, (n_ev + 4) * sizeof(uint32_t)));
-    uint32_t *ev = (uint32_t *)ctx->events.p;
-    ScatterParams sc;
-    sc.c_idx = sp.c_idx; sc.c_a = sp.c_a; sc.c_b = sp.c_b; sc.c_c = sp.c_c; sc.c_d = sp.c_d;
-    sc.tile_off = tile_off; sc.tile_ncand = sp.tile_ncand; sc.n_tiles = n_tiles;
-    sc.start_f = ev; sc.end_f = ev + n_sf; sc.start_r = sc.end_f + n_ef; sc.end_r = sc.start_r + n_sr;
-    sc.m = mi.m;
-    if (n_tiles && n_ev) {
-        k_telofind_scatter<<<(n_tiles + 7) / 8, 256, 0, st>>>(sc);
-        corn_count_launch(ctx);
-        CORN_LAUNCH_CHECK(ctx);
-    }
-
+    // Everything below is launched against SPECULATIVE buffer capacities (grow-only, remembered across
+    // calls) with the exact totals read by the kernels from device memory; the host looks at the
+    // totals once, at the end, and only repeats the sparse phase if a buffer was too small.
     uint64_t n_run = 0;
-    if (!mi.bordered) {
-        n_run = (uint64_t)n_sf + n_sr;
-        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->runs, (n_run + 1) * sizeof(corn_run_t)));
-        if (n_run) {
-            AssembleParams ap;
-            ap.start_f = sc.start_f; ap.end_f = sc.end_f; ap.start_r = sc.start_r; ap.end_r = sc.end_r;
-            ap.n_f = n_sf; ap.n_r = n_sr; ap.rec_off = db->d_rec_off; ap.n_rec = db->n_rec;
-            ap.out = (corn_run_t *)ctx->runs.p; ap.err = d_err;
-            k_telofind_assemble<<<(unsigned)((n_run + 255) / 256), 256, 0, st>>>(ap);
+    uint32_t tot[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };     // totals (4), tile counter, error counter
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t ev_cap = ctx->events.cap / sizeof(uint32_t), run_cap = ctx->runs.cap / sizeof(corn_run_t);
+        const size_t guess = (size_t)(db->total_bytes / 256) + 4096;          // ~8x the random-DNA hit rate
+        if (attempt == 0 && ev_cap < 4 * guess) { CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, 4 * guess * sizeof(uint32_t))); ev_cap = ctx->events.cap / sizeof(uint32_t); }
+        if (attempt == 0 && run_cap < guess) { CORN_TRY(corn_dbuf_reserve(ctx, &ctx->runs, guess * sizeof(corn_run_t))); run_cap = ctx->runs.cap / sizeof(corn_run_t); }
+        if (ev_cap > 0xFFFFFFFFull) ev_cap = 0xFFFFFFFFull;
+        if (run_cap > 0xFFFFFFFFull) run_cap = 0xFFFFFFFFull;
+        uint32_t *ev = (uint32_t *)ctx->events.p;
+        ScatterParams sc;
+        sc.c_idx = sp.c_idx; sc.c_a = sp.c_a; sc.c_b = sp.c_b; sc.c_c = sp.c_c; sc.c_d = sp.c_d;
+        sc.tile_off = tile_off; sc.tile_ncand = sp.tile_ncand; sc.n_tiles = n_tiles;
+        sc.ev = ev; sc.totals = d_totals; sc.capacity = (uint32_t)ev_cap; sc.m = mi.m;
+        if (n_tiles) {
+            k_telofind_scatter<<<(n_tiles + 7) / 8, 256, 0, st>>>(sc);
             corn_count_launch(ctx);
             CORN_LAUNCH_CHECK(ctx);
         }
-    } else if (db->n_rec) {
-        const size_t n2 = 2 * (size_t)db->n_rec;
-        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (2 * n2 + 8) * sizeof(uint32_t)));   // borrowed as a temporary
-        GreedyParams gp;
-        gp.occ_f = sc.start_f; gp.occ_r = sc.start_r; gp.n_f = n_sf; gp.n_r = n_sr;
-        gp.rec_off = db->d_rec_off; gp.n_rec = db->n_rec; gp.m = mi.m;
-        gp.cnt = (uint32_t *)ctx->bins.p; uint32_t *goff = gp.cnt + n2; gp.off = goff; gp.out = NULL;
-        k_telofind_greedy<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>(gp);
-        corn_count_launch(ctx);
-        CORN_LAUNCH_CHECK(ctx);
-        uint32_t *d_tot = (uint32_t *)d_totals;
-        CORN_TRY(corn_scan_u32(ctx, gp.cnt, goff, n2, d_tot));
-        uint32_t t32 = 0;
-        CORN_TRY(corn_read_small(ctx, &t32, d_tot, 4));
-        n_run = t32;
-        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->runs, (n_run + 1) * sizeof(corn_run_t)));
-        gp.out = (corn_run_t *)ctx->runs.p;
-        k_telofind_greedy<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>(gp);
-        corn_count_launch(ctx);
-        CORN_LAUNCH_CHECK(ctx);
+        if (!mi.bordered) {
+            CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, 2 * ((size_t)db->n_rec + 2) * sizeof(uint32_t)));   // rank tables (bins is free here)
+            AssembleParams ap;
+            ap.ev = ev; ap.totals = d_totals; ap.ev_capacity = (uint32_t)ev_cap; ap.run_capacity = (uint32_t)run_cap;
+            ap.rec_off = db->d_rec_off; ap.n_rec = db->n_rec;
+            ap.rank_f = (uint32_t *)ctx->bins.p; ap.rank_r = ap.rank_f + db->n_rec + 2;
+            ap.out = (corn_run_t *)ctx->runs.p; ap.err = d_err;
+            if (db->n_rec) {
+                k_telofind_ranks<<<(db->n_rec + 1 + 255) / 256, 256, 0, st>>>(ap);
+                k_telofind_assemble<<<ctx->sm_count * 8, 256, 0, st>>>(ap);
+                corn_count_launch(ctx, 2);
+                CORN_LAUNCH_CHECK(ctx);
+            }
+            CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+            CORN_TRY(corn_read_small(ctx, tot, d_totals, 32));
+            if (tot[0] != tot[1] || tot[2] != tot[3])
+                return corn_set_err(ctx, CORN_E_INTERNAL, "start/end counts differ: %u/%u %u/%u", tot[0], tot[1], tot[2], tot[3]);
+            n_run = (uint64_t)tot[0] + tot[2];
+            const uint64_t n_ev = 2 * n_run;
+            if (n_ev <= ev_cap && n_run <= run_cap) break;
+            CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, (n_ev + 4) * sizeof(uint32_t)));
+            CORN_TRY(corn_dbuf_reserve(ctx, &ctx->runs, (n_run + 1) * sizeof(corn_run_t)));
+        } else {
+            // self-overlapping motif: the lists hold every occurrence; greedy pass per (record, strand)
+            CORN_TRY(corn_read_small(ctx, tot, d_totals, 16));
+            if ((uint64_t)tot[0] + tot[2] > ev_cap) {
+                CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, ((uint64_t)tot[0] + tot[2] + 4) * sizeof(uint32_t)));
+                continue;
+            }
+            if (db->n_rec) {
+                const size_t n2 = 2 * (size_t)db->n_rec;
+                CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (2 * n2 + 8) * sizeof(uint32_t)));   // borrowed as a temporary
+                GreedyParams gp;
+                gp.occ_f = ev; gp.occ_r = ev + tot[0]; gp.n_f = tot[0]; gp.n_r = tot[2];
+                gp.rec_off = db->d_rec_off; gp.n_rec = db->n_rec; gp.m = mi.m;
+                gp.cnt = (uint32_t *)ctx->bins.p; uint32_t *goff = gp.cnt + n2; gp.off = goff; gp.out = NULL;
+                k_telofind_greedy<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>(gp);
+                corn_count_launch(ctx);
+                CORN_LAUNCH_CHECK(ctx);
+                uint32_t *d_tot = (uint32_t *)d_totals;
+                CORN_TRY(corn_scan_u32(ctx, gp.cnt, goff, n2, d_tot));
+                uint32_t t32 = 0;
+                CORN_TRY(corn_read_small(ctx, &t32, d_tot, 4));
+                n_run = t32;
+                CORN_TRY(corn_dbuf_reserve(ctx, &ctx->runs, (n_run + 1) * sizeof(corn_run_t)));
+                gp.out = (corn_run_t *)ctx->runs.p;
+                k_telofind_greedy<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>(gp);
+                corn_count_launch(ctx);
+                CORN_LAUNCH_CHECK(ctx);
+            }
+            CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+            break;
+        }
     }
-    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
 
     ctx->last_db = db;
     ctx->last_n_run = n_run;
@@ -479,10 +543,8 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
         }
     }
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-    CORN_CUDA(ctx, cudaStreamSynchronize(st));
-    uint32_t herr = 0;
-    CORN_TRY(corn_read_small(ctx, &herr, d_err, 4));
-    if (herr) return corn_set_err(ctx, CORN_E_INTERNAL, "%u runs failed the start/end consistency check", herr);
+    CORN_CUDA(ctx, cudaEventSynchronize(ctx->ev[5]));
+    if (tot[5]) return corn_set_err(ctx, CORN_E_INTERNAL, "%u runs failed the start/end consistency check", tot[5]);
     float all_ms = 0;
     cudaEventElapsedTime(&ctx->timing.scan_ms, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&all_ms, ctx->ev[3], ctx->ev[4]);
@@ -501,6 +563,7 @@ extern "C" int corn_gpu_telofind(corn_ctx_t *ctx, const corn_batch_t *batch, con
 {
     if (!ctx || !batch || !out) return CORN_E_ARG;
     corn_dbatch_t *db = NULL;
+    corn_ctx_adopt(ctx, NULL);   // retire the previous resident batch first: its buffer is reused by the upload
     CORN_TRY(corn_gpu_upload(ctx, batch, &db));
     const float h2d = ctx->timing.h2d_ms;
     corn_ctx_adopt(ctx, db);   // stays resident for a fused corn_gpu_telowin(hits == NULL)

@@ -111,47 +111,83 @@ __global__ void __launch_bounds__(256) k_bins_from_bitmap(const uint32_t *__rest
     bins[g] = (uint8_t)cnt;
 }
 
-// windows.  One thread per bin index g; bin k of record r is window i = 200k when k < n_win(r).
-// Pass 1 (out == NULL) counts passing windows per block; pass 2 writes them at the scanned offset
-// in ascending (record, i) order.
-__global__ void __launch_bounds__(256) k_windows(const uint8_t *__restrict__ bins, const uint32_t *__restrict__ bin_base,
-                                                 const uint32_t *__restrict__ rec_len, uint32_t n_rec, uint32_t n_bins_total,
-                                                 double thr, uint32_t *blk_cnt, const uint32_t *blk_off, corn_window_t *out)
+// windows.  Bin k of record r is window i = 200k when k < n_win(r).  A thread owns 16 consecutive
+// bin indices (one 16-byte load + the 4 bins that follow); with a positive threshold a stretch of
+// 20 empty bins cannot hold a passing window (car = 0), which is the overwhelmingly common case.
+// Pass 1 records a 16-bit pass mask per thread and counts per block; after the block scan pass 2
+// re-derives only the passing windows and writes them in ascending (record, i) order.
+#define WIN_PER_THREAD 16u
+
+__device__ __forceinline__ bool window_at(const uint8_t *__restrict__ bins, const uint32_t *__restrict__ bin_base,
+                                          const uint32_t *__restrict__ rec_len, uint32_t n_rec, uint32_t g, double thr,
+                                          corn_window_t &w)
+{
+    const uint32_t rec = corn_upper_bound(bin_base, n_rec, g) - 1;
+    const uint32_t k = g - bin_base[rec];
+    const uint32_t len = rec_len[rec];
+    if (k >= nwin_of(len)) return false;
+    const uint8_t *b = bins + g;
+    const uint32_t car = (uint32_t)b[0] + b[1] + b[2] + b[3] + b[4];
+    const uint32_t i = k * 200u;
+    const uint32_t den = (i + 1000u < len) ? 1000u : len - i;
+    w.rec = rec; w.start = i; w.end = i + den; w.car = car;
+    return ((double)car / (double)den) >= thr;           // same IEEE double division as src/telomere_windows.c:37
+}
+
+__global__ void __launch_bounds__(256) k_windows_mark(const uint8_t *__restrict__ bins, const uint32_t *__restrict__ bin_base,
+                                                      const uint32_t *__restrict__ rec_len, uint32_t n_rec, uint32_t n_bins_total,
+                                                      double thr, uint16_t *__restrict__ mask_out, uint32_t *__restrict__ blk_cnt)
 {
     __shared__ uint32_t warp_cnt[8];
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bool pass = false;
-    corn_window_t w;
-    w.rec = w.start = w.end = w.car = 0;
-    if (g < n_bins_total) {
-        const uint32_t rec = corn_upper_bound(bin_base, n_rec, g) - 1;
-        const uint32_t k = g - bin_base[rec];
-        const uint32_t len = rec_len[rec];
-        if (k < nwin_of(len)) {
-            const uint8_t *b = bins + g;
-            const uint32_t car = (uint32_t)b[0] + b[1] + b[2] + b[3] + b[4];
-            const uint32_t i = k * 200u;
-            const uint32_t den = (i + 1000u < len) ? 1000u : len - i;
-            pass = ((double)car / (double)den) >= thr;
-            w.rec = rec; w.start = i; w.end = i + den; w.car = car;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t g0 = t * WIN_PER_THREAD;
+    uint32_t mask = 0;
+    if (g0 < n_bins_total) {
+        const uint4 v = __ldg((const uint4 *)(bins + g0));
+        const uint32_t tail = __ldg((const uint32_t *)(bins + g0 + 16));
+        if (!(thr > 0.0) || (v.x | v.y | v.z | v.w | tail) != 0) {
+            corn_window_t w;
+            for (uint32_t j = 0; j < WIN_PER_THREAD && g0 + j < n_bins_total; ++j)
+                if (window_at(bins, bin_base, rec_len, n_rec, g0 + j, thr, w)) mask |= 1u << j;
         }
+        mask_out[t] = (uint16_t)mask;
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    const uint32_t c = corn_warp_sum(__popc(mask));
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = c;
     __syncthreads();
-    if (!out) {
-        if (threadIdx.x == 0) {
-            uint32_t s = 0;
-            for (int i = 0; i < 8; ++i) s += warp_cnt[i];
-            blk_cnt[blockIdx.x] = s;
-        }
-        return;
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int i = 0; i < 8; ++i) s += warp_cnt[i];
+        blk_cnt[blockIdx.x] = s;
     }
-    if (pass) {
-        uint32_t off = blk_off[blockIdx.x];
-        for (int i = 0; i < warp; ++i) off += warp_cnt[i];
-        out[off + __popc(bal & corn_lanemask_lt())] = w;
+}
+
+__global__ void __launch_bounds__(256) k_windows_write(const uint8_t *__restrict__ bins, const uint32_t *__restrict__ bin_base,
+                                                       const uint32_t *__restrict__ rec_len, uint32_t n_rec, uint32_t n_bins_total,
+                                                       double thr, const uint16_t *__restrict__ mask_in, const uint32_t *__restrict__ blk_cnt,
+                                                       const uint32_t *__restrict__ blk_off, uint32_t capacity, corn_window_t *out)
+{
+    __shared__ uint32_t warp_cnt[8];
+    if (blk_cnt[blockIdx.x] == 0) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t g0 = t * WIN_PER_THREAD;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t mask = g0 < n_bins_total ? mask_in[t] : 0u;
+    const uint32_t k = __popc(mask);
+    const uint32_t incl = corn_warp_iscan(k, lane);
+    if (lane == 31) warp_cnt[warp] = incl;
+    __syncthreads();
+    if (!mask) return;
+    uint32_t off = blk_off[blockIdx.x] + incl - k;
+    for (int i = 0; i < warp; ++i) off += warp_cnt[i];
+    uint32_t m = mask;
+    while (m) {
+        const uint32_t j = __ffs(m) - 1;
+        m &= m - 1;
+        corn_window_t w;
+        window_at(bins, bin_base, rec_len, n_rec, g0 + j, thr, w);
+        if (off < capacity) out[off] = w;
+        ++off;
     }
 }
 
@@ -180,7 +216,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
 
     // ---- record lengths on the device --------------------------------------------------------
     uint32_t n_rec = 0;
-    const uint32_t *d_len = NULL;
+    const uint32_t *d_len = NULL, *h_len = NULL;
     uint64_t n_run = 0;
     const corn_run_t *d_runs = NULL;
     int disjoint = 0;
@@ -190,6 +226,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         if (contigs && contigs->n != ctx->last_db->n_rec) return corn_set_err(ctx, CORN_E_ARG, "contigs->n != records of the last telofind");
         n_rec = ctx->last_db->n_rec;
         d_len = ctx->last_db->d_rec_len;
+        h_len = ctx->last_db->h_rec_len;
         n_run = ctx->last_n_run;
         d_runs = (const corn_run_t *)ctx->runs.p;
         disjoint = ctx->last_runs_disjoint;
@@ -204,6 +241,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         if (n_rec) CORN_CUDA(ctx, cudaMemcpyAsync(dl, contigs->length, sizeof(uint32_t) * n_rec, cudaMemcpyHostToDevice, st));
         if (n_run) CORN_CUDA(ctx, cudaMemcpyAsync(dr, hits->run, sizeof(corn_run_t) * n_run, cudaMemcpyHostToDevice, st));
         d_len = dl; d_runs = dr;
+        h_len = contigs->length;
         disjoint = 0;
     }
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
@@ -222,14 +260,17 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     k_bin_counts<<<gr, 256, 0, st>>>(d_len, nb, n_rec);
     corn_count_launch(ctx);
     CORN_TRY(corn_scan_u32(ctx, nb, bin_base, n_rec, d_tot));
-    uint32_t n_bins_total = 0;
-    CORN_TRY(corn_read_small(ctx, &n_bins_total, d_tot, 4));
+    // the totals are known on the host (lengths are host data): no readback, no sync
+    uint64_t bins64 = 0, words64 = 0;
+    for (uint32_t r = 0; r < n_rec; ++r) { bins64 += nbins_of(h_len[r]); words64 += (h_len[r] + 31u) / 32u + 1u; }
+    if (bins64 > 0xFFFFFF00ull || words64 > 0xFFFFFF00ull) return corn_set_err(ctx, CORN_E_TOOBIG, "too many bins");
+    const uint32_t n_bins_total = (uint32_t)bins64;
     // bin_base[n_rec] = total, so upper_bound over n_rec entries is enough; keep the total on the host
-    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (size_t)n_bins_total + 64));
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (size_t)n_bins_total + 128));
     uint8_t *bins = (uint8_t *)ctx->bins.p;
 
     if (disjoint) {
-        CORN_CUDA(ctx, cudaMemsetAsync(bins, 0, (size_t)n_bins_total + 8, st));
+        CORN_CUDA(ctx, cudaMemsetAsync(bins, 0, (size_t)n_bins_total + 64, st));
         if (n_run) {
             k_bins_from_runs<<<(unsigned)((n_run + 255) / 256), 256, 0, st>>>(d_runs, n_run, bin_base, bins);
             corn_count_launch(ctx);
@@ -242,8 +283,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         k_bit_bases<<<gr, 256, 0, st>>>(d_len, words, n_rec);
         corn_count_launch(ctx);
         CORN_TRY(corn_scan_u32(ctx, words, words, n_rec, d_tot + 1));
-        uint32_t n_words = 0;
-        CORN_TRY(corn_read_small(ctx, &n_words, d_tot + 1, 4));
+        const uint32_t n_words = (uint32_t)words64;
         k_words_to_bits<<<gr, 256, 0, st>>>(words, bit_base, n_rec);
         corn_count_launch(ctx);
         CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bitmap, ((size_t)n_words + 2) * sizeof(uint32_t)));
@@ -254,25 +294,36 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
             corn_count_launch(ctx);
             CORN_LAUNCH_CHECK(ctx);
         }
+        CORN_CUDA(ctx, cudaMemsetAsync(bins + n_bins_total, 0, 64, st));
         k_bins_from_bitmap<<<(n_bins_total + 255) / 256, 256, 0, st>>>((const uint32_t *)ctx->bitmap.p, bit_base, bin_base, d_len, n_rec, n_bins_total, bins);
         corn_count_launch(ctx);
         CORN_LAUNCH_CHECK(ctx);
     }
 
-    // ---- windows: count, scan, write -----------------------------------------------------------
-    const uint32_t n_blk = (n_bins_total + 255) / 256;
-    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->tile_tab, ((size_t)n_blk + 1) * 2 * sizeof(uint32_t) + 64));
+    // ---- windows: mark + count, scan, write (one host sync, at the end) --------------------------
+    const uint32_t n_thr = (n_bins_total + WIN_PER_THREAD - 1) / WIN_PER_THREAD;
+    const uint32_t n_blk = (n_thr + 255) / 256;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->tile_tab, ((size_t)n_blk + 1) * 2 * sizeof(uint32_t) + (size_t)n_thr * sizeof(uint16_t) + 256));
     uint32_t *blk_cnt = (uint32_t *)ctx->tile_tab.p, *blk_off = blk_cnt + n_blk + 1;
-    k_windows<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, blk_cnt, NULL, NULL);
+    uint16_t *wmask = (uint16_t *)(blk_off + n_blk + 1);
+    // output capacity is speculative (grow-only, remembered across calls); the write kernel never
+    // exceeds it and the total tells us afterwards whether a second write pass is needed
+    size_t cap_win = ctx->events.cap / sizeof(corn_window_t);
+    if (cap_win < 65536) { CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, 65536 * sizeof(corn_window_t))); cap_win = ctx->events.cap / sizeof(corn_window_t); }
+    k_windows_mark<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, wmask, blk_cnt);
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
     CORN_TRY(corn_scan_u32(ctx, blk_cnt, blk_off, n_blk, d_tot + 2));
+    corn_window_t *d_out = (corn_window_t *)ctx->events.p;
+    k_windows_write<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, wmask, blk_cnt, blk_off, (uint32_t)cap_win, d_out);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
     uint32_t n_win = 0;
     CORN_TRY(corn_read_small(ctx, &n_win, d_tot + 2, 4));
-    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, ((size_t)n_win + 1) * sizeof(corn_window_t)));   // events list is dead by now
-    corn_window_t *d_out = (corn_window_t *)ctx->events.p;
-    if (n_win) {
-        k_windows<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, blk_cnt, blk_off, d_out);
+    if (n_win > cap_win) {                       // first call with many windows (e.g. threshold 0): grow and rewrite
+        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, ((size_t)n_win + 1) * sizeof(corn_window_t)));
+        d_out = (corn_window_t *)ctx->events.p;
+        k_windows_write<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, wmask, blk_cnt, blk_off, n_win, d_out);
         corn_count_launch(ctx);
         CORN_LAUNCH_CHECK(ctx);
     }
