@@ -69,7 +69,7 @@ extern "C" int corn_gpu_init(int device, corn_ctx_t **out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return CORN_E_CUDA; }
     ctx->stream = ctx->own_stream;
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 16; ++i)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { free(ctx); return CORN_E_CUDA; }
     if (cudaMallocHost(&ctx->h_pinned_small, 4096) != cudaSuccess) { free(ctx); return CORN_E_NOMEM; }
     *out = ctx;
@@ -88,7 +88,7 @@ extern "C" void corn_gpu_destroy(corn_ctx_t *ctx)
     corn_dbuf *bufs[] = { &ctx->cand, &ctx->tile_tab, &ctx->events, &ctx->runs, &ctx->misc, &ctx->scan_tmp,
                           &ctx->bins, &ctx->bitmap, &ctx->wins, &ctx->sd_slots, &ctx->sd_out, &ctx->sd_tab };
     for (size_t i = 0; i < sizeof bufs / sizeof bufs[0]; ++i) dbuf_free(bufs[i]);
-    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->own_stream);
     cudaFreeHost(ctx->h_pinned_small);
     free(ctx);
@@ -175,11 +175,18 @@ void corn_host_free(void *p)
     if (p) cudaFreeHost(p);
 }
 
-extern "C" int corn_gpu_last_timing(const corn_ctx_t *ctx, corn_timing_t *t)
+extern "C" int corn_gpu_last_timing(const corn_ctx_t *ctx_c, corn_timing_t *t)
 {
-    if (!ctx || !t) return CORN_E_ARG;
+    if (!ctx_c || !t) return CORN_E_ARG;
+    corn_ctx *ctx = (corn_ctx *)ctx_c;
+    int r = CORN_OK;
+    if (ctx->pending) {                       // an un-synced telofind_dev(out == NULL): finish it first
+        cudaSetDevice(ctx->device);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return CORN_E_CUDA;
+        r = corn_telofind_resolve(ctx);
+    }
     *t = ctx->timing;
-    return CORN_OK;
+    return r;
 }
 extern "C" uint64_t corn_gpu_total_launches(const corn_ctx_t *ctx) { return ctx ? ctx->total_launches : 0; }
 
@@ -332,7 +339,7 @@ extern "C" void corn_gpu_dbatch_free(corn_ctx_t *ctx, corn_dbatch_t *db)
     if (ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
-        if (ctx->last_db == db) ctx->last_db = NULL;
+        if (ctx->last_db == db) { ctx->last_db = NULL; ctx->pending = 0; }
         if (db->alloc_bytes > ctx->spare_bytes) {            // keep the larger buffer for the next upload
             uint8_t *old = ctx->spare_base;
             ctx->spare_base = db->d_base; ctx->spare_bytes = db->alloc_bytes;

@@ -51,7 +51,7 @@ struct corn_ctx {
     int          device;
     int          sm_count;
     cudaStream_t own_stream, stream;
-    cudaEvent_t  ev[8];
+    cudaEvent_t  ev[16];  // 0-1 upload, 2-5 telofind, 8-11 telowin, 2-6 sdust
     char         err[512];
     corn_timing_t timing;
     uint64_t     total_launches;
@@ -79,6 +79,11 @@ struct corn_ctx {
     corn_dbatch *owned_db;
 
     // state left by the last telofind for a fused telowin(hits == NULL)
+    // (telofind_dev(out == NULL) returns without a host sync: `pending` marks results whose totals
+    // and consistency flags have not been looked at yet; the next sync point resolves them)
+    int       pending;
+    char      pending_motif[256];
+    uint32_t  pending_ev_cap, pending_run_cap;
     const corn_dbatch *last_db;
     uint64_t  last_n_run;
     int       last_runs_disjoint;  // runs cannot overlap (border-free motif, no fwd/rev overlap)
@@ -135,6 +140,10 @@ int corn_scan_u32x4(corn_ctx *ctx, const uint4 *d_in, uint4 *d_out, size_t n, ui
 
 // small synchronous readback through pinned scratch (<= 4 KiB)
 int corn_read_small(corn_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+
+// telofind.cu: look at the totals / flags of an un-synced telofind_dev(out == NULL); repeats the sparse
+// phase synchronously if a speculative buffer was too small.  Stream must be idle (after a sync).
+int corn_telofind_resolve(corn_ctx *ctx);
 
 // pinned host result blocks handed to the caller (freed by corn_gpu_*_free)
 void *corn_host_alloc(size_t bytes);

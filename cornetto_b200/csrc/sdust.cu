@@ -118,6 +118,7 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
 {
     if (W < 3 || W > SD_MAX_W) return corn_set_err(ctx, CORN_E_ARG, "sdust window %d outside [3,%d]", W, SD_MAX_W);
     CORN_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->pending) { CORN_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); CORN_TRY(corn_telofind_resolve(ctx)); }
     cudaStream_t st = ctx->stream;
     const float keep_h2d = ctx->timing.h2d_ms;
     memset(&ctx->timing, 0, sizeof ctx->timing);

@@ -28,6 +28,7 @@ namespace {
 struct ScanParams {
     const uint8_t *seq;        // d_seq (position 0 of the batch)
     uint32_t       n_tiles;
+    uint32_t       n_groups, group_len;   // ticket -> tile permutation (see tile_of_ticket)
     uint32_t      *tile_counter;
     // tile candidate lists, SoA, n_tiles * CORN_TILE_CHUNKS entries each
     uint32_t *c_idx;           // global chunk index (byte position / 32)
@@ -55,7 +56,54 @@ __device__ __forceinline__ bool occ_dev(const uint8_t *p, const uint8_t *__restr
     return true;
 }
 
-// Verify + classify the candidates of one tile.  Called by the warp that scanned the tile.
+// Verify + classify the candidates of one tile.  Called by the warp that scanned the tile,
+// one lane per candidate chunk.  Every candidate bit is verified byte-exactly; whether an
+// occurrence starts (ends) a run is read from the verified mask itself when the position m bytes
+// before (after) lies in the same chunk, and from the bytes otherwise -- so no state is shared
+// between lanes, tiles or GPUs.
+__device__ __forceinline__ uint32_t verify_mask(const uint8_t *chunk, uint32_t cand, const uint8_t *__restrict__ pat, int m)
+{
+    uint32_t v = 0;
+    while (cand) {
+        const int b = __ffs(cand) - 1;
+        cand &= cand - 1;
+        if (occ_dev(chunk + b, pat, m)) v |= 1u << b;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void heads_tails(const uint8_t *chunk, uint32_t v, const uint8_t *__restrict__ pat, int m,
+                                            uint32_t &heads, uint32_t &tails)
+{
+    if (m < 32) {
+        const uint32_t lo = (1u << m) - 1u;                 // bits whose predecessor lies in the previous chunk
+        const uint32_t hi = ~(0xffffffffu >> m);            // bits whose successor lies in the next chunk
+        heads = v & ~(v << m) & ~lo;
+        tails = v & ~(v >> m) & ~hi;
+        uint32_t edge = v & lo;
+        while (edge) {
+            const int b = __ffs(edge) - 1;
+            edge &= edge - 1;
+            if (!occ_dev(chunk + b - m, pat, m)) heads |= 1u << b;
+        }
+        edge = v & hi;
+        while (edge) {
+            const int b = __ffs(edge) - 1;
+            edge &= edge - 1;
+            if (!occ_dev(chunk + b + m, pat, m)) tails |= 1u << b;
+        }
+    } else {
+        heads = tails = 0;
+        uint32_t rest = v;
+        while (rest) {
+            const int b = __ffs(rest) - 1;
+            rest &= rest - 1;
+            if (!occ_dev(chunk + b - m, pat, m)) heads |= 1u << b;
+            if (!occ_dev(chunk + b + m, pat, m)) tails |= 1u << b;
+        }
+    }
+}
+
 __device__ void classify_tile(const ScanParams &P, uint32_t tile, uint32_t cnt, int lane)
 {
     const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
@@ -63,26 +111,13 @@ __device__ void classify_tile(const ScanParams &P, uint32_t tile, uint32_t cnt, 
     uint32_t n_sf = 0, n_ef = 0, n_sr = 0, n_er = 0;
     for (uint32_t e = lane; e < cnt; e += 32) {
         const uint32_t idx = __ldcg(P.c_idx + base + e);
-        uint32_t cf = __ldcg(P.c_a + base + e), cr = __ldcg(P.c_b + base + e);
         const uint8_t *chunk = P.seq + (size_t)idx * CORN_CHUNK_BYTES;
-        uint32_t sf = 0, ef = 0, sr = 0, er = 0;
-        while (cf) {
-            const int b = __ffs(cf) - 1;
-            cf &= cf - 1;
-            const uint8_t *p = chunk + b;
-            if (!occ_dev(p, P.pat, m)) continue;
-            if (P.bordered) { sf |= 1u << b; continue; }
-            if (!occ_dev(p - m, P.pat, m)) sf |= 1u << b;
-            if (!occ_dev(p + m, P.pat, m)) ef |= 1u << b;
-        }
-        while (cr) {
-            const int b = __ffs(cr) - 1;
-            cr &= cr - 1;
-            const uint8_t *p = chunk + b;
-            if (!occ_dev(p, P.pat + 256, m)) continue;
-            if (P.bordered) { sr |= 1u << b; continue; }
-            if (!occ_dev(p - m, P.pat + 256, m)) sr |= 1u << b;
-            if (!occ_dev(p + m, P.pat + 256, m)) er |= 1u << b;
+        const uint32_t vf = verify_mask(chunk, __ldcg(P.c_a + base + e), P.pat, m);
+        const uint32_t vr = verify_mask(chunk, __ldcg(P.c_b + base + e), P.pat + 256, m);
+        uint32_t sf = vf, ef = 0, sr = vr, er = 0;
+        if (!P.bordered) {
+            heads_tails(chunk, vf, P.pat, m, sf, ef);
+            heads_tails(chunk, vr, P.pat + 256, m, sr, er);
         }
         P.c_a[base + e] = sf; P.c_b[base + e] = sr;
         P.c_c[base + e] = ef; P.c_d[base + e] = er;
@@ -94,6 +129,17 @@ __device__ void classify_tile(const ScanParams &P, uint32_t tile, uint32_t cnt, 
         P.tile_cnt[tile] = make_uint4(n_sf, n_ef, n_sr, n_er);
         P.tile_ncand[tile] = cnt;
     }
+}
+
+// Tickets are handed out in increasing order, but consecutive tickets sweep round-robin over
+// n_groups equal slices of the buffer, so the LAST tickets fall at slice ends scattered over the
+// genome rather than on the final bytes of the batch.  Assemblies end in a telomere: those last
+// tiles are the densest ones, and a dense tile claimed last would run alone on an idle GPU.
+__device__ __forceinline__ uint32_t tile_of_ticket(const ScanParams &P, uint32_t t)
+{
+    const uint32_t full = P.n_groups * P.group_len;          // tickets covered by the permutation
+    if (t >= full) return t;                                 // remainder (< n_groups tiles) in natural order
+    return (t % P.n_groups) * P.group_len + t / P.n_groups;
 }
 
 // ordered append of the lanes' non-zero masks to the tile list
@@ -134,6 +180,7 @@ __global__ void __launch_bounds__(256, 5) k_telofind_scan(const ScanParams P)
         if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= P.n_tiles) break;
+        tile = tile_of_ticket(P, tile);
 
         const uint8_t *lane_ptr = P.seq + (size_t)tile * CORN_TILE_BYTES + (size_t)lane * CORN_CHUNK_BYTES;
         const size_t   base = (size_t)tile * CORN_TILE_CHUNKS;
@@ -194,6 +241,7 @@ __global__ void __launch_bounds__(256) k_telofind_scan_generic(const ScanParams 
         if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= P.n_tiles) break;
+        tile = tile_of_ticket(P, tile);
         const uint8_t *lane_ptr = P.seq + (size_t)tile * CORN_TILE_BYTES + (size_t)lane * CORN_CHUNK_BYTES;
         const size_t   base = (size_t)tile * CORN_TILE_CHUNKS;
         const uint32_t chunk0 = tile * CORN_TILE_CHUNKS + lane;
@@ -290,17 +338,26 @@ struct AssembleParams {
     uint32_t *err;
 };
 
-// rank_f[r] = #forward starts < rec_off[r]  (r = 0..n_rec), same for reverse: one thread per record
-__global__ void __launch_bounds__(256) k_telofind_ranks(const AssembleParams P)
+// rank_f[r] = #forward run starts before rec_off[r] (r = 0..n_rec), same for reverse.  Records are
+// chunk aligned, so this is the tile prefix plus the starts of the tile's candidate chunks that lie
+// before the record: three dependent loads instead of a binary search over the event lists.
+__global__ void __launch_bounds__(256) k_telofind_ranks(const AssembleParams P, const uint4 *__restrict__ tile_off,
+                                                        const uint32_t *__restrict__ tile_ncand, const uint32_t *__restrict__ c_idx,
+                                                        const uint32_t *__restrict__ c_sf, const uint32_t *__restrict__ c_sr, uint32_t n_tiles)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r > P.n_rec) return;
     const uint4 tot = *P.totals;
-    if ((uint64_t)tot.x + tot.y + tot.z + tot.w > P.ev_capacity) return;
-    const uint32_t *start_f = P.ev, *start_r = P.ev + tot.x + tot.y;
     const uint32_t pos = P.rec_off[r];
-    P.rank_f[r] = corn_lower_bound(start_f, tot.x, pos);
-    P.rank_r[r] = corn_lower_bound(start_r, tot.z, pos);
+    const uint32_t tile = pos / CORN_TILE_BYTES;
+    if (tile >= n_tiles) { P.rank_f[r] = tot.x; P.rank_r[r] = tot.z; return; }
+    const uint4 off = tile_off[tile];
+    uint32_t f = off.x, v = off.z;
+    const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
+    const uint32_t n = tile_ncand[tile], chunk = pos / CORN_CHUNK_BYTES;
+    for (uint32_t e = 0; e < n && c_idx[base + e] < chunk; ++e) { f += __popc(c_sf[base + e]); v += __popc(c_sr[base + e]); }
+    P.rank_f[r] = f;
+    P.rank_r[r] = v;
 }
 
 __global__ void __launch_bounds__(256) k_telofind_assemble(const AssembleParams P)
@@ -387,8 +444,13 @@ static int scan_grid(corn_ctx *ctx, K kernel)
     return ctx->sm_count * per_sm;
 }
 
-static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif, corn_hits_t *out)
+static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif, corn_hits_t *out, int allow_async)
 {
+    if (ctx->pending) {                            // settle an earlier un-synced call before reusing its buffers
+        CORN_CUDA(ctx, cudaSetDevice(ctx->device));
+        CORN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CORN_TRY(corn_telofind_resolve(ctx));
+    }
     if (!motif || !motif[0]) return corn_set_err(ctx, CORN_E_ARG, "empty motif");
     if (strlen(motif) > 255) return corn_set_err(ctx, CORN_E_ARG, "motif longer than 255");
     CORN_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -410,6 +472,8 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
     ScanParams sp;
     sp.seq = db->d_seq;
     sp.n_tiles = n_tiles;
+    sp.n_groups = n_tiles >= 4096 ? 61u : 1u;               // odd, unrelated to contig counts
+    sp.group_len = n_tiles / sp.n_groups;
     sp.c_idx = cand; sp.c_a = cand + n_slots; sp.c_b = cand + 2 * n_slots; sp.c_c = cand + 3 * n_slots; sp.c_d = cand + 4 * n_slots;
     sp.tile_cnt = (uint4 *)ctx->tile_tab.p;
     uint4 *tile_off = sp.tile_cnt + n_tiles;
@@ -480,12 +544,25 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
             ap.rank_f = (uint32_t *)ctx->bins.p; ap.rank_r = ap.rank_f + db->n_rec + 2;
             ap.out = (corn_run_t *)ctx->runs.p; ap.err = d_err;
             if (db->n_rec) {
-                k_telofind_ranks<<<(db->n_rec + 1 + 255) / 256, 256, 0, st>>>(ap);
+                k_telofind_ranks<<<(db->n_rec + 1 + 255) / 256, 256, 0, st>>>(ap, tile_off, sp.tile_ncand, sp.c_idx, sp.c_a, sp.c_b, n_tiles);
                 k_telofind_assemble<<<ctx->sm_count * 8, 256, 0, st>>>(ap);
                 corn_count_launch(ctx, 2);
                 CORN_LAUNCH_CHECK(ctx);
             }
             CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+            if (!out && attempt == 0 && allow_async) {
+                // resident batch, results stay on the device: return without a host sync.  The totals and
+                // the consistency flags are looked at by the next call that synchronises
+                // (corn_gpu_telowin(hits == NULL), corn_gpu_last_timing, ...): corn_telofind_resolve().
+                ctx->pending = 1;
+                snprintf(ctx->pending_motif, sizeof ctx->pending_motif, "%s", motif);
+                ctx->pending_ev_cap = (uint32_t)ev_cap; ctx->pending_run_cap = (uint32_t)run_cap;
+                ctx->last_db = db;
+                ctx->last_n_run = 0;
+                ctx->last_runs_disjoint = !mi.strands_overlap;
+                ctx->last_motif_len = mi.m;
+                return CORN_OK;
+            }
             CORN_TRY(corn_read_small(ctx, tot, d_totals, 32));
             if (tot[0] != tot[1] || tot[2] != tot[3])
                 return corn_set_err(ctx, CORN_E_INTERNAL, "start/end counts differ: %u/%u %u/%u", tot[0], tot[1], tot[2], tot[3]);
@@ -553,10 +630,35 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
     return CORN_OK;
 }
 
+int corn_telofind_resolve(corn_ctx *ctx)
+{
+    if (!ctx->pending) return CORN_OK;
+    ctx->pending = 0;
+    uint32_t tot[8];
+    CORN_TRY(corn_read_small(ctx, tot, ctx->misc.p, 32));
+    const uint64_t n_run = (uint64_t)tot[0] + tot[2];
+    if (tot[0] != tot[1] || tot[2] != tot[3])
+        return corn_set_err(ctx, CORN_E_INTERNAL, "start/end counts differ: %u/%u %u/%u", tot[0], tot[1], tot[2], tot[3]);
+    if (2 * n_run > ctx->pending_ev_cap || n_run > ctx->pending_run_cap) {
+        // a speculative buffer was too small: nothing was written; run again, synchronously
+        char motif[256];
+        snprintf(motif, sizeof motif, "%s", ctx->pending_motif);
+        return telofind_run(ctx, ctx->last_db, motif, NULL, 0);
+    }
+    if (tot[5]) return corn_set_err(ctx, CORN_E_INTERNAL, "%u runs failed the start/end consistency check", tot[5]);
+    ctx->last_n_run = n_run;
+    ctx->timing.out_bytes = n_run * sizeof(corn_run_t);
+    float all_ms = 0;
+    cudaEventElapsedTime(&ctx->timing.scan_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&all_ms, ctx->ev[3], ctx->ev[4]);
+    ctx->timing.post_ms = all_ms;
+    return CORN_OK;
+}
+
 extern "C" int corn_gpu_telofind_dev(corn_ctx_t *ctx, const corn_dbatch_t *db, const char *motif, corn_hits_t *out)
 {
     if (!ctx || !db) return CORN_E_ARG;
-    return telofind_run(ctx, db, motif, out);
+    return telofind_run(ctx, db, motif, out, 1);
 }
 
 extern "C" int corn_gpu_telofind(corn_ctx_t *ctx, const corn_batch_t *batch, const char *motif, corn_hits_t *out)
@@ -568,7 +670,7 @@ extern "C" int corn_gpu_telofind(corn_ctx_t *ctx, const corn_batch_t *batch, con
     const float h2d = ctx->timing.h2d_ms;
     corn_ctx_adopt(ctx, db);   // stays resident for a fused corn_gpu_telowin(hits == NULL)
     ctx->timing.h2d_ms = h2d;
-    return telofind_run(ctx, db, motif, out);
+    return telofind_run(ctx, db, motif, out, 1);
 }
 
 extern "C" void corn_gpu_hits_free(corn_hits_t *hits)

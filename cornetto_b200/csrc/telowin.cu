@@ -48,19 +48,23 @@ __device__ __forceinline__ void bin_add(uint8_t *bins, uint32_t bin, uint32_t am
 }
 
 // disjoint runs -> bins.  One thread per run.
-__global__ void __launch_bounds__(256) k_bins_from_runs(const corn_run_t *__restrict__ runs, uint64_t n_run,
+// (the run count comes from device memory when the producing telofind has not been synced yet)
+__global__ void __launch_bounds__(256) k_bins_from_runs(const corn_run_t *__restrict__ runs, uint64_t n_run_host,
+                                                        const uint4 *__restrict__ totals, uint32_t run_capacity,
                                                         const uint32_t *__restrict__ bin_base, uint8_t *bins)
 {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_run) return;
-    const corn_run_t r = runs[t];
-    const uint32_t b0 = bin_base[r.rec];
-    uint32_t s = r.start;
-    while (s < r.end) {
-        const uint32_t bin = s / 200u;
-        const uint32_t lim = min(r.end, (bin + 1u) * 200u);
-        bin_add(bins, b0 + bin, lim - s);
-        s = lim;
+    uint64_t n_run = n_run_host;
+    if (totals) { const uint4 t4 = *totals; n_run = (uint64_t)t4.x + t4.z; if (n_run > run_capacity) return; }
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_run; t += (uint64_t)gridDim.x * blockDim.x) {
+        const corn_run_t r = runs[t];
+        const uint32_t b0 = bin_base[r.rec];
+        uint32_t s = r.start;
+        while (s < r.end) {
+            const uint32_t bin = s / 200u;
+            const uint32_t lim = min(r.end, (bin + 1u) * 200u);
+            bin_add(bins, b0 + bin, lim - s);
+            s = lim;
+        }
     }
 }
 
@@ -134,18 +138,38 @@ __device__ __forceinline__ bool window_at(const uint8_t *__restrict__ bins, cons
     return ((double)car / (double)den) >= thr;           // same IEEE double division as src/telomere_windows.c:37
 }
 
+// car_min_full: smallest integer car with (double)car / 1000.0 >= thr, found on the host with the
+// same double arithmetic (0 if every count passes, > 1000 if none can): full windows (den = 1000)
+// are then decided by integer compares on sliding 5-bin sums.  Threads whose bins come within a
+// few bins of a record end (partial windows, pad bins) take the exact per-window path.
 __global__ void __launch_bounds__(256) k_windows_mark(const uint8_t *__restrict__ bins, const uint32_t *__restrict__ bin_base,
                                                       const uint32_t *__restrict__ rec_len, uint32_t n_rec, uint32_t n_bins_total,
-                                                      double thr, uint16_t *__restrict__ mask_out, uint32_t *__restrict__ blk_cnt)
+                                                      double thr, uint32_t car_min_full, uint16_t *__restrict__ mask_out, uint32_t *__restrict__ blk_cnt)
 {
     __shared__ uint32_t warp_cnt[8];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t g0 = t * WIN_PER_THREAD;
     uint32_t mask = 0;
     if (g0 < n_bins_total) {
-        const uint4 v = __ldg((const uint4 *)(bins + g0));
-        const uint32_t tail = __ldg((const uint32_t *)(bins + g0 + 16));
-        if (!(thr > 0.0) || (v.x | v.y | v.z | v.w | tail) != 0) {
+        const uint32_t rec = corn_upper_bound(bin_base, n_rec, g0) - 1;
+        const uint32_t k0 = g0 - bin_base[rec];
+        const uint32_t len = rec_len[rec];
+        // windows k0 .. k0+15 all full and inside this record?
+        const bool interior = len > 1000u && (uint64_t)(k0 + WIN_PER_THREAD - 1) * 200u + 1000u < len;
+        if (interior) {
+            const uint4 v = __ldg((const uint4 *)(bins + g0));
+            const uint32_t tail = __ldg((const uint32_t *)(bins + g0 + 16));
+            const uint32_t w[5] = { v.x, v.y, v.z, v.w, tail };
+            uint32_t b[20];
+#pragma unroll
+            for (int i = 0; i < 20; ++i) b[i] = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            uint32_t car = b[0] + b[1] + b[2] + b[3] + b[4];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (car >= car_min_full) mask |= 1u << j;
+                if (j < 15) car += b[j + 5] - b[j];
+            }
+        } else {
             corn_window_t w;
             for (uint32_t j = 0; j < WIN_PER_THREAD && g0 + j < n_bins_total; ++j)
                 if (window_at(bins, bin_base, rec_len, n_rec, g0 + j, thr, w)) mask |= 1u << j;
@@ -211,7 +235,10 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     if (!ctx || !out) return CORN_E_ARG;
     CORN_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    memset(&ctx->timing, 0, sizeof ctx->timing);
+    if (hits && ctx->pending) {                    // unrelated call: settle the outstanding telofind first
+        CORN_CUDA(ctx, cudaStreamSynchronize(st));
+        CORN_TRY(corn_telofind_resolve(ctx));
+    }
     out->win = NULL; out->n_win = 0; out->_owner = NULL;
 
     // ---- record lengths on the device --------------------------------------------------------
@@ -220,7 +247,9 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     uint64_t n_run = 0;
     const corn_run_t *d_runs = NULL;
     int disjoint = 0;
-    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    const int pending = !hits && ctx->pending;     // fused call right after an un-synced telofind_dev(out == NULL)
+    const corn_timing_t t_find = ctx->timing;      // its launch count so far (times are filled in by the resolve below)
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
     if (!hits) {
         if (!ctx->last_db) return corn_set_err(ctx, CORN_E_STATE, "telowin(hits == NULL) needs a preceding telofind on this context");
         if (contigs && contigs->n != ctx->last_db->n_rec) return corn_set_err(ctx, CORN_E_ARG, "contigs->n != records of the last telofind");
@@ -230,7 +259,14 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         n_run = ctx->last_n_run;
         d_runs = (const corn_run_t *)ctx->runs.p;
         disjoint = ctx->last_runs_disjoint;
+        if (pending && !disjoint) {                // the general path sizes its work from the run count: settle first
+            CORN_CUDA(ctx, cudaStreamSynchronize(st));
+            CORN_TRY(corn_telofind_resolve(ctx));
+            return corn_gpu_telowin(ctx, hits, contigs, thr, out);
+        }
+        memset(&ctx->timing, 0, sizeof ctx->timing);
     } else {
+        memset(&ctx->timing, 0, sizeof ctx->timing);
         if (!contigs || (contigs->n && !contigs->length) || (hits->n_run && !hits->run)) return CORN_E_ARG;
         n_rec = contigs->n;
         n_run = hits->n_run;
@@ -244,7 +280,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         h_len = contigs->length;
         disjoint = 0;
     }
-    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[9], st));
     if (n_rec == 0) { CORN_CUDA(ctx, cudaStreamSynchronize(st)); return CORN_OK; }
 
     // ---- tables ---------------------------------------------------------------------------------
@@ -271,8 +307,10 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
 
     if (disjoint) {
         CORN_CUDA(ctx, cudaMemsetAsync(bins, 0, (size_t)n_bins_total + 64, st));
-        if (n_run) {
-            k_bins_from_runs<<<(unsigned)((n_run + 255) / 256), 256, 0, st>>>(d_runs, n_run, bin_base, bins);
+        if (n_run || pending) {
+            const unsigned g = pending ? (unsigned)ctx->sm_count * 8u : (unsigned)((n_run + 255) / 256);
+            k_bins_from_runs<<<g, 256, 0, st>>>(d_runs, n_run, pending ? (const uint4 *)ctx->misc.p : (const uint4 *)NULL,
+                                                 ctx->pending_run_cap, bin_base, bins);
             corn_count_launch(ctx);
             CORN_LAUNCH_CHECK(ctx);
         }
@@ -310,7 +348,10 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     // exceeds it and the total tells us afterwards whether a second write pass is needed
     size_t cap_win = ctx->events.cap / sizeof(corn_window_t);
     if (cap_win < 65536) { CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, 65536 * sizeof(corn_window_t))); cap_win = ctx->events.cap / sizeof(corn_window_t); }
-    k_windows_mark<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, wmask, blk_cnt);
+    // integer form of the test for full windows, derived with the reference's own double expression
+    uint32_t car_min_full = 1001;
+    for (uint32_t c = 0; c <= 1000; ++c) if ((double)c / (double)1000 >= thr) { car_min_full = c; break; }
+    k_windows_mark<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, car_min_full, wmask, blk_cnt);
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
     CORN_TRY(corn_scan_u32(ctx, blk_cnt, blk_off, n_blk, d_tot + 2));
@@ -327,7 +368,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         corn_count_launch(ctx);
         CORN_LAUNCH_CHECK(ctx);
     }
-    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[10], st));
     out->n_win = n_win;
     if (n_win) {
         out->win = (corn_window_t *)corn_host_alloc((size_t)n_win * sizeof(corn_window_t));
@@ -335,12 +376,29 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         out->_owner = out->win;
         CORN_CUDA(ctx, cudaMemcpyAsync(out->win, d_out, (size_t)n_win * sizeof(corn_window_t), cudaMemcpyDeviceToHost, st));
     }
-    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[11], st));
     CORN_CUDA(ctx, cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&ctx->timing.post_ms, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[8], ctx->ev[9]);
+    cudaEventElapsedTime(&ctx->timing.post_ms, ctx->ev[9], ctx->ev[10]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[10], ctx->ev[11]);
     ctx->timing.out_bytes = (uint64_t)n_win * sizeof(corn_window_t);
+    if (pending) {
+        // the stream is idle now: look at the telofind totals/flags that were left unchecked
+        const corn_timing_t t_win = ctx->timing;
+        ctx->timing = t_find;
+        const uint64_t before = ctx->total_launches;
+        int r = corn_telofind_resolve(ctx);
+        if (r != CORN_OK) { corn_gpu_windows_free(out); return r; }
+        if (ctx->total_launches != before) {       // a buffer had been too small and the runs were rebuilt: redo the windows
+            corn_gpu_windows_free(out);
+            return corn_gpu_telowin(ctx, hits, contigs, thr, out);
+        }
+        // report the fused step as one: scan = the telofind scan kernel, post = every other kernel
+        ctx->timing.post_ms += t_win.post_ms;
+        ctx->timing.d2h_ms += t_win.d2h_ms;
+        ctx->timing.launches += t_win.launches;
+        ctx->timing.out_bytes += t_win.out_bytes;
+    }
     return CORN_OK;
 }
 

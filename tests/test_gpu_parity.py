@@ -272,3 +272,31 @@ def test_abi_errors(ctx, capi):
     assert len(ctx.telofind(e)) == 0
     iv, first = ctx.sdust(e)
     assert len(iv) == 0 and list(first) == [0]
+
+
+def test_abi_async_fused_matches_sync(ctx, capi):
+    """telofind_dev(out=NULL) returns without a host sync; the fused telowin(hits=NULL) settles it.
+    Results must equal the synchronous host-buffer path, also when the speculative event/run
+    buffers are too small (dense batch) and the sparse phase has to be repeated."""
+    thr = 0.4 * 0.999 ** 6
+    cases = [
+        [s for _, s in synth.assembly(51, [300_000, 80_000, 1200, 999], telo=(100, 600))],
+        [np.frombuffer(b"TTAGGGA" * 40_000, dtype=np.uint8), np.frombuffer(b"CCCTAAG" * 30_000, dtype=np.uint8)],   # one run per 7 bases
+    ]
+    for recs in cases:
+        hb = capi.HostBatch(recs)
+        want_runs = ctx.telofind(hb, "TTAGGG")
+        want_wins = ctx.telowin(thr)
+        c2 = capi.Context(0)                      # fresh context: buffers start at their speculative sizes
+        db = c2.upload(hb)
+        for _ in range(3):
+            assert c2.telofind_dev(db, "TTAGGG", fetch=False) is None
+            wins = c2.telowin(thr)
+            assert len(wins) == len(want_wins) and (wins == want_wins).all()
+            t = c2.timing()
+            assert t["scan_ms"] > 0 and t["launches"] >= 8
+        runs = c2.telofind_dev(db, "TTAGGG", fetch=True)
+        assert len(runs) == len(want_runs) and (runs == want_runs).all()
+        c2.free(db)
+        c2.close()
+        hb.close()
