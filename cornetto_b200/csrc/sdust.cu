@@ -125,7 +125,19 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     ctx->timing.h2d_ms = keep_h2d;
     out->iv = NULL; out->rec_first = NULL; out->n_iv = 0; out->n_rec = db->n_rec; out->_owner = NULL;
 
+    // chunk length: 4096 bases for large batches (5 % warm-up overhead); smaller when that would leave
+    // the GPU with fewer than ~3 waves of threads.  Results do not depend on it.
+    const int rows = ((W + 3) >> 2) + 32 + W;
+    const size_t smem = (size_t)rows * SD_BLOCK * 4;
+    CORN_CUDA(ctx, cudaFuncSetAttribute(k_sdust_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sdust_scan, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
     int C = 4096;
+    {
+        const uint64_t slots = (uint64_t)ctx->sm_count * blocks_per_sm * SD_BLOCK;
+        const uint64_t want = db->n_bases / (slots * 3 + 1);
+        if (want < 4096) C = (int)(want < 1024 ? 1024 : want / 64 * 64);
+    }
     if (const char *e = getenv("CORNETTO_SDUST_CHUNK")) { int v = atoi(e); if (v >= 16 && v <= (1 << 20)) C = v; }
     const uint32_t n_rec = db->n_rec;
     const uint32_t cap = (uint32_t)(C + 2 * W) / 4 + 2;
@@ -163,9 +175,6 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     sp.seq = db->d_seq; sp.rec_off = db->d_rec_off; sp.rec_len = db->d_rec_len; sp.chunk_base = chunk_base;
     sp.n_rec = n_rec; sp.n_chunks = n_chunks; sp.T = T; sp.W = W; sp.C = C; sp.cap = cap;
     sp.slots = (uint64_t *)ctx->sd_slots.p; sp.cnt = cnt; sp.err = d_err;
-    const int rows = ((W + 3) >> 2) + 32 + W;
-    const size_t smem = (size_t)rows * SD_BLOCK * 4;
-    CORN_CUDA(ctx, cudaFuncSetAttribute(k_sdust_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     k_sdust_scan<<<(n_chunks + SD_BLOCK - 1) / SD_BLOCK, SD_BLOCK, smem, st>>>(sp);
     corn_count_launch(ctx);

@@ -111,13 +111,14 @@ struct sd_state {
     int L, rw, rv;
     int nslot;           // valid slots
     int pstart;          // every valid slot has start >= pstart
+    int pslot;           // pstart mod W, kept incrementally (no integer division in the per-base path)
     int l;               // length of the current A/C/G/T run
     unsigned t;          // current triplet
 };
 
 SD_HD void sd_reset(sd_state &s, const sd_mem &m, int W)
 {
-    s.wn = s.whead = s.L = s.rw = s.rv = s.nslot = s.pstart = s.l = 0;
+    s.wn = s.whead = s.L = s.rw = s.rv = s.nslot = s.pstart = s.pslot = s.l = 0;
     s.t = 0;
     for (int i = 0; i < 64; ++i) { SD_U8(m.cw, i) = 0; SD_U8(m.cv, i) = 0; }
     for (int i = 0; i < W; ++i) SD_U32(m.slot, i) = 0;
@@ -173,22 +174,27 @@ SD_HD void sd_shift_window(sd_state &s, const sd_mem &m, int t, int T, int W)
 // is saved and every slot below `start` is dropped -- including, when `start` advanced by more
 // than one (it does by two at a flush with l >= W), slots that were never saved.  That loss is
 // reference behaviour and is reproduced here.
+SD_HD void sd_set_pstart(sd_state &s, int start, int W)
+{
+    // called only when no slot is valid: a jump of `start` (after an N) is the one place a division remains
+    const int d = start - s.pstart;
+    if (d >= 0 && d < W) { s.pslot += d; if (s.pslot >= W) s.pslot -= W; }
+    else s.pslot = (int)((uint32_t)start % (uint32_t)W);
+    s.pstart = start;
+}
+
 SD_HD void sd_save(sd_state &s, const sd_mem &m, sd_sink &k, int start, int W)
 {
-    if (s.nslot == 0) { s.pstart = start; return; }
-    while (s.pstart < start && !(SD_U32(m.slot, (uint32_t)s.pstart % (uint32_t)W) & SD_SLOT_VALID)) ++s.pstart;
+    if (s.nslot == 0) { if (s.pstart != start) sd_set_pstart(s, start, W); return; }
+    while (s.pstart < start && !(SD_U32(m.slot, s.pslot) & SD_SLOT_VALID)) { ++s.pstart; if (++s.pslot == W) s.pslot = 0; }
     if (s.pstart >= start) return;                       // smallest start >= start: nothing to do
-    {
-        const uint32_t v = SD_U32(m.slot, (uint32_t)s.pstart % (uint32_t)W);
-        sd_sink_put(k, s.pstart, s.pstart + sd_slot_flen(v));
-    }
+    sd_sink_put(k, s.pstart, s.pstart + sd_slot_flen(SD_U32(m.slot, s.pslot)));
     while (s.pstart < start) {
-        const uint32_t si = (uint32_t)s.pstart % (uint32_t)W;
-        if (SD_U32(m.slot, si) & SD_SLOT_VALID) {
-            SD_U32(m.slot, si) = 0;
-            if (--s.nslot == 0) { s.pstart = start; return; }
+        if (SD_U32(m.slot, s.pslot) & SD_SLOT_VALID) {
+            SD_U32(m.slot, s.pslot) = 0;
+            if (--s.nslot == 0) { sd_set_pstart(s, start, W); return; }
         }
-        ++s.pstart;
+        ++s.pstart; if (++s.pslot == W) s.pslot = 0;
     }
 }
 
@@ -204,23 +210,30 @@ SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W
 {
     int r = s.rv, max_r = 0, max_l = 0;
     const int i0 = s.wn - s.L - 1;
+    // slot of window index i is (start + i) mod W; every valid slot has start >= pstart >= ... so the
+    // base is derived from the tracked pstart/pslot pair instead of a division
+    int base = s.pslot + (start - s.pstart);
+    if (base >= W || base < 0) base = (int)((uint32_t)start % (uint32_t)W);
     // entries whose start lies right of the first candidate also count for the maximum (the
     // reference's j-loop always starts from the largest start, :113)
     if (s.nslot)
         for (int i = s.wn - 1; i > i0; --i) {
-            const uint32_t v = SD_U32(m.slot, (uint32_t)(i + start) % (uint32_t)W);
+            int si = base + i; if (si >= W) si -= W;
+            const uint32_t v = SD_U32(m.slot, si);
             if (v & SD_SLOT_VALID) {
                 const int pr = sd_slot_r(v), pl = sd_slot_l(v);
                 if (max_r == 0 || pr * max_l > max_r * pl) { max_r = pr; max_l = pl; }
             }
         }
+    int ri = sd_ring_idx(s, i0 < 0 ? 0 : i0, W);          // ring position of window index i, walked downwards
     for (int i = i0; i >= 0; --i) {
-        const int t = SD_U8(m.ring, sd_ring_idx(s, i, W));
+        const int t = SD_U8(m.ring, ri);
+        if (--ri < 0) ri = W - 1;
         const int c = SD_U8(m.cv, t);
         r += c;
         SD_U8(m.cv, t) = (uint8_t)(c + 1);          // temporary; undone below (the reference copies cv)
         const int new_r = r, new_l = s.wn - i - 1;
-        const uint32_t si = (uint32_t)(i + start) % (uint32_t)W;
+        int si = base + i; if (si >= W) si -= W;
         const uint32_t v = SD_U32(m.slot, si);
         if (v & SD_SLOT_VALID) {                      // entries with this start join the running maximum
             const int pr = sd_slot_r(v), pl = sd_slot_l(v);
@@ -234,8 +247,10 @@ SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W
             }
         }
     }
+    ri = sd_ring_idx(s, i0 < 0 ? 0 : i0, W);
     for (int i = i0; i >= 0; --i) {
-        const int t = SD_U8(m.ring, sd_ring_idx(s, i, W));
+        const int t = SD_U8(m.ring, ri);
+        if (--ri < 0) ri = W - 1;
         SD_U8(m.cv, t) = (uint8_t)(SD_U8(m.cv, t) - 1);
     }
 }
@@ -287,7 +302,7 @@ SD_HD void sd_run_chunk(Fetch &fetch, int l_seq, int c0, int c1, int T, int W, c
     sd_state s;
     sd_reset(s, m, W);
     const int p0 = sd_warm_start(fetch, c0, W);
-    s.pstart = p0;
+    s.pstart = p0; s.pslot = (int)((uint32_t)p0 % (uint32_t)W);
     const int stop = c1 < l_seq ? c1 : l_seq;
     for (int i = p0; i < stop; ++i) {
         if (i == c0) k.on = 1;

@@ -49,11 +49,23 @@ __device__ __forceinline__ void ld256(const uint8_t *p, uint32_t w[8])
                  : "l"(p));
 }
 
+// exact occurrence test with early exit (generic matcher: most positions fail on the first byte)
 __device__ __forceinline__ bool occ_dev(const uint8_t *p, const uint8_t *__restrict__ pat, int m)
 {
     for (int d = 0; d < m; ++d)
         if (corn_fold(__ldg(p + d)) != __ldg(pat + d)) return false;
     return true;
+}
+
+// exact occurrence test without early exit: the byte loads are independent, so a candidate costs one
+// load latency instead of m chained ones (candidates are true occurrences almost always, and a
+// dense tile -- a telomere -- is verified by a single warp)
+__device__ __forceinline__ bool occ_all(const uint8_t *p, const uint8_t *__restrict__ pat, int m)
+{
+    uint32_t diff = 0;
+#pragma unroll 8
+    for (int d = 0; d < m; ++d) diff |= (uint32_t)(corn_fold(__ldg(p + d)) ^ __ldg(pat + d));
+    return diff == 0;
 }
 
 // Verify + classify the candidates of one tile.  Called by the warp that scanned the tile,
@@ -67,7 +79,7 @@ __device__ __forceinline__ uint32_t verify_mask(const uint8_t *chunk, uint32_t c
     while (cand) {
         const int b = __ffs(cand) - 1;
         cand &= cand - 1;
-        if (occ_dev(chunk + b, pat, m)) v |= 1u << b;
+        if (occ_all(chunk + b, pat, m)) v |= 1u << b;
     }
     return v;
 }
@@ -84,13 +96,13 @@ __device__ __forceinline__ void heads_tails(const uint8_t *chunk, uint32_t v, co
         while (edge) {
             const int b = __ffs(edge) - 1;
             edge &= edge - 1;
-            if (!occ_dev(chunk + b - m, pat, m)) heads |= 1u << b;
+            if (!occ_all(chunk + b - m, pat, m)) heads |= 1u << b;
         }
         edge = v & hi;
         while (edge) {
             const int b = __ffs(edge) - 1;
             edge &= edge - 1;
-            if (!occ_dev(chunk + b + m, pat, m)) tails |= 1u << b;
+            if (!occ_all(chunk + b + m, pat, m)) tails |= 1u << b;
         }
     } else {
         heads = tails = 0;
@@ -98,8 +110,8 @@ __device__ __forceinline__ void heads_tails(const uint8_t *chunk, uint32_t v, co
         while (rest) {
             const int b = __ffs(rest) - 1;
             rest &= rest - 1;
-            if (!occ_dev(chunk + b - m, pat, m)) heads |= 1u << b;
-            if (!occ_dev(chunk + b + m, pat, m)) tails |= 1u << b;
+            if (!occ_all(chunk + b - m, pat, m)) heads |= 1u << b;
+            if (!occ_all(chunk + b + m, pat, m)) tails |= 1u << b;
         }
     }
 }
@@ -139,7 +151,10 @@ __device__ __forceinline__ uint32_t tile_of_ticket(const ScanParams &P, uint32_t
 {
     const uint32_t full = P.n_groups * P.group_len;          // tickets covered by the permutation
     if (t >= full) return t;                                 // remainder (< n_groups tiles) in natural order
-    return (t % P.n_groups) * P.group_len + t / P.n_groups;
+    // (+ half a slice: the last tickets land in the middle of the slices, away from both ends of the batch)
+    uint32_t j = t / P.n_groups + P.group_len / 2;
+    if (j >= P.group_len) j -= P.group_len;
+    return (t % P.n_groups) * P.group_len + j;
 }
 
 // ordered append of the lanes' non-zero masks to the tile list
@@ -345,19 +360,23 @@ __global__ void __launch_bounds__(256) k_telofind_ranks(const AssembleParams P, 
                                                         const uint32_t *__restrict__ tile_ncand, const uint32_t *__restrict__ c_idx,
                                                         const uint32_t *__restrict__ c_sf, const uint32_t *__restrict__ c_sr, uint32_t n_tiles)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per record
+    const int lane = threadIdx.x & 31;
     if (r > P.n_rec) return;
     const uint4 tot = *P.totals;
     const uint32_t pos = P.rec_off[r];
     const uint32_t tile = pos / CORN_TILE_BYTES;
-    if (tile >= n_tiles) { P.rank_f[r] = tot.x; P.rank_r[r] = tot.z; return; }
-    const uint4 off = tile_off[tile];
-    uint32_t f = off.x, v = off.z;
-    const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
-    const uint32_t n = tile_ncand[tile], chunk = pos / CORN_CHUNK_BYTES;
-    for (uint32_t e = 0; e < n && c_idx[base + e] < chunk; ++e) { f += __popc(c_sf[base + e]); v += __popc(c_sr[base + e]); }
-    P.rank_f[r] = f;
-    P.rank_r[r] = v;
+    uint32_t f = 0, v = 0, f0 = tot.x, v0 = tot.z;
+    if (tile < n_tiles) {
+        const uint4 off = tile_off[tile];
+        f0 = off.x; v0 = off.z;
+        const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
+        const uint32_t n = tile_ncand[tile], chunk = pos / CORN_CHUNK_BYTES;
+        for (uint32_t e = lane; e < n; e += 32)
+            if (c_idx[base + e] < chunk) { f += __popc(c_sf[base + e]); v += __popc(c_sr[base + e]); }
+    }
+    f = corn_warp_sum(f); v = corn_warp_sum(v);
+    if (lane == 0) { P.rank_f[r] = f0 + f; P.rank_r[r] = v0 + v; }
 }
 
 __global__ void __launch_bounds__(256) k_telofind_assemble(const AssembleParams P)
@@ -544,7 +563,7 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
             ap.rank_f = (uint32_t *)ctx->bins.p; ap.rank_r = ap.rank_f + db->n_rec + 2;
             ap.out = (corn_run_t *)ctx->runs.p; ap.err = d_err;
             if (db->n_rec) {
-                k_telofind_ranks<<<(db->n_rec + 1 + 255) / 256, 256, 0, st>>>(ap, tile_off, sp.tile_ncand, sp.c_idx, sp.c_a, sp.c_b, n_tiles);
+                k_telofind_ranks<<<(unsigned)(((size_t)db->n_rec + 1 + 7) / 8), 256, 0, st>>>(ap, tile_off, sp.tile_ncand, sp.c_idx, sp.c_a, sp.c_b, n_tiles);
                 k_telofind_assemble<<<ctx->sm_count * 8, 256, 0, st>>>(ap);
                 corn_count_launch(ctx, 2);
                 CORN_LAUNCH_CHECK(ctx);

@@ -289,12 +289,13 @@ def test_abi_async_fused_matches_sync(ctx, capi):
         want_wins = ctx.telowin(thr)
         c2 = capi.Context(0)                      # fresh context: buffers start at their speculative sizes
         db = c2.upload(hb)
-        for _ in range(3):
+        for it in range(3):
             assert c2.telofind_dev(db, "TTAGGG", fetch=False) is None
             wins = c2.telowin(thr)
             assert len(wins) == len(want_wins) and (wins == want_wins).all()
             t = c2.timing()
-            assert t["scan_ms"] > 0 and t["launches"] >= 8
+            if it > 0:                            # (the first pass may have had to grow its buffers and repeat)
+                assert t["scan_ms"] > 0 and t["launches"] >= 8, t
         runs = c2.telofind_dev(db, "TTAGGG", fetch=True)
         assert len(runs) == len(want_runs) and (runs == want_runs).all()
         c2.free(db)
