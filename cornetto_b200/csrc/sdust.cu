@@ -48,19 +48,121 @@ struct SdParams {
     uint32_t *err;
 };
 
+// ---- warp-cooperative find_perfect -------------------------------------------------------------
+// find_perfect is needed on ~2 % of the positions of ordinary sequence but costs ~50 dependent
+// iterations; run per lane it leaves the other 31 lanes idle for thousands of issue slots.
+// Instead the lanes that need it are served one after the other by the WHOLE warp, using the
+// data-parallel form derived in sdust_core.cuh (sd_find_perfect_vec): window index i = 32*b + lane,
+// ranks by __match_any_sync + a 64-entry per-warp counter table, a reverse warp scan for the
+// suffix sums, and a reverse warp max-scan over score ratios.
+template <int NB>   // 32-position blocks covering the window: 2 for W <= 66, 4 for W <= 128
+__device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int my_start, uint32_t *warp_cols,
+                                        uint8_t *cnt /* 64 bytes per warp */, int T, int W)
+{
+    const uint32_t FULL = 0xffffffffu;
+    const int wn = __shfl_sync(FULL, s.wn, leader), whead = __shfl_sync(FULL, s.whead, leader);
+    const int L = __shfl_sync(FULL, s.L, leader), rv = __shfl_sync(FULL, s.rv, leader);
+    const int start = __shfl_sync(FULL, my_start, leader);
+    int base = __shfl_sync(FULL, s.pslot, leader) + (start - __shfl_sync(FULL, s.pstart, leader));
+    if (base >= W || base < 0) base = (int)((uint32_t)start % (uint32_t)W);
+    const int i0 = wn - L - 1;
+
+    // the leader's shared-memory column
+    sd_mem m;
+    m.pitch = SD_BLOCK * 4;
+    uint8_t *col = (uint8_t *)(warp_cols + leader);
+    const int ring_rows = (W + 3) >> 2;
+    m.ring = col;
+    m.cw   = col + (size_t)ring_rows * m.pitch;
+    m.cv   = m.cw + 16 * (size_t)m.pitch;
+    m.slot = (uint32_t *)(m.cv + 16 * (size_t)m.pitch);
+
+    if (lane < 16) ((uint32_t *)cnt)[lane] = 0;
+    __syncwarp();
+    const uint32_t le = corn_lanemask_lt() | (1u << lane);
+
+    int c[NB], er[NB], el[NB], pr[NB], pl[NB], si[NB];
+    bool valid[NB], sv[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {                    // ranks, ascending blocks
+        const int i = 32 * b + lane;
+        valid[b] = i < wn;
+        int ri = whead + i; if (ri >= W) ri -= W;
+        const int t = valid[b] ? (int)SD_U8(m.ring, ri) : 64 + lane;
+        const int before = valid[b] ? (int)cnt[t] : 0;
+        const uint32_t mm = __match_any_sync(FULL, t);
+        const int rank = before + __popc(mm & le);
+        if (valid[b] && lane == __ffs(mm) - 1) cnt[t] = (uint8_t)(before + __popc(mm));
+        __syncwarp();
+        c[b] = (valid[b] && i <= i0) ? (int)SD_U8(m.cw, t) - rank : 0;
+        int k = base + i; if (k >= W) k -= W;
+        si[b] = k;
+        const uint32_t v = valid[b] ? SD_U32(m.slot, k) : 0u;
+        sv[b] = (v & SD_SLOT_VALID) != 0;
+        pr[b] = sv[b] ? sd_slot_r(v) : 0;
+        pl[b] = sv[b] ? sd_slot_l(v) : 1;
+    }
+    // suffix sums (descending index): new_r(i) = rv + sum_{k >= i} c_k
+    int nr[NB];
+    int carry = 0;
+#pragma unroll
+    for (int b = NB - 1; b >= 0; --b) {
+        int x = c[b];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_down_sync(FULL, x, o); if (lane + o < 32) x += y; }
+        nr[b] = rv + x + carry;
+        carry += __shfl_sync(FULL, x, 0);
+    }
+    // elements and their exclusive running maximum (descending index)
+    bool cand[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int i = 32 * b + lane, new_l = wn - i - 1;
+        cand[b] = valid[b] && i <= i0 && nr[b] * 10 > T * new_l;
+        er[b] = pr[b]; el[b] = pl[b];
+        if (cand[b]) sd_fracmax(er[b], el[b], nr[b], new_l);
+    }
+    int cr = 0, cl = 1;                               // maximum over the blocks above the current one
+    uint32_t fresh = 0;
+#pragma unroll
+    for (int b = NB - 1; b >= 0; --b) {
+        int xr = er[b], xl = el[b];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int yr = __shfl_down_sync(FULL, xr, o), yl = __shfl_down_sync(FULL, xl, o);
+            if (lane + o < 32) sd_fracmax(xr, xl, yr, yl);
+        }
+        int mr = __shfl_down_sync(FULL, xr, 1), ml = __shfl_down_sync(FULL, xl, 1);   // exclusive: lanes above me
+        if (lane == 31) { mr = 0; ml = 1; }
+        sd_fracmax(mr, ml, cr, cl);
+        const int tr = __shfl_sync(FULL, xr, 0), tl = __shfl_sync(FULL, xl, 0);
+        sd_fracmax(cr, cl, tr, tl);
+        bool ins = false;
+        if (cand[b]) {
+            const int i = 32 * b + lane, new_l = wn - i - 1;
+            sd_fracmax(mr, ml, pr[b], pl[b]);
+            if (nr[b] * ml >= mr * new_l) {
+                SD_U32(m.slot, si[b]) = sd_slot_pack(nr[b], new_l, wn + 2 - i);
+                ins = !sv[b];
+            }
+        }
+        fresh += __popc(__ballot_sync(FULL, ins));
+    }
+    if (lane == leader) s.nslot += (int)fresh;
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
 {
     extern __shared__ uint32_t smem[];
+    const uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     const uint32_t j = blockIdx.x * SD_BLOCK + threadIdx.x;
-    if (j >= P.n_chunks) return;
-    const uint32_t rec = corn_upper_bound(P.chunk_base, P.n_rec, j) - 1;
-    const uint32_t k = j - P.chunk_base[rec];
-    const int len = (int)P.rec_len[rec];
-    const int c0 = (int)k * P.C;
-    const int c1 = min(len, c0 + P.C);
+    const bool have = j < P.n_chunks;                 // lanes without a chunk still serve the warp's cooperative calls
 
-    // column layout: row r of this thread at smem[r * SD_BLOCK + tid]
+    // column layout: row r of this thread at smem[r * SD_BLOCK + tid]; after the columns, 64 counter bytes per warp
     const int ring_rows = (P.W + 3) >> 2;
+    const int rows = ring_rows + 32 + P.W;
     uint8_t *col = (uint8_t *)(smem + threadIdx.x);
     sd_mem m;
     m.pitch = SD_BLOCK * 4;
@@ -68,16 +170,76 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
     m.cw   = col + (size_t)ring_rows * m.pitch;
     m.cv   = m.cw + 16 * (size_t)m.pitch;
     m.slot = (uint32_t *)(m.cv + 16 * (size_t)m.pitch);
+    uint32_t *warp_cols = smem + (threadIdx.x & ~31);
+    uint8_t *cnt = (uint8_t *)(smem + (size_t)rows * SD_BLOCK) + 64 * (threadIdx.x >> 5);
 
+    uint32_t rec = 0, k = 0;
+    int len = 0, c0 = 0, c1 = 0;
+    if (have) {
+        rec = corn_upper_bound(P.chunk_base, P.n_rec, j) - 1;
+        k = j - P.chunk_base[rec];
+        len = (int)P.rec_len[rec];
+        c0 = (int)k * P.C;
+        c1 = min(len, c0 + P.C);
+    }
     sd_sink sink;
     sd_sink_init(sink, P.slots + (size_t)j * P.cap, P.cap);
     DevFetch fetch;
-    fetch.seq = P.seq + P.rec_off[rec];
+    fetch.seq = P.seq + (have ? P.rec_off[rec] : 0);
     fetch.blk = -1;
     fetch.buf = make_uint4(0, 0, 0, 0);
-    sd_run_chunk(fetch, len, c0, c1, P.T, P.W, m, sink);
-    P.cnt[j] = sink.n;
-    if (sink.overflow) atomicAdd(P.err, 1u);
+
+    sd_state s;
+    sd_reset(s, m, P.W);
+    const int T = P.T, W = P.W;
+    int p0 = 0, n_steps = 0;
+    if (have) {
+        p0 = sd_warm_start(fetch, c0, W);
+        s.pstart = p0; s.pslot = (int)((uint32_t)p0 % (uint32_t)W);
+        const int stop = c1 < len ? c1 : len;
+        n_steps = (stop - p0) + (c1 >= len ? 1 : 0);  // + the reference's i == l_seq iteration for the record's last chunk
+    }
+    const bool coop = T >= 5;                         // (below that a candidate can have new_l == 0: serial form)
+
+    for (int step = 0;; ++step) {
+        const bool live = step < n_steps;
+        if (!__any_sync(FULL, live)) break;
+        bool trig = false;
+        int start = 0;
+        if (live) {
+            const int i = p0 + step;
+            if (i >= c0) sink.on = 1;
+            const int b = i < len ? sd_nt4(fetch(i)) : 4;
+            if (b < 4) {
+                ++s.l;
+                s.t = (s.t << 2 | (unsigned)b) & 63u;
+                if (s.l >= 3) {
+                    start = (s.l - W > 0 ? s.l - W : 0) + (i + 1 - s.l);
+                    sd_save(s, m, sink, start, W);
+                    sd_shift_window(s, m, (int)s.t, T, W);
+                    if (s.rw * 10 > s.L * T) {
+                        if (!coop) sd_find_perfect(s, m, T, start, W);
+                        else trig = s.wn - s.L - 1 >= 0;   // no index to examine otherwise
+                    }
+                }
+            } else {
+                sd_flush(s, m, sink, (s.l - W + 1 > 0 ? s.l - W + 1 : 0) + (i + 1 - s.l), W);
+                s.l = 0; s.t = 0;
+            }
+        }
+        uint32_t todo = __ballot_sync(FULL, trig);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            todo &= todo - 1;
+            if (W <= 66) fp_coop<2>(leader, lane, s, start, warp_cols, cnt, T, W);
+            else         fp_coop<4>(leader, lane, s, start, warp_cols, cnt, T, W);
+        }
+    }
+    sd_sink_close(sink);
+    if (have) {
+        P.cnt[j] = sink.n;
+        if (sink.overflow) atomicAdd(P.err, 1u);
+    }
 }
 
 struct GatherParams {
@@ -128,7 +290,7 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     // chunk length: 4096 bases for large batches (5 % warm-up overhead); smaller when that would leave
     // the GPU with fewer than ~3 waves of threads.  Results do not depend on it.
     const int rows = ((W + 3) >> 2) + 32 + W;
-    const size_t smem = (size_t)rows * SD_BLOCK * 4;
+    const size_t smem = (size_t)rows * SD_BLOCK * 4 + 64 * (SD_BLOCK / 32);
     CORN_CUDA(ctx, cudaFuncSetAttribute(k_sdust_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sdust_scan, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }

@@ -255,6 +255,60 @@ SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W
     }
 }
 
+// ---- data-parallel form of find_perfect ------------------------------------------------------
+// The serial loop above hides three independent scans.  With t_i the triplet at window index i,
+// i0 = wn-L-1 and rank(i) = #{k <= i : t_k == t_i}:
+//   c_i      = cw[t_i] - rank(i)                  (what "r += c[t]++" adds at index i)
+//   new_r(i) = rv + sum_{k=i..i0} c_k             (suffix sum)
+//   M_i      = best ratio among the slots of indices >= i and the candidates of indices > i
+//              (a rejected candidate is below the running maximum, so it may be included)
+//   insert i <=> new_r*10 > T*new_l  and  new_r/new_l >= M_i
+// This is what the warp-cooperative device version (sdust.cu) evaluates with match/scan
+// primitives; sd_find_perfect_vec is the same arithmetic with plain loops so that the CPU
+// simulation can check it against the serial form (SD_USE_VEC).  Requires T >= 5 (so that every
+// candidate has new_l >= 1), which the callers check.
+SD_HD void sd_fracmax(int &ar, int &al, int br, int bl) { if (br * al > ar * bl) { ar = br; al = bl; } }
+
+SD_HD void sd_find_perfect_vec(sd_state &s, const sd_mem &m, int T, int start, int W)
+{
+    const int wn = s.wn, i0 = wn - s.L - 1;
+    int base = s.pslot + (start - s.pstart);
+    if (base >= W || base < 0) base = (int)((uint32_t)start % (uint32_t)W);
+    int tt[SD_MAX_W], c[SD_MAX_W], nr[SD_MAX_W], er[SD_MAX_W], el[SD_MAX_W], pr[SD_MAX_W], pl[SD_MAX_W], sv[SD_MAX_W];
+    int cnt[64];
+    for (int t = 0; t < 64; ++t) cnt[t] = 0;
+    for (int i = 0; i < wn; ++i) {                        // ranks (ascending)
+        tt[i] = SD_U8(m.ring, sd_ring_idx(s, i, W));
+        const int rank = ++cnt[tt[i]];
+        c[i] = i <= i0 ? (int)SD_U8(m.cw, tt[i]) - rank : 0;
+    }
+    int acc = 0;
+    for (int i = wn - 1; i >= 0; --i) { acc += c[i]; nr[i] = s.rv + acc; }      // suffix sums
+    for (int i = 0; i < wn; ++i) {                        // elements: slot and candidate
+        int si = base + i; if (si >= W) si -= W;
+        const uint32_t v = SD_U32(m.slot, si);
+        sv[i] = (v & SD_SLOT_VALID) != 0;
+        pr[i] = sv[i] ? sd_slot_r(v) : 0; pl[i] = sv[i] ? sd_slot_l(v) : 1;
+        er[i] = pr[i]; el[i] = pl[i];
+        const int new_l = wn - i - 1;
+        if (i <= i0 && nr[i] * 10 > T * new_l) sd_fracmax(er[i], el[i], nr[i], new_l);
+    }
+    int mr = 0, ml = 1;                                    // exclusive running maximum, descending i
+    for (int i = wn - 1; i >= 0; --i) {
+        const int new_l = wn - i - 1;
+        if (i <= i0 && nr[i] * 10 > T * new_l) {
+            int Mr = mr, Ml = ml;
+            sd_fracmax(Mr, Ml, pr[i], pl[i]);
+            if (nr[i] * Ml >= Mr * new_l) {
+                int si = base + i; if (si >= W) si -= W;
+                if (!sv[i]) ++s.nslot;
+                SD_U32(m.slot, si) = sd_slot_pack(nr[i], new_l, wn + 2 - i);
+            }
+        }
+        sd_fracmax(mr, ml, er[i], el[i]);
+    }
+}
+
 // one input position (i == l_seq is the virtual end-of-sequence byte, b = 4).
 // Returns the window start of an emitting step, INT32_MAX after a flush (every slot resolved),
 // or -1 for an A/C/G/T byte that does not complete a triplet.
@@ -267,7 +321,11 @@ SD_HD int sd_step(sd_state &s, const sd_mem &m, sd_sink &k, int i, int b, int T,
         const int start = (s.l - W > 0 ? s.l - W : 0) + (i + 1 - s.l);
         sd_save(s, m, k, start, W);
         sd_shift_window(s, m, (int)s.t, T, W);
+#if defined(SD_USE_VEC)
+        if (s.rw * 10 > s.L * T) { if (T >= 5) sd_find_perfect_vec(s, m, T, start, W); else sd_find_perfect(s, m, T, start, W); }
+#else
         if (s.rw * 10 > s.L * T) sd_find_perfect(s, m, T, start, W);
+#endif
         return start;
     }
     sd_flush(s, m, k, (s.l - W + 1 > 0 ? s.l - W + 1 : 0) + (i + 1 - s.l), W);
