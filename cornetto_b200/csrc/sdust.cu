@@ -30,9 +30,11 @@ struct DevFetch {
     {
         const int b = i >> 4;
         if (b != blk) { buf = __ldg((const uint4 *)(seq + ((size_t)b << 4))); blk = b; }
-        const int k = i & 15;
-        const uint32_t w = k < 8 ? (k < 4 ? buf.x : buf.y) : (k < 12 ? buf.z : buf.w);
-        return (uint8_t)(w >> ((k & 3) * 8));
+        // branch-free byte select (a chain of ?: here made the compiler clone the whole step body four
+        // times, one per source register, and run each clone with a quarter of the lanes)
+        const uint32_t k = (uint32_t)i & 15u;
+        const uint32_t lo = __byte_perm(buf.x, buf.y, k & 7u), hi = __byte_perm(buf.z, buf.w, k & 7u);
+        return (uint8_t)((k & 8u) ? hi : lo);
     }
 };
 
@@ -194,7 +196,8 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
     const int T = P.T, W = P.W;
     int p0 = 0, n_steps = 0;
     if (have) {
-        p0 = sd_warm_start(fetch, c0, W);
+        p0 = sd_warm_start(fetch, c0, W) & ~15;       // (a longer warm-up is always valid) all lanes then refill their
+                                                      // 16-byte fetch buffer on the same steps
         s.pstart = p0; s.pslot = (int)((uint32_t)p0 % (uint32_t)W);
         const int stop = c1 < len ? c1 : len;
         n_steps = (stop - p0) + (c1 >= len ? 1 : 0);  // + the reference's i == l_seq iteration for the record's last chunk

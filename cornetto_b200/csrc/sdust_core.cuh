@@ -43,11 +43,16 @@
 #define SD_MAX_W 128
 
 // seq_nt4_table, src/sdust/sdust.c:23-40: A/a C/c G/g T/t -> 0..3, bytes 0..3 -> 0..3, rest 4
+// Branch-free on purpose: written as an if/else chain the four bases became four divergent paths that
+// only rejoined at the end of the step, i.e. the whole per-base body ran four times per warp.
 SD_HD int sd_nt4(uint8_t c)
 {
-    if (c < 4) return c;
-    const uint8_t u = c & 0xDF;
-    return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : 4;
+    const uint32_t u = c & 0xDFu;                          // fold case
+    const uint32_t k = (c >> 1) & 3u;                      // A 0, C 1, T 2, G 3 for valid letters
+    const uint32_t expect = (0x47544341u >> (8u * k)) & 0xFFu;   // 'A','C','T','G'
+    const uint32_t code = (0x2310u >> (4u * k)) & 3u;      // -> A 0, C 1, G 2, T 3
+    const uint32_t r = (u == expect) ? code : 4u;
+    return (int)(c < 4 ? (uint32_t)c : r);
 }
 
 // Per-thread state arrays live in shared memory on the device with one 4-byte wide column per
