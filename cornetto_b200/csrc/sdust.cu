@@ -159,8 +159,14 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
     extern __shared__ uint32_t smem[];
     const uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const uint32_t j = blockIdx.x * SD_BLOCK + threadIdx.x;
-    const bool have = j < P.n_chunks;                 // lanes without a chunk still serve the warp's cooperative calls
+    // chunk of this lane: consecutive chunks go to DIFFERENT warps (lane l of warp w takes chunk
+    // l * n_warps + w).  Low-complexity stretches (satellites, telomeres) make their chunks many times
+    // more expensive; spread over the warps they cost each warp one slow lane instead of leaving one
+    // warp with 32 of them as the kernel's tail.
+    const uint32_t n_warps = (P.n_chunks + 31u) / 32u;
+    const uint32_t warp_id = (blockIdx.x * SD_BLOCK + threadIdx.x) >> 5;
+    const uint32_t j = (uint32_t)lane * n_warps + warp_id;
+    const bool have = warp_id < n_warps && j < P.n_chunks;   // lanes without a chunk still serve the warp's cooperative calls
 
     // column layout: row r of this thread at smem[r * SD_BLOCK + tid]; after the columns, 64 counter bytes per warp
     const int ring_rows = (P.W + 3) >> 2;
