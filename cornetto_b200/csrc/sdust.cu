@@ -50,15 +50,79 @@ struct SdParams {
     uint32_t *err;
 };
 
-// ---- warp-cooperative find_perfect -------------------------------------------------------------
+// ---- shared-memory layout of a block -------------------------------------------------------------
+//   [ cw | cv columns : 32 rows x SD_BLOCK x 4 B ][ ring arrays : SD_BLOCK x ring_words x 4 B ]
+//   [ slot arrays : SD_BLOCK x slot_words x 4 B ][ 64 counter bytes per warp ]
+// ring_words / slot_words are odd, so that the same index in consecutive threads falls into
+// consecutive banks.
+struct SdLayout {
+    int ring_words, slot_words;
+    __host__ __device__ SdLayout(int W) : ring_words(((W + 3) >> 2) | 1), slot_words(W | 1) {}
+    __host__ __device__ size_t bytes() const { return (size_t)SD_BLOCK * 4 * (32 + ring_words + slot_words) + 64 * (SD_BLOCK / 32); }
+};
+
+__device__ __forceinline__ sd_mem sd_mem_of(uint32_t *smem, const SdLayout &lay, int tid)
+{
+    sd_mem m;
+    m.pitch = SD_BLOCK * 4;
+    m.cw = (uint8_t *)(smem + tid);
+    m.cv = m.cw + 16 * (size_t)m.pitch;
+    uint32_t *rings = smem + 32 * SD_BLOCK;
+    m.ring = (uint8_t *)(rings + (size_t)tid * lay.ring_words);
+    m.slot = rings + (size_t)SD_BLOCK * lay.ring_words + (size_t)tid * lay.slot_words;
+    return m;
+}
+
+// ---- warp-cooperative routines ---------------------------------------------------------------------
 // find_perfect is needed on ~2 % of the positions of ordinary sequence but costs ~50 dependent
-// iterations; run per lane it leaves the other 31 lanes idle for thousands of issue slots.
-// Instead the lanes that need it are served one after the other by the WHOLE warp, using the
-// data-parallel form derived in sdust_core.cuh (sd_find_perfect_vec): window index i = 32*b + lane,
-// ranks by __match_any_sync + a 64-entry per-warp counter table, a reverse warp scan for the
-// suffix sums, and a reverse warp max-scan over score ratios.
+// iterations, and the suffix-shrink loop of shift_window runs ~12 iterations on ~1 % of them; run
+// per lane they leave the other 31 lanes idle for thousands of issue slots.  Instead the lanes
+// that need them are served one after the other by the WHOLE warp: window index i = 32*b + lane,
+// equal-triplet ranks by __match_any_sync, reverse warp scans for the suffix sums and for the
+// running maximum of score ratios (the data-parallel form derived in sdust_core.cuh).
+
+// shrink v until the first occurrence of t has been dropped (sd_shift_window_pop)
+template <int NB>
+__device__ __forceinline__ void pop_coop(int leader, int lane, sd_state &s, int my_t, uint32_t *smem, const SdLayout &lay, int W)
+{
+    const uint32_t FULL = 0xffffffffu;
+    const int wn = __shfl_sync(FULL, s.wn, leader), whead = __shfl_sync(FULL, s.whead, leader);
+    const int L = __shfl_sync(FULL, s.L, leader), t = __shfl_sync(FULL, my_t, leader);
+    const sd_mem m = sd_mem_of(smem, lay, (threadIdx.x & ~31) + leader);
+    const int v0 = wn - L;                            // first index of v
+    const uint32_t le = corn_lanemask_lt() | (1u << lane);
+    int x[NB];
+    bool inv[NB];
+    int p = 1 << 30;                                  // index of the first occurrence of t in v
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int i = 32 * b + lane;
+        inv[b] = i >= v0 && i < wn;
+        int ri = whead + i; if (ri >= W) ri -= W;
+        x[b] = inv[b] ? (int)SD_RING(ri) : -1;
+        const uint32_t hit = __ballot_sync(FULL, x[b] == t);
+        if (hit && p == (1 << 30)) p = 32 * b + __ffs(hit) - 1;
+    }
+    int sub = 0;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int i = 32 * b + lane;
+        const bool popped = inv[b] && i <= p;
+        const int key = popped ? x[b] : 64 + lane;
+        const uint32_t mm = __match_any_sync(FULL, key);
+        if (popped) {
+            const int cvx = SD_U8(m.cv, x[b]);        // count before this block's pops
+            sub += cvx - __popc(mm & le);             // "rv -= --cv[x]" for the rank-th equal element
+            if (lane == __ffs(mm) - 1) SD_U8(m.cv, x[b]) = (uint8_t)(cvx - __popc(mm));
+        }
+        __syncwarp();
+    }
+    sub = (int)corn_warp_sum((uint32_t)sub);
+    if (lane == leader) { s.rv -= sub; s.L -= p - v0 + 1; }
+}
+
 template <int NB>   // 32-position blocks covering the window: 2 for W <= 66, 4 for W <= 128
-__device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int my_start, uint32_t *warp_cols,
+__device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int my_start, uint32_t *smem, const SdLayout &lay,
                                         uint8_t *cnt /* 64 bytes per warp */, int T, int W)
 {
     const uint32_t FULL = 0xffffffffu;
@@ -68,45 +132,32 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
     int base = __shfl_sync(FULL, s.pslot, leader) + (start - __shfl_sync(FULL, s.pstart, leader));
     if (base >= W || base < 0) base = (int)((uint32_t)start % (uint32_t)W);
     const int i0 = wn - L - 1;
-
-    // the leader's shared-memory column
-    sd_mem m;
-    m.pitch = SD_BLOCK * 4;
-    uint8_t *col = (uint8_t *)(warp_cols + leader);
-    const int ring_rows = (W + 3) >> 2;
-    m.ring = col;
-    m.cw   = col + (size_t)ring_rows * m.pitch;
-    m.cv   = m.cw + 16 * (size_t)m.pitch;
-    m.slot = (uint32_t *)(m.cv + 16 * (size_t)m.pitch);
+    const sd_mem m = sd_mem_of(smem, lay, (threadIdx.x & ~31) + leader);
 
     if (lane < 16) ((uint32_t *)cnt)[lane] = 0;
     __syncwarp();
     const uint32_t le = corn_lanemask_lt() | (1u << lane);
 
-    int c[NB], er[NB], el[NB], pr[NB], pl[NB], si[NB];
-    bool valid[NB], sv[NB];
+    int c[NB];
+    bool valid[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {                    // ranks, ascending blocks
         const int i = 32 * b + lane;
         valid[b] = i < wn;
         int ri = whead + i; if (ri >= W) ri -= W;
-        const int t = valid[b] ? (int)SD_U8(m.ring, ri) : 64 + lane;
+        const int t = valid[b] ? (int)SD_RING(ri) : 64 + lane;
         const int before = valid[b] ? (int)cnt[t] : 0;
         const uint32_t mm = __match_any_sync(FULL, t);
         const int rank = before + __popc(mm & le);
         if (valid[b] && lane == __ffs(mm) - 1) cnt[t] = (uint8_t)(before + __popc(mm));
         __syncwarp();
         c[b] = (valid[b] && i <= i0) ? (int)SD_U8(m.cw, t) - rank : 0;
-        int k = base + i; if (k >= W) k -= W;
-        si[b] = k;
-        const uint32_t v = valid[b] ? SD_U32(m.slot, k) : 0u;
-        sv[b] = (v & SD_SLOT_VALID) != 0;
-        pr[b] = sv[b] ? sd_slot_r(v) : 0;
-        pl[b] = sv[b] ? sd_slot_l(v) : 1;
     }
     // suffix sums (descending index): new_r(i) = rv + sum_{k >= i} c_k
     int nr[NB];
+    bool cand[NB];
     int carry = 0;
+    bool any_cand = false;
 #pragma unroll
     for (int b = NB - 1; b >= 0; --b) {
         int x = c[b];
@@ -114,13 +165,24 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_down_sync(FULL, x, o); if (lane + o < 32) x += y; }
         nr[b] = rv + x + carry;
         carry += __shfl_sync(FULL, x, 0);
+        const int i = 32 * b + lane, new_l = wn - i - 1;
+        cand[b] = valid[b] && i <= i0 && nr[b] * 10 > T * new_l;
+        any_cand |= cand[b];
     }
-    // elements and their exclusive running maximum (descending index)
-    bool cand[NB];
+    if (!__any_sync(FULL, any_cand)) return;          // nothing can be inserted: P is left untouched
+
+    // elements (existing slot, candidate) and their exclusive running maximum (descending index)
+    int er[NB], el[NB], pr[NB], pl[NB], si[NB];
+    bool sv[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int i = 32 * b + lane, new_l = wn - i - 1;
-        cand[b] = valid[b] && i <= i0 && nr[b] * 10 > T * new_l;
+        int k = base + i; if (k >= W) k -= W;
+        si[b] = k;
+        const uint32_t v = valid[b] ? SD_SLOT(k) : 0u;
+        sv[b] = (v & SD_SLOT_VALID) != 0;
+        pr[b] = sv[b] ? sd_slot_r(v) : 0;
+        pl[b] = sv[b] ? sd_slot_l(v) : 1;
         er[b] = pr[b]; el[b] = pl[b];
         if (cand[b]) sd_fracmax(er[b], el[b], nr[b], new_l);
     }
@@ -144,7 +206,7 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
             const int i = 32 * b + lane, new_l = wn - i - 1;
             sd_fracmax(mr, ml, pr[b], pl[b]);
             if (nr[b] * ml >= mr * new_l) {
-                SD_U32(m.slot, si[b]) = sd_slot_pack(nr[b], new_l, wn + 2 - i);
+                SD_SLOT(si[b]) = sd_slot_pack(nr[b], new_l, wn + 2 - i);
                 ins = !sv[b];
             }
         }
@@ -168,18 +230,10 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
     const uint32_t j = (uint32_t)lane * n_warps + warp_id;
     const bool have = warp_id < n_warps && j < P.n_chunks;   // lanes without a chunk still serve the warp's cooperative calls
 
-    // column layout: row r of this thread at smem[r * SD_BLOCK + tid]; after the columns, 64 counter bytes per warp
-    const int ring_rows = (P.W + 3) >> 2;
-    const int rows = ring_rows + 32 + P.W;
-    uint8_t *col = (uint8_t *)(smem + threadIdx.x);
-    sd_mem m;
-    m.pitch = SD_BLOCK * 4;
-    m.ring = col;
-    m.cw   = col + (size_t)ring_rows * m.pitch;
-    m.cv   = m.cw + 16 * (size_t)m.pitch;
-    m.slot = (uint32_t *)(m.cv + 16 * (size_t)m.pitch);
-    uint32_t *warp_cols = smem + (threadIdx.x & ~31);
-    uint8_t *cnt = (uint8_t *)(smem + (size_t)rows * SD_BLOCK) + 64 * (threadIdx.x >> 5);
+    const int T = P.T, W = P.W;
+    const SdLayout lay(W);
+    const sd_mem m = sd_mem_of(smem, lay, threadIdx.x);
+    uint8_t *cnt = (uint8_t *)(smem + (size_t)SD_BLOCK * (32 + lay.ring_words + lay.slot_words)) + 64 * (threadIdx.x >> 5);
 
     uint32_t rec = 0, k = 0;
     int len = 0, c0 = 0, c1 = 0;
@@ -191,15 +245,14 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
         c1 = min(len, c0 + P.C);
     }
     sd_sink sink;
-    sd_sink_init(sink, P.slots + (size_t)j * P.cap, P.cap);
+    sd_sink_init(sink, P.slots + (size_t)(have ? j : 0) * P.cap, P.cap);
     DevFetch fetch;
     fetch.seq = P.seq + (have ? P.rec_off[rec] : 0);
     fetch.blk = -1;
     fetch.buf = make_uint4(0, 0, 0, 0);
 
     sd_state s;
-    sd_reset(s, m, P.W);
-    const int T = P.T, W = P.W;
+    sd_reset(s, m, W);
     int p0 = 0, n_steps = 0;
     if (have) {
         p0 = sd_warm_start(fetch, c0, W) & ~15;       // (a longer warm-up is always valid) all lanes then refill their
@@ -213,7 +266,7 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
     for (int step = 0;; ++step) {
         const bool live = step < n_steps;
         if (!__any_sync(FULL, live)) break;
-        bool trig = false;
+        bool emit = false, need_pop = false;
         int start = 0;
         if (live) {
             const int i = p0 + step;
@@ -225,23 +278,32 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
                 if (s.l >= 3) {
                     start = (s.l - W > 0 ? s.l - W : 0) + (i + 1 - s.l);
                     sd_save(s, m, sink, start, W);
-                    sd_shift_window(s, m, (int)s.t, T, W);
-                    if (s.rw * 10 > s.L * T) {
-                        if (!coop) sd_find_perfect(s, m, T, start, W);
-                        else trig = s.wn - s.L - 1 >= 0;   // no index to examine otherwise
-                    }
+                    need_pop = sd_shift_window_push(s, m, (int)s.t, T, W);
+                    emit = true;
                 }
             } else {
                 sd_flush(s, m, sink, (s.l - W + 1 > 0 ? s.l - W + 1 : 0) + (i + 1 - s.l), W);
                 s.l = 0; s.t = 0;
             }
         }
-        uint32_t todo = __ballot_sync(FULL, trig);
+        uint32_t todo = __ballot_sync(FULL, need_pop);
         while (todo) {
             const int leader = __ffs(todo) - 1;
             todo &= todo - 1;
-            if (W <= 66) fp_coop<2>(leader, lane, s, start, warp_cols, cnt, T, W);
-            else         fp_coop<4>(leader, lane, s, start, warp_cols, cnt, T, W);
+            if (W <= 66) pop_coop<2>(leader, lane, s, (int)s.t, smem, lay, W);
+            else         pop_coop<4>(leader, lane, s, (int)s.t, smem, lay, W);
+        }
+        bool trig = false;
+        if (emit && s.rw * 10 > s.L * T) {
+            if (!coop) sd_find_perfect(s, m, T, start, W);
+            else trig = s.wn - s.L - 1 >= 0;          // no index to examine otherwise
+        }
+        todo = __ballot_sync(FULL, trig);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            todo &= todo - 1;
+            if (W <= 66) fp_coop<2>(leader, lane, s, start, smem, lay, cnt, T, W);
+            else         fp_coop<4>(leader, lane, s, start, smem, lay, cnt, T, W);
         }
     }
     sd_sink_close(sink);
@@ -298,8 +360,7 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
 
     // chunk length: 4096 bases for large batches (5 % warm-up overhead); smaller when that would leave
     // the GPU with fewer than ~3 waves of threads.  Results do not depend on it.
-    const int rows = ((W + 3) >> 2) + 32 + W;
-    const size_t smem = (size_t)rows * SD_BLOCK * 4 + 64 * (SD_BLOCK / 32);
+    const size_t smem = SdLayout(W).bytes();
     CORN_CUDA(ctx, cudaFuncSetAttribute(k_sdust_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sdust_scan, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }

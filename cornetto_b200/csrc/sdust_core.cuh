@@ -55,19 +55,25 @@ SD_HD int sd_nt4(uint8_t c)
     return (int)(c < 4 ? (uint32_t)c : r);
 }
 
-// Per-thread state arrays live in shared memory on the device with one 4-byte wide column per
-// thread (so a thread always hits its own bank whatever index it uses).  pitch = bytes between
-// consecutive 4-byte rows of one thread's column; on the host pitch = 4 (a plain array).
+// Per-thread state lives in shared memory on the device.
+//   cw, cv   are indexed by data (the triplet): one 4-byte wide COLUMN per thread, so a thread always
+//            hits its own bank whatever index it uses.  pitch = bytes between consecutive 4-byte rows
+//            of a column; on the host pitch = 4 (a plain array).
+//   ring, slot  are indexed by window position, which is (nearly) the same for all lanes of a warp:
+//            plain per-thread arrays with an odd word stride between threads, conflict-free both
+//            for that access and for the warp-cooperative routines, where 32 lanes read 32
+//            consecutive entries of ONE thread's arrays.
 struct sd_mem {
     uint8_t  *ring;    // W entries: triplet codes of the window deque
-    uint8_t  *cw;      // 64 window counters
-    uint8_t  *cv;      // 64 suffix counters
+    uint8_t  *cw;      // 64 window counters (column)
+    uint8_t  *cv;      // 64 suffix counters (column)
     uint32_t *slot;    // W slots: valid:1 | flen:8 | l:8 | r:15
-    uint32_t  pitch;   // bytes
+    uint32_t  pitch;   // bytes, for cw / cv
 };
 
 #define SD_U8(base, i)  (*((base) + ((uint32_t)(i) >> 2) * m.pitch + ((uint32_t)(i) & 3u)))
-#define SD_U32(base, i) (*(uint32_t *)((uint8_t *)(base) + (uint32_t)(i) * m.pitch))
+#define SD_RING(i)      (m.ring[(i)])
+#define SD_SLOT(i)      (m.slot[(i)])
 
 #define SD_SLOT_VALID 0x80000000u
 SD_HD uint32_t sd_slot_pack(int r, int l, int flen) { return SD_SLOT_VALID | ((uint32_t)flen << 23) | ((uint32_t)l << 15) | (uint32_t)r; }
@@ -126,7 +132,7 @@ SD_HD void sd_reset(sd_state &s, const sd_mem &m, int W)
     s.wn = s.whead = s.L = s.rw = s.rv = s.nslot = s.pstart = s.pslot = s.l = 0;
     s.t = 0;
     for (int i = 0; i < 64; ++i) { SD_U8(m.cw, i) = 0; SD_U8(m.cv, i) = 0; }
-    for (int i = 0; i < W; ++i) SD_U32(m.slot, i) = 0;
+    for (int i = 0; i < W; ++i) SD_SLOT(i) = 0;
 }
 
 SD_HD int sd_ring_idx(const sd_state &s, int i, int W)
@@ -135,11 +141,13 @@ SD_HD int sd_ring_idx(const sd_state &s, int i, int W)
     return k >= W ? k - W : k;
 }
 
-// shift_window(): sdust.c:66-86
-SD_HD void sd_shift_window(sd_state &s, const sd_mem &m, int t, int T, int W)
+// shift_window(): sdust.c:66-86, in two halves so that the device can run the second one
+// (a data-dependent loop) cooperatively.  _push does everything up to and including the counter
+// updates for the new triplet and reports whether the suffix v must shrink; _pop is that loop.
+SD_HD bool sd_shift_window_push(sd_state &s, const sd_mem &m, int t, int T, int W)
 {
     if (s.wn >= W - 2) {
-        const int x = SD_U8(m.ring, s.whead);
+        const int x = SD_RING(s.whead);
         s.whead = s.whead + 1 >= W ? 0 : s.whead + 1;
         --s.wn;
         const int c = SD_U8(m.cw, x) - 1;
@@ -152,27 +160,33 @@ SD_HD void sd_shift_window(sd_state &s, const sd_mem &m, int t, int T, int W)
             s.rv -= d;
         }
     }
-    SD_U8(m.ring, sd_ring_idx(s, s.wn, W)) = (uint8_t)t;
+    SD_RING(sd_ring_idx(s, s.wn, W)) = (uint8_t)t;
     ++s.wn;
     ++s.L;
-    {
-        const int c = SD_U8(m.cw, t);
-        s.rw += c;
-        SD_U8(m.cw, t) = (uint8_t)(c + 1);
-        const int d = SD_U8(m.cv, t);
-        s.rv += d;
-        SD_U8(m.cv, t) = (uint8_t)(d + 1);
-        if ((d + 1) * 10 > T << 1) {
-            int x;
-            do {
-                x = SD_U8(m.ring, sd_ring_idx(s, s.wn - s.L, W));
-                const int e = SD_U8(m.cv, x) - 1;
-                SD_U8(m.cv, x) = (uint8_t)e;
-                s.rv -= e;
-                --s.L;
-            } while (x != t);
-        }
-    }
+    const int c = SD_U8(m.cw, t);
+    s.rw += c;
+    SD_U8(m.cw, t) = (uint8_t)(c + 1);
+    const int d = SD_U8(m.cv, t);
+    s.rv += d;
+    SD_U8(m.cv, t) = (uint8_t)(d + 1);
+    return (d + 1) * 10 > T << 1;
+}
+
+SD_HD void sd_shift_window_pop(sd_state &s, const sd_mem &m, int t, int W)
+{
+    int x;
+    do {
+        x = SD_RING(sd_ring_idx(s, s.wn - s.L, W));
+        const int e = SD_U8(m.cv, x) - 1;
+        SD_U8(m.cv, x) = (uint8_t)e;
+        s.rv -= e;
+        --s.L;
+    } while (x != t);
+}
+
+SD_HD void sd_shift_window(sd_state &s, const sd_mem &m, int t, int T, int W)
+{
+    if (sd_shift_window_push(s, m, t, T, W)) sd_shift_window_pop(s, m, t, W);
 }
 
 // save_masked_regions(): sdust.c:88-102.  If the smallest start is below `start`, that ONE slot
@@ -191,12 +205,12 @@ SD_HD void sd_set_pstart(sd_state &s, int start, int W)
 SD_HD void sd_save(sd_state &s, const sd_mem &m, sd_sink &k, int start, int W)
 {
     if (s.nslot == 0) { if (s.pstart != start) sd_set_pstart(s, start, W); return; }
-    while (s.pstart < start && !(SD_U32(m.slot, s.pslot) & SD_SLOT_VALID)) { ++s.pstart; if (++s.pslot == W) s.pslot = 0; }
+    while (s.pstart < start && !(SD_SLOT(s.pslot) & SD_SLOT_VALID)) { ++s.pstart; if (++s.pslot == W) s.pslot = 0; }
     if (s.pstart >= start) return;                       // smallest start >= start: nothing to do
-    sd_sink_put(k, s.pstart, s.pstart + sd_slot_flen(SD_U32(m.slot, s.pslot)));
+    sd_sink_put(k, s.pstart, s.pstart + sd_slot_flen(SD_SLOT(s.pslot)));
     while (s.pstart < start) {
-        if (SD_U32(m.slot, s.pslot) & SD_SLOT_VALID) {
-            SD_U32(m.slot, s.pslot) = 0;
+        if (SD_SLOT(s.pslot) & SD_SLOT_VALID) {
+            SD_SLOT(s.pslot) = 0;
             if (--s.nslot == 0) { sd_set_pstart(s, start, W); return; }
         }
         ++s.pstart; if (++s.pslot == W) s.pslot = 0;
@@ -224,7 +238,7 @@ SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W
     if (s.nslot)
         for (int i = s.wn - 1; i > i0; --i) {
             int si = base + i; if (si >= W) si -= W;
-            const uint32_t v = SD_U32(m.slot, si);
+            const uint32_t v = SD_SLOT(si);
             if (v & SD_SLOT_VALID) {
                 const int pr = sd_slot_r(v), pl = sd_slot_l(v);
                 if (max_r == 0 || pr * max_l > max_r * pl) { max_r = pr; max_l = pl; }
@@ -232,14 +246,14 @@ SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W
         }
     int ri = sd_ring_idx(s, i0 < 0 ? 0 : i0, W);          // ring position of window index i, walked downwards
     for (int i = i0; i >= 0; --i) {
-        const int t = SD_U8(m.ring, ri);
+        const int t = SD_RING(ri);
         if (--ri < 0) ri = W - 1;
         const int c = SD_U8(m.cv, t);
         r += c;
         SD_U8(m.cv, t) = (uint8_t)(c + 1);          // temporary; undone below (the reference copies cv)
         const int new_r = r, new_l = s.wn - i - 1;
         int si = base + i; if (si >= W) si -= W;
-        const uint32_t v = SD_U32(m.slot, si);
+        const uint32_t v = SD_SLOT(si);
         if (v & SD_SLOT_VALID) {                      // entries with this start join the running maximum
             const int pr = sd_slot_r(v), pl = sd_slot_l(v);
             if (max_r == 0 || pr * max_l > max_r * pl) { max_r = pr; max_l = pl; }
@@ -248,13 +262,13 @@ SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W
             if (max_r == 0 || new_r * max_l >= max_r * new_l) {
                 max_r = new_r; max_l = new_l;
                 if (!(v & SD_SLOT_VALID)) ++s.nslot;
-                SD_U32(m.slot, si) = sd_slot_pack(new_r, new_l, s.wn + 2 - i);
+                SD_SLOT(si) = sd_slot_pack(new_r, new_l, s.wn + 2 - i);
             }
         }
     }
     ri = sd_ring_idx(s, i0 < 0 ? 0 : i0, W);
     for (int i = i0; i >= 0; --i) {
-        const int t = SD_U8(m.ring, ri);
+        const int t = SD_RING(ri);
         if (--ri < 0) ri = W - 1;
         SD_U8(m.cv, t) = (uint8_t)(SD_U8(m.cv, t) - 1);
     }
@@ -283,7 +297,7 @@ SD_HD void sd_find_perfect_vec(sd_state &s, const sd_mem &m, int T, int start, i
     int cnt[64];
     for (int t = 0; t < 64; ++t) cnt[t] = 0;
     for (int i = 0; i < wn; ++i) {                        // ranks (ascending)
-        tt[i] = SD_U8(m.ring, sd_ring_idx(s, i, W));
+        tt[i] = SD_RING(sd_ring_idx(s, i, W));
         const int rank = ++cnt[tt[i]];
         c[i] = i <= i0 ? (int)SD_U8(m.cw, tt[i]) - rank : 0;
     }
@@ -291,7 +305,7 @@ SD_HD void sd_find_perfect_vec(sd_state &s, const sd_mem &m, int T, int start, i
     for (int i = wn - 1; i >= 0; --i) { acc += c[i]; nr[i] = s.rv + acc; }      // suffix sums
     for (int i = 0; i < wn; ++i) {                        // elements: slot and candidate
         int si = base + i; if (si >= W) si -= W;
-        const uint32_t v = SD_U32(m.slot, si);
+        const uint32_t v = SD_SLOT(si);
         sv[i] = (v & SD_SLOT_VALID) != 0;
         pr[i] = sv[i] ? sd_slot_r(v) : 0; pl[i] = sv[i] ? sd_slot_l(v) : 1;
         er[i] = pr[i]; el[i] = pl[i];
@@ -307,7 +321,7 @@ SD_HD void sd_find_perfect_vec(sd_state &s, const sd_mem &m, int T, int start, i
             if (nr[i] * Ml >= Mr * new_l) {
                 int si = base + i; if (si >= W) si -= W;
                 if (!sv[i]) ++s.nslot;
-                SD_U32(m.slot, si) = sd_slot_pack(nr[i], new_l, wn + 2 - i);
+                SD_SLOT(si) = sd_slot_pack(nr[i], new_l, wn + 2 - i);
             }
         }
         sd_fracmax(mr, ml, er[i], el[i]);
