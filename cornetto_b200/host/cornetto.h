@@ -32,6 +32,7 @@ int sdust_main(int argc, char *argv[]);
 int assbed_main(int argc, char *argv[]);
 
 /* misc.c */
+uint64_t cornetto_batch_capacity(const char *path, int n_parts);
 double realtime(void);
 double cputime(void);
 long   peakrss(void);
@@ -71,15 +72,24 @@ void         rec_batch_destroy(rec_batch_t *b);
  * batch makes the batch grow.  Returns the number of records now in the batch. */
 uint32_t     rec_batch_fill(rec_batch_t *b, fastx_t *fx);
 
-/* ---- buffered text output ------------------------------------------------------------------- */
+/* ---- buffered text output (fp == NULL: grows in memory, written out later with outbuf_write) -- */
 typedef struct { char *buf; size_t n, cap; FILE *fp; } outbuf_t;
 void outbuf_init(outbuf_t *o, FILE *fp);
+void outbuf_write(outbuf_t *o, FILE *fp);     /* memory buffer -> fp, then empty it */
 void outbuf_flush(outbuf_t *o);
 void outbuf_free(outbuf_t *o);
 void outbuf_str(outbuf_t *o, const char *s, size_t len);
 void outbuf_u64(outbuf_t *o, uint64_t v);
 void outbuf_i32(outbuf_t *o, int32_t v);
 void outbuf_chr(outbuf_t *o, char c);
+
+/* ---- batch pipeline: one parser thread, one worker thread per GPU context --------------------
+ * Records are parsed into pinned batches by the calling thread while worker threads run the GPU
+ * call and format the text of earlier batches; output is written strictly in batch order, so the
+ * result is byte-identical to the sequential loop of the reference (src/find_telomere.c:101-105).
+ * $CORNETTO_GPUS = number of devices to use (default 1; batches go round-robin over them). */
+typedef void (*batch_fn)(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *out, void *arg);
+void run_batch_pipeline(fastx_t *fx, const char *path, batch_fn fn, void *arg);
 
 /* ---- khash iteration order (src/khash.h:230-348,395-400), for telobreaks' output order -------- */
 size_t khash_str_order(const char *const *names, size_t n, size_t *order);

@@ -1,6 +1,7 @@
 /* cornetto_b200/host/misc.c -- timing helpers for the stderr footer (reference: src/misc.c:48-70),
  * the shared GPU context, and buffered text output. */
 #include <sys/resource.h>
+#include <sys/stat.h>
 #include <sys/time.h>
 
 #include "cornetto.h"
@@ -49,6 +50,26 @@ void cornetto_gpu_release(void)
     g_ctx = NULL;
 }
 
+uint64_t cornetto_batch_capacity(const char *path, int n_parts)
+{
+    uint64_t cap = 1ull << 30;
+    const char *e = getenv("CORNETTO_BATCH_MB"), *eb = getenv("CORNETTO_BATCH_BYTES");
+    if (eb && atoll(eb) > 0) cap = (uint64_t)atoll(eb);
+    else if (e && atoll(e) > 0) cap = (uint64_t)atoll(e) << 20;
+    else {
+        struct stat st;
+        size_t n = strlen(path);
+        int gz = n > 3 && strcmp(path + n - 3, ".gz") == 0;
+        if (!gz && strcmp(path, "-") != 0 && stat(path, &st) == 0 && S_ISREG(st.st_mode)) {
+            /* plain file: the whole input fits one batch per part (records + padding <= file size + slack) */
+            uint64_t want = (uint64_t)st.st_size / (uint64_t)(n_parts > 0 ? n_parts : 1) + (1u << 16);
+            if (want < cap) cap = want;
+        }
+    }
+    if (cap > CORN_MAX_BATCH_BYTES) cap = CORN_MAX_BATCH_BYTES;
+    return cap;
+}
+
 /* ---- output ------------------------------------------------------------------------------------ */
 void outbuf_init(outbuf_t *o, FILE *fp)
 {
@@ -56,12 +77,20 @@ void outbuf_init(outbuf_t *o, FILE *fp)
     o->buf = (char *)malloc(o->cap);
     CORN_MALLOC_CHK(o->buf);
 }
-void outbuf_flush(outbuf_t *o) { if (o->n) fwrite(o->buf, 1, o->n, o->fp); o->n = 0; }
-void outbuf_free(outbuf_t *o) { outbuf_flush(o); fflush(o->fp); free(o->buf); o->buf = NULL; }
-static inline void need(outbuf_t *o, size_t k) { if (o->n + k > o->cap) outbuf_flush(o); }
+void outbuf_flush(outbuf_t *o) { if (o->fp && o->n) { fwrite(o->buf, 1, o->n, o->fp); o->n = 0; } }
+void outbuf_free(outbuf_t *o) { outbuf_flush(o); if (o->fp) fflush(o->fp); free(o->buf); o->buf = NULL; }
+void outbuf_write(outbuf_t *o, FILE *fp) { if (o->n) fwrite(o->buf, 1, o->n, fp); o->n = 0; }
+static inline void need(outbuf_t *o, size_t k)
+{
+    if (o->n + k <= o->cap) return;
+    if (o->fp) { outbuf_flush(o); if (k <= o->cap) return; }
+    while (o->n + k > o->cap) o->cap *= 2;
+    o->buf = (char *)realloc(o->buf, o->cap);
+    CORN_MALLOC_CHK(o->buf);
+}
 void outbuf_str(outbuf_t *o, const char *s, size_t len)
 {
-    if (len > o->cap / 2) { outbuf_flush(o); fwrite(s, 1, len, o->fp); return; }
+    if (o->fp && len > o->cap / 2) { outbuf_flush(o); fwrite(s, 1, len, o->fp); return; }
     need(o, len);
     memcpy(o->buf + o->n, s, len);
     o->n += len;

@@ -6,7 +6,31 @@
  * replaced by corn_gpu_sdust() on batches of records. */
 #include "cornetto.h"
 
-uint64_t cornetto_batch_capacity(const char *path);
+typedef struct { int T, W; } sdust_arg_t;
+
+static void sdust_batch(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *ob, void *arg)
+{
+    const sdust_arg_t *a = (const sdust_arg_t *)arg;
+    corn_batch_t view;
+    corn_hbatch_view(b->hb, &view);
+    corn_intervals_t iv;
+    int r = corn_gpu_sdust(ctx, &view, a->T, a->W, &iv);
+    if (r != CORN_OK) {
+        CORN_ERROR("sdust: %s (%s)", corn_gpu_strerror(r), corn_gpu_last_error(ctx));
+        exit(EXIT_FAILURE);
+    }
+    for (uint32_t rec = 0; rec < iv.n_rec; ++rec) {
+        const char *name = b->name[rec];
+        const size_t nl = strlen(name);
+        for (uint64_t k = iv.rec_first[rec]; k < iv.rec_first[rec + 1]; ++k) {
+            outbuf_str(ob, name, nl);
+            outbuf_chr(ob, '\t'); outbuf_i32(ob, (int32_t)(iv.iv[k] >> 32));
+            outbuf_chr(ob, '\t'); outbuf_i32(ob, (int32_t)iv.iv[k]);
+            outbuf_chr(ob, '\n');
+        }
+    }
+    corn_gpu_intervals_free(&iv);
+}
 
 int sdust_main(int argc, char *argv[])
 {
@@ -41,34 +65,9 @@ int sdust_main(int argc, char *argv[])
     }
     fastx_t *fx = fastx_open(file);
     if (!fx) return 0;     /* the reference reads nothing from an unopenable file and returns 0 */
-    corn_ctx_t *ctx = cornetto_gpu();
-
-    const uint64_t cap = cornetto_batch_capacity(file);
-    uint64_t max_rec = cap / 64 + 16;
-    if (max_rec > (1u << 23)) max_rec = 1u << 23;
-    rec_batch_t *b = rec_batch_create(cap, (uint32_t)max_rec);
-    outbuf_t ob;
-    outbuf_init(&ob, stdout);
-    while (rec_batch_fill(b, fx) > 0) {
-        corn_batch_t view;
-        corn_hbatch_view(b->hb, &view);
-        corn_intervals_t iv;
-        int r = corn_gpu_sdust(ctx, &view, T, W, &iv);
-        if (r != CORN_OK) cornetto_gpu_die("sdust", r);
-        for (uint32_t rec = 0; rec < iv.n_rec; ++rec) {
-            const char *name = b->name[rec];
-            const size_t nl = strlen(name);
-            for (uint64_t k = iv.rec_first[rec]; k < iv.rec_first[rec + 1]; ++k) {
-                outbuf_str(&ob, name, nl);
-                outbuf_chr(&ob, '\t'); outbuf_i32(&ob, (int32_t)(iv.iv[k] >> 32));
-                outbuf_chr(&ob, '\t'); outbuf_i32(&ob, (int32_t)iv.iv[k]);
-                outbuf_chr(&ob, '\n');
-            }
-        }
-        corn_gpu_intervals_free(&iv);
-    }
-    outbuf_free(&ob);
-    rec_batch_destroy(b);
+    sdust_arg_t sa;
+    sa.T = T; sa.W = W;
+    run_batch_pipeline(fx, file, sdust_batch, &sa);
     fastx_close(fx);
     return 0;
 }

@@ -5,27 +5,31 @@
  * one line  name \t len \t strand \t start \t end \t end-start  per maximal tandem run, strand 0
  * runs of a record before its strand 1 runs.  The per-record toupper()/strstr() scan is replaced
  * by corn_gpu_telofind() on batches of records. */
-#include <sys/stat.h>
-
 #include "cornetto.h"
 
-uint64_t cornetto_batch_capacity(const char *path)
+static void telofind_batch(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *ob, void *arg)
 {
-    uint64_t cap = 1ull << 30;
-    const char *e = getenv("CORNETTO_BATCH_MB"), *eb = getenv("CORNETTO_BATCH_BYTES");
-    if (eb && atoll(eb) > 0) cap = (uint64_t)atoll(eb);
-    else if (e && atoll(e) > 0) cap = (uint64_t)atoll(e) << 20;
-    else {
-        struct stat st;
-        size_t n = strlen(path);
-        int gz = n > 3 && strcmp(path + n - 3, ".gz") == 0;
-        if (!gz && strcmp(path, "-") != 0 && stat(path, &st) == 0 && S_ISREG(st.st_mode)) {
-            uint64_t want = (uint64_t)st.st_size + (1u << 16);
-            if (want < cap) cap = want;
-        }
+    const char *query = (const char *)arg;
+    corn_batch_t view;
+    corn_hbatch_view(b->hb, &view);
+    corn_hits_t hits;
+    int r = corn_gpu_telofind(ctx, &view, query, &hits);
+    if (r != CORN_OK) {
+        CORN_ERROR("telofind: %s (%s)", corn_gpu_strerror(r), corn_gpu_last_error(ctx));
+        exit(EXIT_FAILURE);
     }
-    if (cap > CORN_MAX_BATCH_BYTES) cap = CORN_MAX_BATCH_BYTES;
-    return cap;
+    for (uint64_t i = 0; i < hits.n_run; ++i) {
+        const corn_run_t *h = &hits.run[i];
+        const char *name = b->name[h->rec];
+        outbuf_str(ob, name, strlen(name));
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, view.length[h->rec]);
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->strand);
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->start);
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->end);
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->end - h->start);
+        outbuf_chr(ob, '\n');
+    }
+    corn_gpu_hits_free(&hits);
 }
 
 int find_telomere_main(int argc, char *argv[])
@@ -40,41 +44,12 @@ int find_telomere_main(int argc, char *argv[])
 
     fastx_t *fx = fastx_open(fasta);
     CORN_F_CHK(fx, fasta);
-    corn_ctx_t *ctx = cornetto_gpu();
-
-    const uint64_t cap = cornetto_batch_capacity(fasta);
-    uint64_t max_rec = cap / 64 + 16;
-    if (max_rec > (1u << 23)) max_rec = 1u << 23;
-    rec_batch_t *b = rec_batch_create(cap, (uint32_t)max_rec);
-    outbuf_t ob;
-    outbuf_init(&ob, stdout);
-
     if (query[0] == 0) {
         /* the reference spins forever on an empty motif (strstr always matches); refuse instead */
         CORN_ERROR("%s", "empty motif");
         exit(EXIT_FAILURE);
     }
-    while (rec_batch_fill(b, fx) > 0) {
-        corn_batch_t view;
-        corn_hbatch_view(b->hb, &view);
-        corn_hits_t hits;
-        int r = corn_gpu_telofind(ctx, &view, query, &hits);
-        if (r != CORN_OK) cornetto_gpu_die("telofind", r);
-        for (uint64_t i = 0; i < hits.n_run; ++i) {
-            const corn_run_t *h = &hits.run[i];
-            const char *name = b->name[h->rec];
-            outbuf_str(&ob, name, strlen(name));
-            outbuf_chr(&ob, '\t'); outbuf_u64(&ob, view.length[h->rec]);
-            outbuf_chr(&ob, '\t'); outbuf_u64(&ob, h->strand);
-            outbuf_chr(&ob, '\t'); outbuf_u64(&ob, h->start);
-            outbuf_chr(&ob, '\t'); outbuf_u64(&ob, h->end);
-            outbuf_chr(&ob, '\t'); outbuf_u64(&ob, h->end - h->start);
-            outbuf_chr(&ob, '\n');
-        }
-        corn_gpu_hits_free(&hits);
-    }
-    outbuf_free(&ob);
-    rec_batch_destroy(b);
+    run_batch_pipeline(fx, fasta, telofind_batch, (void *)query);
     fastx_close(fx);
     return EXIT_SUCCESS;
 }
