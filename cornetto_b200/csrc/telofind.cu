@@ -36,6 +36,8 @@ struct ScanParams {
     uint32_t *c_c, *c_d;       // after classification: end masks fwd / rev
     uint4    *tile_cnt;        // per tile: #start_f, #end_f, #start_r, #end_r
     uint32_t *tile_ncand;
+    uint32_t *dense_list;      // tiles whose candidate list is long (telomeres, satellites): classified by
+    uint32_t *dense_count;     // k_telofind_classify_dense with the whole GPU instead of by the scanning warp
     const uint8_t *pat;        // device: fwd[256] then rev[256]
     uint64_t fc, rc;           // packed 2-bit codes (plane matcher)
     int      m;
@@ -116,30 +118,70 @@ __device__ __forceinline__ void heads_tails(const uint8_t *chunk, uint32_t v, co
     }
 }
 
+__device__ __forceinline__ void classify_entry(const ScanParams &P, size_t slot, uint32_t &n_sf, uint32_t &n_ef, uint32_t &n_sr, uint32_t &n_er)
+{
+    const int m = P.m;
+    const uint32_t idx = __ldcg(P.c_idx + slot);
+    const uint8_t *chunk = P.seq + (size_t)idx * CORN_CHUNK_BYTES;
+    const uint32_t vf = verify_mask(chunk, __ldcg(P.c_a + slot), P.pat, m);
+    const uint32_t vr = verify_mask(chunk, __ldcg(P.c_b + slot), P.pat + 256, m);
+    uint32_t sf = vf, ef = 0, sr = vr, er = 0;
+    if (!P.bordered) {
+        heads_tails(chunk, vf, P.pat, m, sf, ef);
+        heads_tails(chunk, vr, P.pat + 256, m, sr, er);
+    }
+    P.c_a[slot] = sf; P.c_b[slot] = sr;
+    P.c_c[slot] = ef; P.c_d[slot] = er;
+    n_sf += __popc(sf); n_ef += __popc(ef); n_sr += __popc(sr); n_er += __popc(er);
+}
+
+// A tile with more candidate chunks than this is not classified by the warp that scanned it: a
+// telomere fills all 1024 slots of its tile, and one warp chewing through them while the rest of the
+// GPU has run out of tiles was the kernel's tail.  Such tiles are queued for k_telofind_classify_dense.
+#define CORN_DENSE_TILE 96u
+
 __device__ void classify_tile(const ScanParams &P, uint32_t tile, uint32_t cnt, int lane)
 {
     const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
-    const int m = P.m;
-    uint32_t n_sf = 0, n_ef = 0, n_sr = 0, n_er = 0;
-    for (uint32_t e = lane; e < cnt; e += 32) {
-        const uint32_t idx = __ldcg(P.c_idx + base + e);
-        const uint8_t *chunk = P.seq + (size_t)idx * CORN_CHUNK_BYTES;
-        const uint32_t vf = verify_mask(chunk, __ldcg(P.c_a + base + e), P.pat, m);
-        const uint32_t vr = verify_mask(chunk, __ldcg(P.c_b + base + e), P.pat + 256, m);
-        uint32_t sf = vf, ef = 0, sr = vr, er = 0;
-        if (!P.bordered) {
-            heads_tails(chunk, vf, P.pat, m, sf, ef);
-            heads_tails(chunk, vr, P.pat + 256, m, sr, er);
+    if (cnt > CORN_DENSE_TILE) {
+        if (lane == 0) {
+            P.tile_ncand[tile] = cnt;
+            P.dense_list[atomicAdd(P.dense_count, 1u)] = tile;
         }
-        P.c_a[base + e] = sf; P.c_b[base + e] = sr;
-        P.c_c[base + e] = ef; P.c_d[base + e] = er;
-        n_sf += __popc(sf); n_ef += __popc(ef); n_sr += __popc(sr); n_er += __popc(er);
+        return;
     }
+    uint32_t n_sf = 0, n_ef = 0, n_sr = 0, n_er = 0;
+    for (uint32_t e = lane; e < cnt; e += 32) classify_entry(P, base + e, n_sf, n_ef, n_sr, n_er);
     n_sf = corn_warp_sum(n_sf); n_ef = corn_warp_sum(n_ef);
     n_sr = corn_warp_sum(n_sr); n_er = corn_warp_sum(n_er);
     if (lane == 0) {
         P.tile_cnt[tile] = make_uint4(n_sf, n_ef, n_sr, n_er);
         P.tile_ncand[tile] = cnt;
+    }
+}
+
+// one block per queued tile (grid-stride over the queue), one thread per candidate chunk
+__global__ void __launch_bounds__(256) k_telofind_classify_dense(const ScanParams P)
+{
+    __shared__ uint32_t red[4][8];
+    const uint32_t n_dense = *P.dense_count;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t d = blockIdx.x; d < n_dense; d += gridDim.x) {
+        const uint32_t tile = P.dense_list[d];
+        const uint32_t cnt = P.tile_ncand[tile];
+        const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
+        uint32_t n_sf = 0, n_ef = 0, n_sr = 0, n_er = 0;
+        for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) classify_entry(P, base + e, n_sf, n_ef, n_sr, n_er);
+        n_sf = corn_warp_sum(n_sf); n_ef = corn_warp_sum(n_ef);
+        n_sr = corn_warp_sum(n_sr); n_er = corn_warp_sum(n_er);
+        if (lane == 0) { red[0][warp] = n_sf; red[1][warp] = n_ef; red[2][warp] = n_sr; red[3][warp] = n_er; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint4 t = make_uint4(0, 0, 0, 0);
+            for (int w = 0; w < 8; ++w) { t.x += red[0][w]; t.y += red[1][w]; t.z += red[2][w]; t.w += red[3][w]; }
+            P.tile_cnt[tile] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -484,7 +526,7 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
     const size_t n_slots = (size_t)n_tiles * CORN_TILE_CHUNKS;
     CORN_TRY(corn_dbuf_reserve(ctx, &ctx->cand, 5 * n_slots * sizeof(uint32_t) + 256));
     // tile_tab: counts (uint4) | offsets (uint4) | ncand (u32) ; misc: totals uint4, counter, err, pattern
-    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->tile_tab, (size_t)n_tiles * (2 * sizeof(uint4) + sizeof(uint32_t)) + 256));
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->tile_tab, (size_t)n_tiles * (2 * sizeof(uint4) + 2 * sizeof(uint32_t)) + 256));
     CORN_TRY(corn_dbuf_reserve(ctx, &ctx->misc, 4096));
 
     uint32_t *cand = (uint32_t *)ctx->cand.p;
@@ -497,10 +539,12 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
     sp.tile_cnt = (uint4 *)ctx->tile_tab.p;
     uint4 *tile_off = sp.tile_cnt + n_tiles;
     sp.tile_ncand = (uint32_t *)(tile_off + n_tiles);
+    sp.dense_list = sp.tile_ncand + n_tiles;
     uint8_t *misc = (uint8_t *)ctx->misc.p;
     uint4 *d_totals = (uint4 *)misc;                    // 16 B
-    sp.tile_counter = (uint32_t *)(misc + 16);          // [0] tile counter, [1] error counter
+    sp.tile_counter = (uint32_t *)(misc + 16);          // [0] tile counter, [1] error counter, [2] dense-tile queue length
     uint32_t *d_err = sp.tile_counter + 1;
+    sp.dense_count = sp.tile_counter + 2;
     uint8_t *d_pat = misc + 64;                         // 512 B
     sp.pat = d_pat;
     sp.fc = mi.fc; sp.rc = mi.rc; sp.m = mi.m; sp.bordered = mi.bordered;
@@ -511,7 +555,7 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
     memcpy(hpat, mi.fwd, mi.m); memcpy(hpat + 256, mi.rev, mi.m);
     memcpy(ctx->h_pinned_small, hpat, 512);
     CORN_CUDA(ctx, cudaMemcpyAsync(d_pat, ctx->h_pinned_small, 512, cudaMemcpyHostToDevice, st));
-    k_reset_counter<<<1, 32, 0, st>>>(sp.tile_counter, 2);
+    k_reset_counter<<<1, 32, 0, st>>>(sp.tile_counter, 3);
     corn_count_launch(ctx);
 
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
@@ -530,6 +574,11 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
         CORN_LAUNCH_CHECK(ctx);
     }
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    if (n_tiles) {
+        k_telofind_classify_dense<<<ctx->sm_count * 2, 256, 0, st>>>(sp);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+    }
 
     CORN_TRY(corn_scan_u32x4(ctx, sp.tile_cnt, tile_off, n_tiles, d_totals));
 
