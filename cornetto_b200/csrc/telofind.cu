@@ -342,38 +342,80 @@ __device__ __forceinline__ void emit_bits(uint32_t mask, uint32_t *dst, uint32_t
     }
 }
 
+// one batch = 32 consecutive candidate chunks of a tile, one per lane; `off` = where this batch's
+// events start in the four lists.  Returns the batch's counts.
+__device__ __forceinline__ uint4 scatter_batch(const ScatterParams &P, size_t base, uint32_t e0, uint32_t cnt, uint4 off,
+                                               uint32_t *start_f, uint32_t *end_f, uint32_t *start_r, uint32_t *end_r,
+                                               int lane, bool write)
+{
+    const uint32_t e = e0 + lane;
+    uint32_t idx = 0, sf = 0, sr = 0, ef = 0, er = 0;
+    if (e < cnt) {
+        idx = P.c_idx[base + e];
+        sf = P.c_a[base + e]; sr = P.c_b[base + e];
+        ef = P.c_c[base + e]; er = P.c_d[base + e];
+    }
+    // two 16-bit counters per word: per-lane counts <= 32, warp totals <= 1024
+    const uint32_t k_f = __popc(sf) | (__popc(ef) << 16), k_r = __popc(sr) | (__popc(er) << 16);
+    const uint32_t i_f = corn_warp_iscan(k_f, lane), i_r = corn_warp_iscan(k_r, lane);
+    if (write) {
+        const uint32_t pos0 = idx * CORN_CHUNK_BYTES;
+        const uint32_t x_f = i_f - k_f, x_r = i_r - k_r;          // exclusive
+        emit_bits(sf, start_f + off.x + (x_f & 0xFFFFu), pos0);
+        emit_bits(ef, end_f + off.y + (x_f >> 16), pos0 + P.m);
+        emit_bits(sr, start_r + off.z + (x_r & 0xFFFFu), pos0);
+        emit_bits(er, end_r + off.w + (x_r >> 16), pos0 + P.m);
+    }
+    const uint32_t t_f = __shfl_sync(0xffffffffu, i_f, 31), t_r = __shfl_sync(0xffffffffu, i_r, 31);
+    return make_uint4(t_f & 0xFFFFu, t_f >> 16, t_r & 0xFFFFu, t_r >> 16);
+}
+
+// A block owns 8 consecutive tiles.  Ordinary tiles: one warp each.  Dense tiles (see
+// CORN_DENSE_TILE): all eight warps, batch counts -> scan over the batches -> write.
 __global__ void __launch_bounds__(256) k_telofind_scatter(const ScatterParams P)
 {
-    const int lane = threadIdx.x & 31;
-    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (tile >= P.n_tiles) return;
-    const uint32_t cnt = P.tile_ncand[tile];
-    if (cnt == 0) return;
+    __shared__ uint4 bat[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint4 tot = *P.totals;
     if ((uint64_t)tot.x + tot.y + tot.z + tot.w > P.capacity) return;     // host grows the buffer and relaunches
     uint32_t *start_f = P.ev, *end_f = start_f + tot.x, *start_r = end_f + tot.y, *end_r = start_r + tot.z;
-    uint4 off = P.tile_off[tile];
-    const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
-    for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        uint32_t idx = 0, sf = 0, sr = 0, ef = 0, er = 0;
-        if (e < cnt) {
-            idx = P.c_idx[base + e];
-            sf = P.c_a[base + e]; sr = P.c_b[base + e];
-            ef = P.c_c[base + e]; er = P.c_d[base + e];
+    const uint32_t tile0 = blockIdx.x * 8u;
+    {
+        const uint32_t tile = tile0 + warp;
+        const uint32_t cnt = tile < P.n_tiles ? P.tile_ncand[tile] : 0u;
+        if (cnt && cnt <= CORN_DENSE_TILE) {
+            uint4 off = P.tile_off[tile];
+            const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
+            for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+                const uint4 c = scatter_batch(P, base, e0, cnt, off, start_f, end_f, start_r, end_r, lane, true);
+                off.x += c.x; off.y += c.y; off.z += c.z; off.w += c.w;
+            }
         }
-        const uint32_t pos0 = idx * CORN_CHUNK_BYTES;
-        const uint32_t k_sf = __popc(sf), k_ef = __popc(ef), k_sr = __popc(sr), k_er = __popc(er);
-        const uint32_t i_sf = corn_warp_iscan(k_sf, lane), i_ef = corn_warp_iscan(k_ef, lane);
-        const uint32_t i_sr = corn_warp_iscan(k_sr, lane), i_er = corn_warp_iscan(k_er, lane);
-        emit_bits(sf, start_f + off.x + i_sf - k_sf, pos0);
-        emit_bits(ef, end_f + off.y + i_ef - k_ef, pos0 + P.m);
-        emit_bits(sr, start_r + off.z + i_sr - k_sr, pos0);
-        emit_bits(er, end_r + off.w + i_er - k_er, pos0 + P.m);
-        off.x += __shfl_sync(0xffffffffu, i_sf, 31);
-        off.y += __shfl_sync(0xffffffffu, i_ef, 31);
-        off.z += __shfl_sync(0xffffffffu, i_sr, 31);
-        off.w += __shfl_sync(0xffffffffu, i_er, 31);
+    }
+    for (uint32_t t = 0; t < 8; ++t) {
+        const uint32_t tile = tile0 + t;
+        if (tile >= P.n_tiles) break;
+        const uint32_t cnt = P.tile_ncand[tile];
+        if (cnt <= CORN_DENSE_TILE) continue;                              // uniform over the block
+        const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
+        const uint32_t nb = (cnt + 31) / 32;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        for (uint32_t b = warp; b < nb; b += 8) {
+            const uint4 c = scatter_batch(P, base, b * 32, cnt, zero, start_f, end_f, start_r, end_r, lane, false);
+            if (lane == 0) bat[b] = c;
+        }
+        __syncthreads();
+        if (warp == 0) {                                                   // exclusive scan over <= 32 batches
+            const uint4 c = (uint32_t)lane < nb ? bat[lane] : zero;
+            const uint4 o = P.tile_off[tile];
+            const uint32_t ix = corn_warp_iscan(c.x, lane), iy = corn_warp_iscan(c.y, lane);
+            const uint32_t iz = corn_warp_iscan(c.z, lane), iw = corn_warp_iscan(c.w, lane);
+            bat[lane] = make_uint4(o.x + ix - c.x, o.y + iy - c.y, o.z + iz - c.z, o.w + iw - c.w);
+        }
+        __syncthreads();
+        for (uint32_t b = warp; b < nb; b += 8)
+            scatter_batch(P, base, b * 32, cnt, bat[b], start_f, end_f, start_r, end_r, lane, true);
+        __syncthreads();
     }
 }
 
