@@ -342,22 +342,29 @@ __device__ __forceinline__ void emit_bits(uint32_t mask, uint32_t *dst, uint32_t
     }
 }
 
-// one batch = 32 consecutive candidate chunks of a tile, one per lane; `off` = where this batch's
-// events start in the four lists.  Returns the batch's counts.
+// one batch = G consecutive candidate chunks of a tile, one per lane of a G-lane group (G = 8 for
+// ordinary tiles: their lists hold ~16 entries, so four tiles share a warp; G = 32 for dense
+// tiles).  `off` = where this batch's events start in the four lists.  Returns the batch's counts.
+template <int G>
 __device__ __forceinline__ uint4 scatter_batch(const ScatterParams &P, size_t base, uint32_t e0, uint32_t cnt, uint4 off,
                                                uint32_t *start_f, uint32_t *end_f, uint32_t *start_r, uint32_t *end_r,
-                                               int lane, bool write)
+                                               int gl /* lane within the group */, bool write)
 {
-    const uint32_t e = e0 + lane;
+    const uint32_t e = e0 + gl;
     uint32_t idx = 0, sf = 0, sr = 0, ef = 0, er = 0;
     if (e < cnt) {
         idx = P.c_idx[base + e];
         sf = P.c_a[base + e]; sr = P.c_b[base + e];
         ef = P.c_c[base + e]; er = P.c_d[base + e];
     }
-    // two 16-bit counters per word: per-lane counts <= 32, warp totals <= 1024
+    // two 16-bit counters per word: per-lane counts <= 32, group totals <= 1024
     const uint32_t k_f = __popc(sf) | (__popc(ef) << 16), k_r = __popc(sr) | (__popc(er) << 16);
-    const uint32_t i_f = corn_warp_iscan(k_f, lane), i_r = corn_warp_iscan(k_r, lane);
+    uint32_t i_f = k_f, i_r = k_r;
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, i_f, o, G), b = __shfl_up_sync(0xffffffffu, i_r, o, G);
+        if (gl >= o) { i_f += a; i_r += b; }
+    }
     if (write) {
         const uint32_t pos0 = idx * CORN_CHUNK_BYTES;
         const uint32_t x_f = i_f - k_f, x_r = i_r - k_r;          // exclusive
@@ -366,11 +373,11 @@ __device__ __forceinline__ uint4 scatter_batch(const ScatterParams &P, size_t ba
         emit_bits(sr, start_r + off.z + (x_r & 0xFFFFu), pos0);
         emit_bits(er, end_r + off.w + (x_r >> 16), pos0 + P.m);
     }
-    const uint32_t t_f = __shfl_sync(0xffffffffu, i_f, 31), t_r = __shfl_sync(0xffffffffu, i_r, 31);
+    const uint32_t t_f = __shfl_sync(0xffffffffu, i_f, G - 1, G), t_r = __shfl_sync(0xffffffffu, i_r, G - 1, G);
     return make_uint4(t_f & 0xFFFFu, t_f >> 16, t_r & 0xFFFFu, t_r >> 16);
 }
 
-// A block owns 8 consecutive tiles.  Ordinary tiles: one warp each.  Dense tiles (see
+// A block owns 32 consecutive tiles.  Ordinary tiles: one 8-lane group each.  Dense tiles (see
 // CORN_DENSE_TILE): all eight warps, batch counts -> scan over the batches -> write.
 __global__ void __launch_bounds__(256) k_telofind_scatter(const ScatterParams P)
 {
@@ -379,20 +386,24 @@ __global__ void __launch_bounds__(256) k_telofind_scatter(const ScatterParams P)
     const uint4 tot = *P.totals;
     if ((uint64_t)tot.x + tot.y + tot.z + tot.w > P.capacity) return;     // host grows the buffer and relaunches
     uint32_t *start_f = P.ev, *end_f = start_f + tot.x, *start_r = end_f + tot.y, *end_r = start_r + tot.z;
-    const uint32_t tile0 = blockIdx.x * 8u;
+    const uint32_t tile0 = blockIdx.x * 32u;
     {
-        const uint32_t tile = tile0 + warp;
-        const uint32_t cnt = tile < P.n_tiles ? P.tile_ncand[tile] : 0u;
-        if (cnt && cnt <= CORN_DENSE_TILE) {
-            uint4 off = P.tile_off[tile];
-            const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
-            for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
-                const uint4 c = scatter_batch(P, base, e0, cnt, off, start_f, end_f, start_r, end_r, lane, true);
-                off.x += c.x; off.y += c.y; off.z += c.z; off.w += c.w;
-            }
+        const uint32_t tile = tile0 + (threadIdx.x >> 3);
+        const int gl = threadIdx.x & 7;
+        uint32_t cnt = tile < P.n_tiles ? P.tile_ncand[tile] : 0u;
+        if (cnt > CORN_DENSE_TILE) cnt = 0;
+        uint4 off = cnt ? P.tile_off[tile] : make_uint4(0, 0, 0, 0);
+        const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
+        // the four groups of a warp loop together (shuffles are warp-wide): until the longest list is done
+        uint32_t longest = cnt;
+        longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, 8));
+        longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, 16));
+        for (uint32_t e0 = 0; e0 < longest; e0 += 8) {
+            const uint4 c = scatter_batch<8>(P, base, e0, cnt, off, start_f, end_f, start_r, end_r, gl, true);
+            off.x += c.x; off.y += c.y; off.z += c.z; off.w += c.w;
         }
     }
-    for (uint32_t t = 0; t < 8; ++t) {
+    for (uint32_t t = 0; t < 32; ++t) {
         const uint32_t tile = tile0 + t;
         if (tile >= P.n_tiles) break;
         const uint32_t cnt = P.tile_ncand[tile];
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(256) k_telofind_scatter(const ScatterParams P)
         const uint32_t nb = (cnt + 31) / 32;
         const uint4 zero = make_uint4(0, 0, 0, 0);
         for (uint32_t b = warp; b < nb; b += 8) {
-            const uint4 c = scatter_batch(P, base, b * 32, cnt, zero, start_f, end_f, start_r, end_r, lane, false);
+            const uint4 c = scatter_batch<32>(P, base, b * 32, cnt, zero, start_f, end_f, start_r, end_r, lane, false);
             if (lane == 0) bat[b] = c;
         }
         __syncthreads();
@@ -414,7 +425,7 @@ __global__ void __launch_bounds__(256) k_telofind_scatter(const ScatterParams P)
         }
         __syncthreads();
         for (uint32_t b = warp; b < nb; b += 8)
-            scatter_batch(P, base, b * 32, cnt, bat[b], start_f, end_f, start_r, end_r, lane, true);
+            scatter_batch<32>(P, base, b * 32, cnt, bat[b], start_f, end_f, start_r, end_r, lane, true);
         __syncthreads();
     }
 }
@@ -642,7 +653,7 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
         sc.tile_off = tile_off; sc.tile_ncand = sp.tile_ncand; sc.n_tiles = n_tiles;
         sc.ev = ev; sc.totals = d_totals; sc.capacity = (uint32_t)ev_cap; sc.m = mi.m;
         if (n_tiles) {
-            k_telofind_scatter<<<(n_tiles + 7) / 8, 256, 0, st>>>(sc);
+            k_telofind_scatter<<<(n_tiles + 31) / 32, 256, 0, st>>>(sc);
             corn_count_launch(ctx);
             CORN_LAUNCH_CHECK(ctx);
         }
