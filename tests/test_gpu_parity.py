@@ -301,3 +301,18 @@ def test_abi_async_fused_matches_sync(ctx, capi):
         c2.free(db)
         c2.close()
         hb.close()
+
+
+def test_cli_multi_gpu_workers(tmp_path, oracle_bin):
+    """CORNETTO_GPUS=N: batches round-robin over N contexts (N devices when present), stdout in batch
+    order.  With one visible device the request is clamped and the two workers share it."""
+    recs = synth.assembly(61, [60_000, 9_000, 33_000, 1200, 999, 48_000, 7, 21_000], n_gaps=2, telo=(40, 300), microsat_per_mb=1500.0)
+    fa = write(str(tmp_path / "m.fa"), synth.fasta_bytes(recs))
+    want_t, _, _ = run([oracle_bin, "telofind", fa])
+    want_s, _, _ = run([oracle_bin, "sdust", fa])
+    for gpus in ("1", "2", "4"):
+        env = {"CORNETTO_GPUS": gpus, "CORNETTO_BATCH_BYTES": "40000"}
+        out, _, _ = cornetto(["telofind", fa], env=env)
+        assert out == want_t, gpus
+        out, _, _ = cornetto(["sdust", fa], env=env)
+        assert out == want_s, gpus
