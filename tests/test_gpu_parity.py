@@ -316,3 +316,30 @@ def test_cli_multi_gpu_workers(tmp_path, oracle_bin):
         assert out == want_t, gpus
         out, _, _ = cornetto(["sdust", fa], env=env)
         assert out == want_s, gpus
+
+
+def test_abi_many_short_reads(ctx, capi):
+    """FASTQ-like batch (BASELINE.json configs[4] in miniature): tens of thousands of records, many
+    shorter than a tile, some shorter than the motif or empty -- exercises the record tables."""
+    rng = np.random.default_rng(71)
+    lens = np.maximum(0, (rng.lognormal(0.0, 0.9, size=30_000) * 900).astype(np.int64) - 50)
+    lens[::997] = 0
+    lens[1::991] = 5
+    recs = []
+    for i, L in enumerate(lens):
+        s = synth.random_dna(rng, int(L))
+        if L >= 60 and i % 7 == 0:
+            k = int(rng.integers(2, 9))
+            s[-6 * k:] = np.tile(np.frombuffer(b"TTAGGG", dtype=np.uint8), k)
+        if L >= 60 and i % 11 == 0:
+            k = int(rng.integers(2, 9))
+            s[:6 * k] = np.tile(np.frombuffer(b"CCCTAA", dtype=np.uint8), k)
+        recs.append(s)
+    hb = capi.HostBatch(recs)
+    got = as_rows(ctx.telofind(hb, "TTAGGG"))
+    want = oracle_telofind(recs, "TTAGGG")
+    assert got.shape == want.shape and (got == want).all()
+    iv, first = ctx.sdust(hb, 20, 64)
+    wiv, wfirst = oracle_sdust(recs, 20, 64)
+    assert (first == wfirst).all() and len(iv) == len(wiv) and (iv == wiv).all()
+    hb.close()
