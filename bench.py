@@ -286,8 +286,8 @@ def load_traffic():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CORN_BENCH_WORKLOAD", "c2"))
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -413,6 +413,7 @@ def main():
     import ctypes as C
     hb = C.c_void_p()
     capi._check(None, L.corn_hbatch_create(total_bytes + 64, len(lengths), C.byref(hb)), "corn_hbatch_create")
+    capi._check(None, L.corn_hbatch_pin(hb), "corn_hbatch_pin")
     cur = L.corn_hbatch_cursor(hb)
     capi._check(ctx.ctx, L.corn_bench_download_all(ctx.ctx, db, cur), "download")
     for Lr in lengths:                           # same layout rule => same offsets; padding is already zero

@@ -53,7 +53,7 @@ class Timing(C.Structure):
 SYMBOLS = [
     "corn_gpu_device_count", "corn_gpu_init", "corn_gpu_destroy", "corn_gpu_strerror", "corn_gpu_last_error",
     "corn_gpu_set_stream",
-    "corn_hbatch_create", "corn_hbatch_destroy", "corn_hbatch_reset", "corn_hbatch_room", "corn_hbatch_cursor",
+    "corn_hbatch_create", "corn_hbatch_pin", "corn_hbatch_destroy", "corn_hbatch_reset", "corn_hbatch_room", "corn_hbatch_cursor",
     "corn_hbatch_commit", "corn_hbatch_add", "corn_hbatch_view",
     "corn_gpu_upload", "corn_gpu_dbatch_free", "corn_gpu_dbatch_seq_ptr", "corn_gpu_dbatch_bytes",
     "corn_gpu_dbatch_alloc", "corn_gpu_dbatch_download",
@@ -87,6 +87,7 @@ def load() -> C.CDLL:
     L.corn_gpu_last_error.restype = C.c_char_p
     L.corn_gpu_set_stream.argtypes = [vp, vp]
     L.corn_hbatch_create.argtypes = [u64, u32, C.POINTER(vp)]
+    L.corn_hbatch_pin.argtypes = [vp]
     L.corn_hbatch_destroy.argtypes = [vp]
     L.corn_hbatch_destroy.restype = None
     L.corn_hbatch_reset.argtypes = [vp]
@@ -201,6 +202,7 @@ class Context:
 
     # ---- batches ---------------------------------------------------------------------------------
     def upload(self, hb: HostBatch):
+        self.L.corn_hbatch_pin(hb.h)
         db = C.c_void_p()
         _check(self.ctx, self.L.corn_gpu_upload(self.ctx, C.byref(hb.view), C.byref(db)), "corn_gpu_upload")
         return db
@@ -221,6 +223,7 @@ class Context:
 
     # ---- operators -------------------------------------------------------------------------------
     def telofind(self, hb: HostBatch, motif: str = "TTAGGG") -> np.ndarray:
+        self.L.corn_hbatch_pin(hb.h)
         h = Hits()
         _check(self.ctx, self.L.corn_gpu_telofind(self.ctx, C.byref(hb.view), motif.encode(), C.byref(h)), "corn_gpu_telofind")
         out = _copy_struct_array(h.run, h.n_run, RUN_DTYPE)
@@ -259,6 +262,7 @@ class Context:
         return vals, first
 
     def sdust(self, hb: HostBatch, T: int = 20, W: int = 64):
+        self.L.corn_hbatch_pin(hb.h)
         iv = Intervals()
         _check(self.ctx, self.L.corn_gpu_sdust(self.ctx, C.byref(hb.view), T, W, C.byref(iv)), "corn_gpu_sdust")
         return self._intervals(iv)

@@ -211,11 +211,10 @@ extern "C" int corn_hbatch_create(uint64_t capacity_bytes, uint32_t max_records,
     if (capacity_bytes > CORN_MAX_BATCH_BYTES) return CORN_E_TOOBIG;
     corn_hbatch *hb = (corn_hbatch *)calloc(1, sizeof *hb);
     if (!hb) return CORN_E_NOMEM;
-    // pinned when a CUDA device is present, plain memory otherwise (so that host-only logic
-    // -- parsing, layout -- can be unit-tested on a machine without a GPU)
+    // plain page-aligned memory: no CUDA call here (driver start-up takes seconds and must not
+    // delay the parser); corn_hbatch_pin() page-locks it later, on the thread that owns the GPU
     void *p = NULL;
-    if (cudaMallocHost(&p, capacity_bytes) == cudaSuccess) hb->pinned = 1;
-    else { cudaGetLastError(); p = malloc(capacity_bytes); }
+    if (posix_memalign(&p, 4096, capacity_bytes) != 0) p = NULL;
     hb->seq = (uint8_t *)p;
     hb->offset = (uint64_t *)malloc(sizeof(uint64_t) * max_records);
     hb->length = (uint32_t *)malloc(sizeof(uint32_t) * max_records);
@@ -229,8 +228,18 @@ extern "C" int corn_hbatch_create(uint64_t capacity_bytes, uint32_t max_records,
 extern "C" void corn_hbatch_destroy(corn_hbatch_t *hb)
 {
     if (!hb) return;
-    if (hb->seq) { if (hb->pinned) cudaFreeHost(hb->seq); else free(hb->seq); }
+    if (hb->seq) { if (hb->pinned) cudaHostUnregister(hb->seq); free(hb->seq); }
     free(hb->offset); free(hb->length); free(hb);
+}
+
+extern "C" int corn_hbatch_pin(corn_hbatch_t *hb)
+{
+    if (!hb) return CORN_E_ARG;
+    if (hb->pinned) return CORN_OK;
+    cudaError_t e = cudaHostRegister(hb->seq, hb->cap, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? CORN_E_NOMEM : CORN_E_CUDA; }
+    hb->pinned = 1;
+    return CORN_OK;
 }
 
 extern "C" void corn_hbatch_reset(corn_hbatch_t *hb) { hb->used = 0; hb->n_rec = 0; }

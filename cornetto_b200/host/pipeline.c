@@ -29,7 +29,7 @@ static void *worker_main(void *p)
     worker_t *w = (worker_t *)p;
     int r = corn_gpu_init(w->device, &w->ctx);
     if (r != CORN_OK) {
-        CORN_ERROR("cannot initialise GPU %d: %s", w->device, corn_gpu_strerror(r));
+        CORN_ERROR("cannot initialise the GPU (device %d): %s", w->device, corn_gpu_strerror(r));
         exit(EXIT_FAILURE);
     }
     for (;;) {
@@ -38,6 +38,7 @@ static void *worker_main(void *p)
         const int st = w->state;
         pthread_mutex_unlock(&w->mu);
         if (st == 2) break;
+        corn_hbatch_pin(w->batch->hb);                  /* once per buffer; a failure only costs H2D speed */
         w->fn(w->ctx, w->batch, &w->out, w->arg);
         pthread_mutex_lock(&w->mu);
         w->state = 0;
@@ -60,12 +61,14 @@ void run_batch_pipeline(fastx_t *fx, const char *path, batch_fn fn, void *arg)
     int n_gpus = 1;
     const char *e = getenv("CORNETTO_GPUS");
     if (e && atoi(e) > 0) n_gpus = atoi(e);
-    const int avail = corn_gpu_device_count();
-    if (avail <= 0) {
-        CORN_ERROR("cannot initialise the GPU: %s", corn_gpu_strerror(avail < 0 ? avail : CORN_E_NOGPU));
-        exit(EXIT_FAILURE);
+    if (n_gpus > 1) {                                   /* (the single-GPU path leaves all CUDA start-up to the workers, */
+        const int avail = corn_gpu_device_count();      /*  so that parsing overlaps the seconds the driver needs)       */
+        if (avail <= 0) {
+            CORN_ERROR("cannot initialise the GPU: %s", corn_gpu_strerror(avail < 0 ? avail : CORN_E_NOGPU));
+            exit(EXIT_FAILURE);
+        }
+        if (n_gpus > avail) n_gpus = avail;
     }
-    if (n_gpus > avail) n_gpus = avail;
     const int n_workers = n_gpus > 1 ? n_gpus : 2;     /* one device: two workers double-buffer */
     const char *dev0 = getenv("CORNETTO_GPU");
     const int base_dev = (n_gpus == 1 && dev0) ? atoi(dev0) : 0;

@@ -71,11 +71,14 @@ typedef struct corn_batch {
     uint64_t        total_bytes;  /* multiple of CORN_ALIGN, <= CORN_MAX_BATCH_BYTES */
 } corn_batch_t;
 
-/* Builder for a batch in PINNED host memory (what the kseq-style reader fills directly, so the
- * H2D copy runs at full PCIe rate).  Replaces the per-record kstring_t buffer that
- * kseq_read() grows with realloc (src/kseq.h:201-211). */
+/* Builder for a host batch (what the kseq-style reader fills directly).  Replaces the per-record
+ * kstring_t buffer that kseq_read() grows with realloc (src/kseq.h:201-211).
+ * corn_hbatch_create() touches no CUDA API, so parsing can start while the driver is still
+ * initialising on another thread; corn_hbatch_pin() page-locks the buffer (cudaHostRegister, once;
+ * needs a device) so that the H2D copy runs at full PCIe rate. */
 typedef struct corn_hbatch corn_hbatch_t;
 int      corn_hbatch_create(uint64_t capacity_bytes, uint32_t max_records, corn_hbatch_t **hb);
+int      corn_hbatch_pin(corn_hbatch_t *hb);
 void     corn_hbatch_destroy(corn_hbatch_t *hb);
 void     corn_hbatch_reset(corn_hbatch_t *hb);
 /* Space left for ONE more record (bytes of sequence), 0 if the record table is full. */
