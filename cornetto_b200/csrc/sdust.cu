@@ -46,22 +46,25 @@ struct SdParams {
     int T, W, C;
     uint32_t cap;
     uint64_t *slots;                // n_chunks * cap
+    uint32_t *gslots;               // n_chunks * (W | 1) words, zeroed: the perfect-interval rings
     uint32_t *cnt;                  // [n_chunks]
     uint32_t *err;
 };
 
 // ---- shared-memory layout of a block -------------------------------------------------------------
 //   [ cw | cv columns : 32 rows x SD_BLOCK x 4 B ][ ring arrays : SD_BLOCK x ring_words x 4 B ]
-//   [ slot arrays : SD_BLOCK x slot_words x 4 B ][ 64 counter bytes per warp ]
-// ring_words / slot_words are odd, so that the same index in consecutive threads falls into
-// consecutive banks.
+//   [ 64 counter bytes per warp ]
+// ring_words is odd, so that the same index in consecutive threads falls into consecutive banks.
+// The W slots of the perfect-interval ring live in GLOBAL memory (one 4*slot_words-byte row per
+// chunk, L2 resident): they are only touched inside low-complexity sequence, and keeping them out
+// of shared memory doubles the number of resident warps (196 B instead of 456 B per thread).
 struct SdLayout {
     int ring_words, slot_words;
     __host__ __device__ SdLayout(int W) : ring_words(((W + 3) >> 2) | 1), slot_words(W | 1) {}
-    __host__ __device__ size_t bytes() const { return (size_t)SD_BLOCK * 4 * (32 + ring_words + slot_words) + 64 * (SD_BLOCK / 32); }
+    __host__ __device__ size_t bytes() const { return (size_t)SD_BLOCK * 4 * (32 + ring_words) + 64 * (SD_BLOCK / 32); }
 };
 
-__device__ __forceinline__ sd_mem sd_mem_of(uint32_t *smem, const SdLayout &lay, int tid)
+__device__ __forceinline__ sd_mem sd_mem_of(uint32_t *smem, const SdLayout &lay, int tid, uint32_t *slots)
 {
     sd_mem m;
     m.pitch = SD_BLOCK * 4;
@@ -69,8 +72,16 @@ __device__ __forceinline__ sd_mem sd_mem_of(uint32_t *smem, const SdLayout &lay,
     m.cv = m.cw + 16 * (size_t)m.pitch;
     uint32_t *rings = smem + 32 * SD_BLOCK;
     m.ring = (uint8_t *)(rings + (size_t)tid * lay.ring_words);
-    m.slot = rings + (size_t)SD_BLOCK * lay.ring_words + (size_t)tid * lay.slot_words;
+    m.slot = slots;
     return m;
+}
+
+// a lane's slot row, broadcast from the leader of a cooperative call
+__device__ __forceinline__ uint32_t *bcast_ptr(uint32_t *p, int leader)
+{
+    const unsigned long long v = (unsigned long long)p;
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, leader), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), leader);
+    return (uint32_t *)(((unsigned long long)hi << 32) | lo);
 }
 
 // ---- warp-cooperative routines ---------------------------------------------------------------------
@@ -83,12 +94,12 @@ __device__ __forceinline__ sd_mem sd_mem_of(uint32_t *smem, const SdLayout &lay,
 
 // shrink v until the first occurrence of t has been dropped (sd_shift_window_pop)
 template <int NB>
-__device__ __forceinline__ void pop_coop(int leader, int lane, sd_state &s, int my_t, uint32_t *smem, const SdLayout &lay, int W)
+__device__ __forceinline__ void pop_coop(int leader, int lane, sd_state &s, int my_t, uint32_t *smem, const SdLayout &lay, int W)   // (does not touch the slots)
 {
     const uint32_t FULL = 0xffffffffu;
     const int wn = __shfl_sync(FULL, s.wn, leader), whead = __shfl_sync(FULL, s.whead, leader);
     const int L = __shfl_sync(FULL, s.L, leader), t = __shfl_sync(FULL, my_t, leader);
-    const sd_mem m = sd_mem_of(smem, lay, (threadIdx.x & ~31) + leader);
+    const sd_mem m = sd_mem_of(smem, lay, (threadIdx.x & ~31) + leader, NULL);
     const int v0 = wn - L;                            // first index of v
     const uint32_t le = corn_lanemask_lt() | (1u << lane);
     int x[NB];
@@ -123,7 +134,7 @@ __device__ __forceinline__ void pop_coop(int leader, int lane, sd_state &s, int 
 
 template <int NB>   // 32-position blocks covering the window: 2 for W <= 66, 4 for W <= 128
 __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int my_start, uint32_t *smem, const SdLayout &lay,
-                                        uint8_t *cnt /* 64 bytes per warp */, int T, int W)
+                                        uint32_t *my_slots, uint8_t *cnt /* 64 bytes per warp */, int T, int W)
 {
     const uint32_t FULL = 0xffffffffu;
     const int wn = __shfl_sync(FULL, s.wn, leader), whead = __shfl_sync(FULL, s.whead, leader);
@@ -132,7 +143,7 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
     int base = __shfl_sync(FULL, s.pslot, leader) + (start - __shfl_sync(FULL, s.pstart, leader));
     if (base >= W || base < 0) base = (int)((uint32_t)start % (uint32_t)W);
     const int i0 = wn - L - 1;
-    const sd_mem m = sd_mem_of(smem, lay, (threadIdx.x & ~31) + leader);
+    const sd_mem m = sd_mem_of(smem, lay, (threadIdx.x & ~31) + leader, bcast_ptr(my_slots, leader));
 
     if (lane < 16) ((uint32_t *)cnt)[lane] = 0;
     __syncwarp();
@@ -232,8 +243,9 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
 
     const int T = P.T, W = P.W;
     const SdLayout lay(W);
-    const sd_mem m = sd_mem_of(smem, lay, threadIdx.x);
-    uint8_t *cnt = (uint8_t *)(smem + (size_t)SD_BLOCK * (32 + lay.ring_words + lay.slot_words)) + 64 * (threadIdx.x >> 5);
+    uint32_t *my_slots = P.gslots + (size_t)(have ? j : 0) * lay.slot_words;
+    const sd_mem m = sd_mem_of(smem, lay, threadIdx.x, my_slots);
+    uint8_t *cnt = (uint8_t *)(smem + (size_t)SD_BLOCK * (32 + lay.ring_words)) + 64 * (threadIdx.x >> 5);
 
     uint32_t rec = 0, k = 0;
     int len = 0, c0 = 0, c1 = 0;
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
     fetch.buf = make_uint4(0, 0, 0, 0);
 
     sd_state s;
-    sd_reset(s, m, W);
+    sd_reset_counters(s, m);                          // (the slot rows were zeroed by a memset before the launch)
     int p0 = 0, n_steps = 0;
     if (have) {
         p0 = sd_warm_start(fetch, c0, W) & ~15;       // (a longer warm-up is always valid) all lanes then refill their
@@ -302,8 +314,8 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
         while (todo) {
             const int leader = __ffs(todo) - 1;
             todo &= todo - 1;
-            if (W <= 66) fp_coop<2>(leader, lane, s, start, smem, lay, cnt, T, W);
-            else         fp_coop<4>(leader, lane, s, start, smem, lay, cnt, T, W);
+            if (W <= 66) fp_coop<2>(leader, lane, s, start, smem, lay, my_slots, cnt, T, W);
+            else         fp_coop<4>(leader, lane, s, start, smem, lay, my_slots, cnt, T, W);
         }
     }
     sd_sink_close(sink);
@@ -396,7 +408,9 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
         for (uint32_t r = 0; r <= n_rec; ++r) h_first[r] = 0;
         return CORN_OK;
     }
-    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_slots, (size_t)n_chunks * cap * sizeof(uint64_t)));
+    const size_t slot_words = (size_t)(W | 1);
+    const size_t iv_bytes = ((size_t)n_chunks * cap * sizeof(uint64_t) + 255) & ~(size_t)255;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_slots, iv_bytes + (size_t)n_chunks * slot_words * sizeof(uint32_t)));
 
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     k_sdust_nchunks<<<(n_rec + 255) / 256, 256, 0, st>>>(db->d_rec_len, nch, n_rec, (uint32_t)C);
@@ -407,6 +421,8 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     sp.seq = db->d_seq; sp.rec_off = db->d_rec_off; sp.rec_len = db->d_rec_len; sp.chunk_base = chunk_base;
     sp.n_rec = n_rec; sp.n_chunks = n_chunks; sp.T = T; sp.W = W; sp.C = C; sp.cap = cap;
     sp.slots = (uint64_t *)ctx->sd_slots.p; sp.cnt = cnt; sp.err = d_err;
+    sp.gslots = (uint32_t *)((uint8_t *)ctx->sd_slots.p + iv_bytes);
+    CORN_CUDA(ctx, cudaMemsetAsync(sp.gslots, 0, (size_t)n_chunks * slot_words * sizeof(uint32_t), st));
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     k_sdust_scan<<<(n_chunks + SD_BLOCK - 1) / SD_BLOCK, SD_BLOCK, smem, st>>>(sp);
     corn_count_launch(ctx);

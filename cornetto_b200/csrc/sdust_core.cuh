@@ -127,11 +127,16 @@ struct sd_state {
     unsigned t;          // current triplet
 };
 
-SD_HD void sd_reset(sd_state &s, const sd_mem &m, int W)
+SD_HD void sd_reset_counters(sd_state &s, const sd_mem &m)
 {
     s.wn = s.whead = s.L = s.rw = s.rv = s.nslot = s.pstart = s.pslot = s.l = 0;
     s.t = 0;
     for (int i = 0; i < 64; ++i) { SD_U8(m.cw, i) = 0; SD_U8(m.cv, i) = 0; }
+}
+
+SD_HD void sd_reset(sd_state &s, const sd_mem &m, int W)
+{
+    sd_reset_counters(s, m);
     for (int i = 0; i < W; ++i) SD_SLOT(i) = 0;
 }
 

@@ -146,6 +146,7 @@ __device__ void classify_tile(const ScanParams &P, uint32_t tile, uint32_t cnt, 
     if (cnt > CORN_DENSE_TILE) {
         if (lane == 0) {
             P.tile_ncand[tile] = cnt;
+            P.tile_cnt[tile] = make_uint4(0, 0, 0, 0);             // accumulated by k_telofind_classify_dense
             P.dense_list[atomicAdd(P.dense_count, 1u)] = tile;
         }
         return;
@@ -160,26 +161,26 @@ __device__ void classify_tile(const ScanParams &P, uint32_t tile, uint32_t cnt, 
     }
 }
 
-// one block per queued tile (grid-stride over the queue), one thread per candidate chunk
+// one block per 256 candidate chunks of a queued tile (grid-stride over the queue), one thread per chunk
 __global__ void __launch_bounds__(256) k_telofind_classify_dense(const ScanParams P)
 {
     __shared__ uint32_t red[4][8];
-    const uint32_t n_dense = *P.dense_count;
+    const uint32_t n_items = *P.dense_count * (CORN_TILE_CHUNKS / 256u);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t d = blockIdx.x; d < n_dense; d += gridDim.x) {
-        const uint32_t tile = P.dense_list[d];
+    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const uint32_t tile = P.dense_list[it / (CORN_TILE_CHUNKS / 256u)];
+        const uint32_t e = (it % (CORN_TILE_CHUNKS / 256u)) * 256u + threadIdx.x;
         const uint32_t cnt = P.tile_ncand[tile];
-        const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
         uint32_t n_sf = 0, n_ef = 0, n_sr = 0, n_er = 0;
-        for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) classify_entry(P, base + e, n_sf, n_ef, n_sr, n_er);
+        if (e < cnt) classify_entry(P, (size_t)tile * CORN_TILE_CHUNKS + e, n_sf, n_ef, n_sr, n_er);
         n_sf = corn_warp_sum(n_sf); n_ef = corn_warp_sum(n_ef);
         n_sr = corn_warp_sum(n_sr); n_er = corn_warp_sum(n_er);
         if (lane == 0) { red[0][warp] = n_sf; red[1][warp] = n_ef; red[2][warp] = n_sr; red[3][warp] = n_er; }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            uint4 t = make_uint4(0, 0, 0, 0);
-            for (int w = 0; w < 8; ++w) { t.x += red[0][w]; t.y += red[1][w]; t.z += red[2][w]; t.w += red[3][w]; }
-            P.tile_cnt[tile] = t;
+        if (threadIdx.x < 4) {
+            uint32_t t = 0;
+            for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+            if (t) atomicAdd(&((uint32_t *)&P.tile_cnt[tile])[threadIdx.x], t);
         }
         __syncthreads();
     }
@@ -628,7 +629,7 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
     }
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     if (n_tiles) {
-        k_telofind_classify_dense<<<ctx->sm_count * 2, 256, 0, st>>>(sp);
+        k_telofind_classify_dense<<<ctx->sm_count * 4, 256, 0, st>>>(sp);
         corn_count_launch(ctx);
         CORN_LAUNCH_CHECK(ctx);
     }

@@ -144,14 +144,22 @@ __device__ __forceinline__ bool window_at(const uint8_t *__restrict__ bins, cons
 // few bins of a record end (partial windows, pad bins) take the exact per-window path.
 __global__ void __launch_bounds__(256) k_windows_mark(const uint8_t *__restrict__ bins, const uint32_t *__restrict__ bin_base,
                                                       const uint32_t *__restrict__ rec_len, uint32_t n_rec, uint32_t n_bins_total,
-                                                      double thr, uint32_t car_min_full, uint16_t *__restrict__ mask_out, uint32_t *__restrict__ blk_cnt)
+                                                      double thr, uint32_t car_min_full, uint16_t *__restrict__ mask_out, uint32_t *__restrict__ blk_cnt,
+                                                      uint32_t *__restrict__ hot_blocks, uint32_t *__restrict__ n_hot)
 {
     __shared__ uint32_t warp_cnt[8];
+    __shared__ uint32_t blk_rec[2];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t g0 = t * WIN_PER_THREAD;
+    // record of the block's first and last bin: almost always the same one, then no thread searches
+    if (threadIdx.x < 2) {
+        const uint32_t g = min(n_bins_total - 1, (blockIdx.x * blockDim.x + (threadIdx.x ? blockDim.x - 1 : 0)) * WIN_PER_THREAD + (threadIdx.x ? WIN_PER_THREAD - 1 : 0));
+        blk_rec[threadIdx.x] = corn_upper_bound(bin_base, n_rec, g) - 1;
+    }
+    __syncthreads();
     uint32_t mask = 0;
     if (g0 < n_bins_total) {
-        const uint32_t rec = corn_upper_bound(bin_base, n_rec, g0) - 1;
+        const uint32_t rec = blk_rec[0] == blk_rec[1] ? blk_rec[0] : corn_upper_bound(bin_base, n_rec, g0) - 1;
         const uint32_t k0 = g0 - bin_base[rec];
         const uint32_t len = rec_len[rec];
         // windows k0 .. k0+15 all full and inside this record?
@@ -183,35 +191,42 @@ __global__ void __launch_bounds__(256) k_windows_mark(const uint8_t *__restrict_
         uint32_t s = 0;
         for (int i = 0; i < 8; ++i) s += warp_cnt[i];
         blk_cnt[blockIdx.x] = s;
+        if (s) hot_blocks[atomicAdd(n_hot, 1u)] = blockIdx.x;      // order is irrelevant: offsets come from the scan
     }
 }
 
 __global__ void __launch_bounds__(256) k_windows_write(const uint8_t *__restrict__ bins, const uint32_t *__restrict__ bin_base,
                                                        const uint32_t *__restrict__ rec_len, uint32_t n_rec, uint32_t n_bins_total,
                                                        double thr, const uint16_t *__restrict__ mask_in, const uint32_t *__restrict__ blk_cnt,
-                                                       const uint32_t *__restrict__ blk_off, uint32_t capacity, corn_window_t *out)
+                                                       const uint32_t *__restrict__ blk_off, uint32_t capacity, corn_window_t *out,
+                                                       const uint32_t *__restrict__ hot_blocks, const uint32_t *__restrict__ n_hot)
 {
     __shared__ uint32_t warp_cnt[8];
-    if (blk_cnt[blockIdx.x] == 0) return;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t g0 = t * WIN_PER_THREAD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t mask = g0 < n_bins_total ? mask_in[t] : 0u;
-    const uint32_t k = __popc(mask);
-    const uint32_t incl = corn_warp_iscan(k, lane);
-    if (lane == 31) warp_cnt[warp] = incl;
-    __syncthreads();
-    if (!mask) return;
-    uint32_t off = blk_off[blockIdx.x] + incl - k;
-    for (int i = 0; i < warp; ++i) off += warp_cnt[i];
-    uint32_t m = mask;
-    while (m) {
-        const uint32_t j = __ffs(m) - 1;
-        m &= m - 1;
-        corn_window_t w;
-        window_at(bins, bin_base, rec_len, n_rec, g0 + j, thr, w);
-        if (off < capacity) out[off] = w;
-        ++off;
+    const uint32_t n = *n_hot;
+    for (uint32_t h = blockIdx.x; h < n; h += gridDim.x) {         // only the blocks of the mark pass that found something
+        const uint32_t blk = hot_blocks[h];
+        const uint32_t t = blk * blockDim.x + threadIdx.x;
+        const uint32_t g0 = t * WIN_PER_THREAD;
+        const uint32_t mask = g0 < n_bins_total ? mask_in[t] : 0u;
+        const uint32_t k = __popc(mask);
+        const uint32_t incl = corn_warp_iscan(k, lane);
+        if (lane == 31) warp_cnt[warp] = incl;
+        __syncthreads();
+        if (mask) {
+            uint32_t off = blk_off[blk] + incl - k;
+            for (int i = 0; i < warp; ++i) off += warp_cnt[i];
+            uint32_t m = mask;
+            while (m) {
+                const uint32_t j = __ffs(m) - 1;
+                m &= m - 1;
+                corn_window_t w;
+                window_at(bins, bin_base, rec_len, n_rec, g0 + j, thr, w);
+                if (off < capacity) out[off] = w;
+                ++off;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -341,9 +356,11 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     // ---- windows: mark + count, scan, write (one host sync, at the end) --------------------------
     const uint32_t n_thr = (n_bins_total + WIN_PER_THREAD - 1) / WIN_PER_THREAD;
     const uint32_t n_blk = (n_thr + 255) / 256;
-    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->tile_tab, ((size_t)n_blk + 1) * 2 * sizeof(uint32_t) + (size_t)n_thr * sizeof(uint16_t) + 256));
-    uint32_t *blk_cnt = (uint32_t *)ctx->tile_tab.p, *blk_off = blk_cnt + n_blk + 1;
-    uint16_t *wmask = (uint16_t *)(blk_off + n_blk + 1);
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->tile_tab, ((size_t)n_blk + 1) * 3 * sizeof(uint32_t) + (size_t)n_thr * sizeof(uint16_t) + 256));
+    uint32_t *blk_cnt = (uint32_t *)ctx->tile_tab.p, *blk_off = blk_cnt + n_blk + 1, *hot = blk_off + n_blk + 1;
+    uint16_t *wmask = (uint16_t *)(hot + n_blk + 1);
+    uint32_t *n_hot = d_tot + 3;
+    CORN_CUDA(ctx, cudaMemsetAsync(n_hot, 0, sizeof(uint32_t), st));
     // output capacity is speculative (grow-only, remembered across calls); the write kernel never
     // exceeds it and the total tells us afterwards whether a second write pass is needed
     size_t cap_win = ctx->events.cap / sizeof(corn_window_t);
@@ -351,12 +368,13 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     // integer form of the test for full windows, derived with the reference's own double expression
     uint32_t car_min_full = 1001;
     for (uint32_t c = 0; c <= 1000; ++c) if ((double)c / (double)1000 >= thr) { car_min_full = c; break; }
-    k_windows_mark<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, car_min_full, wmask, blk_cnt);
+    k_windows_mark<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, car_min_full, wmask, blk_cnt, hot, n_hot);
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
     CORN_TRY(corn_scan_u32(ctx, blk_cnt, blk_off, n_blk, d_tot + 2));
     corn_window_t *d_out = (corn_window_t *)ctx->events.p;
-    k_windows_write<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, wmask, blk_cnt, blk_off, (uint32_t)cap_win, d_out);
+    const unsigned g_write = (unsigned)(n_blk < (uint32_t)ctx->sm_count * 4 ? n_blk : (uint32_t)ctx->sm_count * 4);
+    k_windows_write<<<g_write, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, wmask, blk_cnt, blk_off, (uint32_t)cap_win, d_out, hot, n_hot);
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
     uint32_t n_win = 0;
@@ -364,7 +382,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     if (n_win > cap_win) {                       // first call with many windows (e.g. threshold 0): grow and rewrite
         CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, ((size_t)n_win + 1) * sizeof(corn_window_t)));
         d_out = (corn_window_t *)ctx->events.p;
-        k_windows_write<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, wmask, blk_cnt, blk_off, n_win, d_out);
+        k_windows_write<<<g_write, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, wmask, blk_cnt, blk_off, n_win, d_out, hot, n_hot);
         corn_count_launch(ctx);
         CORN_LAUNCH_CHECK(ctx);
     }
