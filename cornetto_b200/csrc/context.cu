@@ -297,22 +297,26 @@ static int dbatch_new(corn_ctx *ctx, const uint64_t *offset, const uint32_t *len
     db->total_bytes = total_bytes;
     db->h_rec_off = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n_rec + 1));
     db->h_rec_len = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n_rec + 1));
-    if (!db->h_rec_off || !db->h_rec_len) { free(db->h_rec_off); free(db->h_rec_len); free(db); return CORN_E_NOMEM; }
+    db->h_bin_base = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n_rec + 1));
+    if (!db->h_rec_off || !db->h_rec_len || !db->h_bin_base) { free(db->h_rec_off); free(db->h_rec_len); free(db->h_bin_base); free(db); return CORN_E_NOMEM; }
     uint64_t prev_end = 0;
     for (uint32_t i = 0; i < n_rec; ++i) {
         uint64_t o = offset[i], l = length[i];
         int bad = (o % CORN_ALIGN) || o < prev_end || o + l + 1 > total_bytes || l > 0x7FFFFFFFull;
         if (bad) {
-            free(db->h_rec_off); free(db->h_rec_len); free(db);
+            free(db->h_rec_off); free(db->h_rec_len); free(db->h_bin_base); free(db);
             return corn_set_err(ctx, CORN_E_LAYOUT, "record %u: offset %llu length %llu", i, (unsigned long long)o, (unsigned long long)l);
         }
         prev_end = o + l + 1;
         db->h_rec_off[i] = (uint32_t)o;
         db->h_rec_len[i] = (uint32_t)l;
+        db->h_bin_base[i] = (uint32_t)(db->n_bins_total > 0xFFFFFF00ull ? 0xFFFFFF00ull : db->n_bins_total);
+        db->n_bins_total += corn_nbins_of((uint32_t)l);
         db->n_bases += l;
     }
     db->h_rec_off[n_rec] = (uint32_t)total_bytes;
     db->h_rec_len[n_rec] = 0;
+    db->h_bin_base[n_rec] = (uint32_t)(db->n_bins_total > 0xFFFFFF00ull ? 0xFFFFFF00ull : db->n_bins_total);
 
     cudaError_t e;
     // round the data area up to whole tiles so the scan kernel never needs a bounds check
@@ -328,13 +332,15 @@ static int dbatch_new(corn_ctx *ctx, const uint64_t *offset, const uint32_t *len
     }
     if (e == cudaSuccess) e = cudaMalloc((void **)&db->d_rec_off, sizeof(uint32_t) * ((size_t)n_rec + 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&db->d_rec_len, sizeof(uint32_t) * ((size_t)n_rec + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&db->d_bin_base, sizeof(uint32_t) * ((size_t)n_rec + 1));
     if (e != cudaSuccess) {
         cudaGetLastError();
         const unsigned long long want = db->alloc_bytes;
         if (db->d_base) cudaFree(db->d_base);
         if (db->d_rec_off) cudaFree(db->d_rec_off);
         if (db->d_rec_len) cudaFree(db->d_rec_len);
-        free(db->h_rec_off); free(db->h_rec_len); free(db);
+        if (db->d_bin_base) cudaFree(db->d_bin_base);
+        free(db->h_rec_off); free(db->h_rec_len); free(db->h_bin_base); free(db);
         return corn_set_err(ctx, CORN_E_NOMEM, "cudaMalloc of %llu bytes: %s", want, cudaGetErrorString(e));
     }
     db->d_seq = db->d_base + CORN_GUARD_BYTES;
@@ -356,8 +362,8 @@ extern "C" void corn_gpu_dbatch_free(corn_ctx_t *ctx, corn_dbatch_t *db)
         }
     }
     if (db->d_base) cudaFree(db->d_base);
-    cudaFree(db->d_rec_off); cudaFree(db->d_rec_len);
-    free(db->h_rec_off); free(db->h_rec_len); free(db);
+    cudaFree(db->d_rec_off); cudaFree(db->d_rec_len); cudaFree(db->d_bin_base);
+    free(db->h_rec_off); free(db->h_rec_len); free(db->h_bin_base); free(db);
 }
 
 void corn_ctx_adopt(corn_ctx *ctx, corn_dbatch *db)
@@ -373,6 +379,7 @@ static int dbatch_tables_to_device(corn_ctx *ctx, corn_dbatch *db)
 {
     CORN_CUDA(ctx, cudaMemcpyAsync(db->d_rec_off, db->h_rec_off, sizeof(uint32_t) * ((size_t)db->n_rec + 1), cudaMemcpyHostToDevice, ctx->stream));
     CORN_CUDA(ctx, cudaMemcpyAsync(db->d_rec_len, db->h_rec_len, sizeof(uint32_t) * ((size_t)db->n_rec + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CORN_CUDA(ctx, cudaMemcpyAsync(db->d_bin_base, db->h_bin_base, sizeof(uint32_t) * ((size_t)db->n_rec + 1), cudaMemcpyHostToDevice, ctx->stream));
     return CORN_OK;
 }
 

@@ -40,7 +40,13 @@ struct corn_dbatch {
     uint32_t *h_rec_off;   // host copies
     uint32_t *h_rec_len;
     uint64_t  n_bases;     // sum of lengths
+    uint32_t *d_bin_base;  // [n_rec+1] telowin: first 200-bp bin of each record (corn_nbins_of bins per record)
+    uint32_t *h_bin_base;
+    uint64_t  n_bins_total;
 };
+
+// telowin geometry: a record owns ceil(len/200) bins plus four zero bins so that a window can always read five
+static inline __host__ __device__ uint32_t corn_nbins_of(uint32_t len) { return (len + 199u) / 200u + 4u; }
 
 struct corn_dbuf {         // grow-only device scratch
     void  *p;
@@ -86,6 +92,7 @@ struct corn_ctx {
     uint32_t  pending_ev_cap, pending_run_cap;
     const corn_dbatch *last_db;
     uint64_t  last_n_run;
+    uint32_t  last_n_win;          // windows returned by the previous telowin: sizes the speculative D2H copy
     int       last_runs_disjoint;  // runs cannot overlap (border-free motif, no fwd/rev overlap)
     int       last_motif_len;
 
@@ -144,6 +151,8 @@ int corn_read_small(corn_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
 // telofind.cu: look at the totals / flags of an un-synced telofind_dev(out == NULL); repeats the sparse
 // phase synchronously if a speculative buffer was too small.  Stream must be idle (after a sync).
 int corn_telofind_resolve(corn_ctx *ctx);
+// same, with the first 32 bytes of ctx->misc (totals, counters) already read back by the caller
+int corn_telofind_resolve_with(corn_ctx *ctx, const uint32_t tot[8]);
 
 // pinned host result blocks handed to the caller (freed by corn_gpu_*_free)
 void *corn_host_alloc(size_t bytes);

@@ -755,9 +755,15 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
 int corn_telofind_resolve(corn_ctx *ctx)
 {
     if (!ctx->pending) return CORN_OK;
-    ctx->pending = 0;
     uint32_t tot[8];
     CORN_TRY(corn_read_small(ctx, tot, ctx->misc.p, 32));
+    return corn_telofind_resolve_with(ctx, tot);
+}
+
+int corn_telofind_resolve_with(corn_ctx *ctx, const uint32_t tot[8])
+{
+    if (!ctx->pending) return CORN_OK;
+    ctx->pending = 0;
     const uint64_t n_run = (uint64_t)tot[0] + tot[2];
     if (tot[0] != tot[1] || tot[2] != tot[3])
         return corn_set_err(ctx, CORN_E_INTERNAL, "start/end counts differ: %u/%u %u/%u", tot[0], tot[1], tot[2], tot[3]);

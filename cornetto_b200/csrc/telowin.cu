@@ -26,18 +26,11 @@ struct WinTables {
     uint32_t        n_rec;
 };
 
-__host__ __device__ inline uint32_t nbins_of(uint32_t len) { return (len + 199u) / 200u + 4u; }
 __host__ __device__ inline uint32_t nwin_of(uint32_t len)
 {
     if (len == 0) return 0;                       // den == 0 -> NaN compare, never printed
     if (len <= 1000) return 1;
     return (len - 1000u + 199u) / 200u + 1u;      // last i is the first multiple of 200 with i+1000 >= len
-}
-
-__global__ void k_bin_counts(const uint32_t *__restrict__ rec_len, uint32_t *__restrict__ nb, uint32_t n_rec)
-{
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n_rec) nb[r] = nbins_of(rec_len[r]);
 }
 
 __device__ __forceinline__ void bin_add(uint8_t *bins, uint32_t bin, uint32_t amount)
@@ -299,24 +292,33 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     if (n_rec == 0) { CORN_CUDA(ctx, cudaStreamSynchronize(st)); return CORN_OK; }
 
     // ---- tables ---------------------------------------------------------------------------------
-    // misc: [0..16) totals ; tile_tab is free after telofind's scatter: reuse for per-record tables
+    // misc: [0,32) telofind totals/counters | [32,48) telowin counters (one readback fetches both)
     CORN_TRY(corn_dbuf_reserve(ctx, &ctx->misc, 4096));
-    uint32_t *d_tot = (uint32_t *)((uint8_t *)ctx->misc.p + 1024);
+    uint32_t *d_tot = (uint32_t *)((uint8_t *)ctx->misc.p + 32);
+    CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 16, st));
     const size_t tab_bytes = ((size_t)n_rec + 2) * (2 * sizeof(uint32_t) + sizeof(uint64_t) + sizeof(uint32_t)) + 256;
-    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->wins, tab_bytes));   // head of `wins` holds the tables until the output is sized
-    // (the output itself is written into ctx->bitmap's sibling buffer below)
-    uint32_t *nb = (uint32_t *)ctx->wins.p;              // [n_rec]   bins per record
-    uint32_t *bin_base = nb + (n_rec + 1);               // [n_rec+1]
-    const unsigned gr = (n_rec + 255) / 256;
-    k_bin_counts<<<gr, 256, 0, st>>>(d_len, nb, n_rec);
-    corn_count_launch(ctx);
-    CORN_TRY(corn_scan_u32(ctx, nb, bin_base, n_rec, d_tot));
-    // the totals are known on the host (lengths are host data): no readback, no sync
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->wins, tab_bytes));
+    // first bin of every record: host arithmetic on the (host-known) lengths, cached with a resident batch
+    uint32_t *bin_base_buf = (uint32_t *)ctx->wins.p;    // [n_rec+1] (text-driven path)
+    const uint32_t *bin_base = NULL;
     uint64_t bins64 = 0, words64 = 0;
-    for (uint32_t r = 0; r < n_rec; ++r) { bins64 += nbins_of(h_len[r]); words64 += (h_len[r] + 31u) / 32u + 1u; }
+    for (uint32_t r = 0; r < n_rec; ++r) words64 += (h_len[r] + 31u) / 32u + 1u;
+    if (!hits) {
+        bin_base = ctx->last_db->d_bin_base;
+        bins64 = ctx->last_db->n_bins_total;
+    } else {
+        uint32_t *hb = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n_rec + 1));
+        if (!hb) return corn_set_err(ctx, CORN_E_NOMEM, "bin table");
+        for (uint32_t r = 0; r < n_rec; ++r) { hb[r] = (uint32_t)(bins64 > 0xFFFFFF00ull ? 0xFFFFFF00ull : bins64); bins64 += corn_nbins_of(h_len[r]); }
+        hb[n_rec] = (uint32_t)(bins64 > 0xFFFFFF00ull ? 0xFFFFFF00ull : bins64);
+        cudaError_t ce = cudaMemcpyAsync(bin_base_buf, hb, sizeof(uint32_t) * ((size_t)n_rec + 1), cudaMemcpyHostToDevice, st);   // pageable: staged before return
+        free(hb);
+        if (ce != cudaSuccess) return corn_set_err(ctx, CORN_E_CUDA, "bin table upload: %s", cudaGetErrorString(ce));
+        bin_base = bin_base_buf;
+    }
     if (bins64 > 0xFFFFFF00ull || words64 > 0xFFFFFF00ull) return corn_set_err(ctx, CORN_E_TOOBIG, "too many bins");
     const uint32_t n_bins_total = (uint32_t)bins64;
-    // bin_base[n_rec] = total, so upper_bound over n_rec entries is enough; keep the total on the host
+    const unsigned gr = (n_rec + 255) / 256;
     CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (size_t)n_bins_total + 128));
     uint8_t *bins = (uint8_t *)ctx->bins.p;
 
@@ -331,7 +333,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         }
     } else {
         // 1 bit per base, records word aligned
-        uint32_t *words = bin_base + (n_rec + 1);                         // [n_rec] then scanned in place
+        uint32_t *words = bin_base_buf + (n_rec + 1);                     // [n_rec] then scanned in place
         uint64_t *bit_base = (uint64_t *)(((uintptr_t)(words + n_rec + 1) + 7) & ~(uintptr_t)7);
         k_bit_bases<<<gr, 256, 0, st>>>(d_len, words, n_rec);
         corn_count_launch(ctx);
@@ -377,8 +379,20 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     k_windows_write<<<g_write, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, wmask, blk_cnt, blk_off, (uint32_t)cap_win, d_out, hot, n_hot);
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
-    uint32_t n_win = 0;
-    CORN_TRY(corn_read_small(ctx, &n_win, d_tot + 2, 4));
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[10], st));
+    // ONE host sync for the whole call: the counters (and, for a fused call, the telofind totals that
+    // were left unchecked) come back together with a speculative copy of the first windows
+    size_t spec = (size_t)ctx->last_n_win + ctx->last_n_win / 4 + 4096;
+    if (spec > cap_win) spec = cap_win;
+    corn_window_t *h_win = (corn_window_t *)corn_host_alloc(spec * sizeof(corn_window_t));
+    if (!h_win) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc of %zu windows", spec);
+    CORN_CUDA(ctx, cudaMemcpyAsync(h_win, d_out, spec * sizeof(corn_window_t), cudaMemcpyDeviceToHost, st));
+    CORN_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned_small, ctx->misc.p, 64, cudaMemcpyDeviceToHost, st));
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[11], st));
+    CORN_CUDA(ctx, cudaStreamSynchronize(st));
+    uint32_t hv[16];
+    memcpy(hv, ctx->h_pinned_small, 64);
+    const uint32_t n_win = hv[8 + 2];
     if (n_win > cap_win) {                       // first call with many windows (e.g. threshold 0): grow and rewrite
         CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, ((size_t)n_win + 1) * sizeof(corn_window_t)));
         d_out = (corn_window_t *)ctx->events.p;
@@ -386,16 +400,16 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         corn_count_launch(ctx);
         CORN_LAUNCH_CHECK(ctx);
     }
-    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[10], st));
-    out->n_win = n_win;
-    if (n_win) {
-        out->win = (corn_window_t *)corn_host_alloc((size_t)n_win * sizeof(corn_window_t));
-        if (!out->win) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc of %u windows", n_win);
-        out->_owner = out->win;
-        CORN_CUDA(ctx, cudaMemcpyAsync(out->win, d_out, (size_t)n_win * sizeof(corn_window_t), cudaMemcpyDeviceToHost, st));
+    if (n_win > spec) {                          // more windows than the speculative copy covered
+        corn_host_free(h_win);
+        h_win = (corn_window_t *)corn_host_alloc((size_t)n_win * sizeof(corn_window_t));
+        if (!h_win) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc of %u windows", n_win);
+        CORN_CUDA(ctx, cudaMemcpyAsync(h_win, d_out, (size_t)n_win * sizeof(corn_window_t), cudaMemcpyDeviceToHost, st));
+        CORN_CUDA(ctx, cudaStreamSynchronize(st));
     }
-    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[11], st));
-    CORN_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->last_n_win = n_win;
+    out->n_win = n_win;
+    out->win = h_win; out->_owner = h_win;
     cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[8], ctx->ev[9]);
     cudaEventElapsedTime(&ctx->timing.post_ms, ctx->ev[9], ctx->ev[10]);
     cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[10], ctx->ev[11]);
@@ -405,7 +419,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         const corn_timing_t t_win = ctx->timing;
         ctx->timing = t_find;
         const uint64_t before = ctx->total_launches;
-        int r = corn_telofind_resolve(ctx);
+        int r = corn_telofind_resolve_with(ctx, hv);
         if (r != CORN_OK) { corn_gpu_windows_free(out); return r; }
         if (ctx->total_launches != before) {       // a buffer had been too small and the runs were rebuilt: redo the windows
             corn_gpu_windows_free(out);
