@@ -333,13 +333,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    import ctypes as C
+    Lc = ctx.L
+    wins_s, tim_s = capi.Windows(), capi.Timing()
+    p_wins, p_tim = C.byref(wins_s), C.byref(tim_s)
+
     def step():
         # resident batch, results stay on the device: telofind_dev(out=NULL) returns without a host sync
-        # and the fused telowin(hits=NULL) call is the step's single synchronisation point; timing()
-        # then covers both calls (scan_ms = k_telofind_scan, post_ms = every other kernel of the step)
-        ctx.telofind_dev(db, "TTAGGG", fetch=False)
-        w = ctx.telowin(THR)
-        return ctx.timing(), w
+        # and the fused telowin(hits=NULL) call is the step's single synchronisation point (it brings
+        # the passing windows back to pinned host memory); last_timing then covers both calls
+        # (scan_ms = k_telofind_scan, post_ms = every other kernel of the step).  Plain ctypes calls
+        # on preallocated structs keep the harness's own per-step overhead to a few microseconds.
+        rc = Lc.corn_gpu_telofind_dev(ctx.ctx, db, b"TTAGGG", None)
+        if rc == 0:
+            rc = Lc.corn_gpu_telowin(ctx.ctx, None, None, THR, p_wins)
+        if rc != 0:
+            capi._check(ctx.ctx, rc, "fused step")
+        n = wins_s.n_win
+        Lc.corn_gpu_windows_free(p_wins)
+        Lc.corn_gpu_last_timing(ctx.ctx, p_tim)
+        return tim_s, n
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -352,11 +365,10 @@ def main():
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
-        tm, w = step()
-        scan_ms.append(tm["scan_ms"])
-        post_ms.append(tm["post_ms"])
-        out_bytes = tm["out_bytes"]
-        n_win = len(w)
+        tm, n_win = step()
+        scan_ms.append(tm.scan_ms)
+        post_ms.append(tm.post_ms)
+        out_bytes = tm.out_bytes
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
@@ -410,7 +422,6 @@ def main():
 
     # ---- e2e: host buffers through the public C ABI (H2D + kernels + D2H inside the timed region) ----
     L = ctx.L
-    import ctypes as C
     hb = C.c_void_p()
     capi._check(None, L.corn_hbatch_create(total_bytes + 64, len(lengths), C.byref(hb)), "corn_hbatch_create")
     capi._check(None, L.corn_hbatch_pin(hb), "corn_hbatch_pin")
