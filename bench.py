@@ -119,12 +119,19 @@ class Clocks:
 
     def __init__(self, device):
         self.device = device
-        self.rows = []
+        self.rows = []          # (arrival time, fields)
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -135,7 +142,7 @@ class Clocks:
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
             if len(f) >= 9:
-                self.rows.append(f)
+                self.rows.append((time.time(), f))
 
     def stop(self):
         if not self.proc:
@@ -146,10 +153,14 @@ class Clocks:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        # samples that arrived inside the timed region (the sampler itself is started before the warm-up)
+        inside = [f for (t, f) in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.02)]
+        if not inside:
+            inside = [f for (_, f) in self.rows[-3:]]
+        sm = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in inside if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in inside:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -286,7 +297,7 @@ def load_traffic():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CORN_BENCH_WORKLOAD", "c2"))
@@ -354,15 +365,16 @@ def main():
         Lc.corn_gpu_last_timing(ctx.ctx, p_tim)
         return tim_s, n
 
+    clocks = Clocks(local)
+    clocks.start()
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    clocks = Clocks(local)
-    clocks.start()
     launches0 = ctx.total_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, post_ms, out_bytes, n_win = [], [], 0, 0
     barrier()
+    clocks.mark_begin()
     ev0.record(stream)
     for _ in range(args.steps):
         tm, n_win = step()
@@ -371,6 +383,7 @@ def main():
         out_bytes = tm.out_bytes
     ev1.record(stream)
     barrier()
+    clocks.mark_end()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.total_launches() - launches0
     clk = clocks.stop()
