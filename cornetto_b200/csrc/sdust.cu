@@ -121,8 +121,9 @@ __device__ __forceinline__ void pop_coop(int leader, int lane, sd_state &s, int 
         const bool popped = inv[b] && i <= p;
         const int key = popped ? x[b] : 64 + lane;
         const uint32_t mm = __match_any_sync(FULL, key);
+        const int cvx = popped ? (int)SD_U8(m.cv, x[b]) : 0;          // count before this block's pops
+        __syncwarp();                                 // every lane of a group has read cv[x] before its leader updates it
         if (popped) {
-            const int cvx = SD_U8(m.cv, x[b]);        // count before this block's pops
             sub += cvx - __popc(mm & le);             // "rv -= --cv[x]" for the rank-th equal element
             if (lane == __ffs(mm) - 1) SD_U8(m.cv, x[b]) = (uint8_t)(cvx - __popc(mm));
         }
@@ -160,6 +161,7 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
         const int before = valid[b] ? (int)cnt[t] : 0;
         const uint32_t mm = __match_any_sync(FULL, t);
         const int rank = before + __popc(mm & le);
+        __syncwarp();                                 // every lane of a group has read cnt[t] before its leader updates it
         if (valid[b] && lane == __ffs(mm) - 1) cnt[t] = (uint8_t)(before + __popc(mm));
         __syncwarp();
         c[b] = (valid[b] && i <= i0) ? (int)SD_U8(m.cw, t) - rank : 0;
