@@ -49,6 +49,7 @@ struct SdParams {
     uint32_t *gslots;               // n_chunks * (W | 1) words, zeroed: the perfect-interval rings
     uint32_t *cnt;                  // [n_chunks]
     uint32_t *err;
+    uint32_t *task_counter;
 };
 
 // ---- shared-memory layout of a block -------------------------------------------------------------
@@ -229,25 +230,20 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
+// one warp-task: 32 chunks (one per lane) stepped in lockstep
+__device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp_id, uint32_t n_warps, uint32_t *smem, const SdLayout &lay,
+                                                uint8_t *cnt, int lane)
 {
-    extern __shared__ uint32_t smem[];
     const uint32_t FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    // chunk of this lane: consecutive chunks go to DIFFERENT warps (lane l of warp w takes chunk
+    // chunk of this lane: consecutive chunks go to DIFFERENT warp-tasks (lane l of task w takes chunk
     // l * n_warps + w).  Low-complexity stretches (satellites, telomeres) make their chunks many times
-    // more expensive; spread over the warps they cost each warp one slow lane instead of leaving one
+    // more expensive; spread over the tasks they cost each one slow lane instead of leaving one
     // warp with 32 of them as the kernel's tail.
-    const uint32_t n_warps = (P.n_chunks + 31u) / 32u;
-    const uint32_t warp_id = (blockIdx.x * SD_BLOCK + threadIdx.x) >> 5;
     const uint32_t j = (uint32_t)lane * n_warps + warp_id;
-    const bool have = warp_id < n_warps && j < P.n_chunks;   // lanes without a chunk still serve the warp's cooperative calls
-
+    const bool have = j < P.n_chunks;                 // lanes without a chunk still serve the warp's cooperative calls
     const int T = P.T, W = P.W;
-    const SdLayout lay(W);
     uint32_t *my_slots = P.gslots + (size_t)(have ? j : 0) * lay.slot_words;
     const sd_mem m = sd_mem_of(smem, lay, threadIdx.x, my_slots);
-    uint8_t *cnt = (uint8_t *)(smem + (size_t)SD_BLOCK * (32 + lay.ring_words)) + 64 * (threadIdx.x >> 5);
 
     uint32_t rec = 0, k = 0;
     int len = 0, c0 = 0, c1 = 0;
@@ -327,6 +323,25 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
     }
 }
 
+// Persistent grid: warps claim warp-tasks from a counter, so the kernel ends one task -- not one wave
+// of blocks -- after the last claim.
+__global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
+{
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const SdLayout lay(P.W);
+    uint8_t *cnt = (uint8_t *)(smem + (size_t)SD_BLOCK * (32 + lay.ring_words)) + 64 * (threadIdx.x >> 5);
+    const uint32_t n_warps = (P.n_chunks + 31u) / 32u;
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(P.task_counter, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_warps) break;
+        sdust_warp_task(P, w, n_warps, smem, lay, cnt, lane);
+        __syncwarp();
+    }
+}
+
 struct GatherParams {
     const uint64_t *slots;
     const uint32_t *cnt;
@@ -392,7 +407,7 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     CORN_TRY(corn_dbuf_reserve(ctx, &ctx->misc, 4096));
     uint32_t *d_tot = (uint32_t *)((uint8_t *)ctx->misc.p + 2048);
     uint32_t *d_err = d_tot + 4;
-    CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 32, st));
+    CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 64, st));
     // host-side chunk count (lengths are known on the host): sizes the tables without a readback
     uint64_t n_chunks64 = 0;
     for (uint32_t r = 0; r < n_rec; ++r) n_chunks64 += ((uint64_t)db->h_rec_len[r] + C - 1) / C;
@@ -422,11 +437,14 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     SdParams sp;
     sp.seq = db->d_seq; sp.rec_off = db->d_rec_off; sp.rec_len = db->d_rec_len; sp.chunk_base = chunk_base;
     sp.n_rec = n_rec; sp.n_chunks = n_chunks; sp.T = T; sp.W = W; sp.C = C; sp.cap = cap;
-    sp.slots = (uint64_t *)ctx->sd_slots.p; sp.cnt = cnt; sp.err = d_err;
+    sp.slots = (uint64_t *)ctx->sd_slots.p; sp.cnt = cnt; sp.err = d_err; sp.task_counter = d_tot + 8;
     sp.gslots = (uint32_t *)((uint8_t *)ctx->sd_slots.p + iv_bytes);
     CORN_CUDA(ctx, cudaMemsetAsync(sp.gslots, 0, (size_t)n_chunks * slot_words * sizeof(uint32_t), st));
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    k_sdust_scan<<<(n_chunks + SD_BLOCK - 1) / SD_BLOCK, SD_BLOCK, smem, st>>>(sp);
+    {
+        const unsigned want = (n_chunks + SD_BLOCK - 1) / SD_BLOCK, resident = (unsigned)(ctx->sm_count * blocks_per_sm);
+        k_sdust_scan<<<want < resident ? want : resident, SD_BLOCK, smem, st>>>(sp);
+    }
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
