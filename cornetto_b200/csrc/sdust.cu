@@ -50,6 +50,7 @@ struct SdParams {
     uint32_t *cnt;                  // [n_chunks]
     uint32_t *err;
     uint32_t *task_counter;
+    const uint32_t *task_list;      // ticket -> warp-task, expensive tasks first
 };
 
 // ---- shared-memory layout of a block -------------------------------------------------------------
@@ -323,6 +324,53 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
     }
 }
 
+// ---- cost-aware task order -----------------------------------------------------------------------
+// A chunk inside a tandem repeat (telomere, satellite) needs both cooperative routines at every
+// step, which makes its whole warp-task 3-4x as long as an ordinary one.  If such a task is claimed
+// late, it is the tail of the kernel.  A probe looks at 64 bases in the middle of every chunk: few
+// distinct triplets => expensive.  Tasks with an expensive lane are put at the front of the ticket
+// order.  (Purely a scheduling hint: results do not depend on it.)
+__global__ void __launch_bounds__(256) k_sdust_probe(const SdParams P, uint8_t *flag)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n_chunks) return;
+    const uint32_t rec = corn_upper_bound(P.chunk_base, P.n_rec, j) - 1;
+    const uint32_t k = j - P.chunk_base[rec];
+    const uint32_t len = P.rec_len[rec];
+    const uint32_t c0 = k * (uint32_t)P.C, c1 = min(len, c0 + (uint32_t)P.C);
+    uint32_t a = (c0 + (c1 - c0) / 2) & ~15u;                       // 64 bytes around the middle, 16-byte aligned
+    if (a + 64 > c1) a = c1 >= 64 ? (c1 - 64) & ~15u : 0;
+    const uint4 *p = (const uint4 *)(P.seq + P.rec_off[rec] + a);
+    uint64_t seen = 0;
+    uint32_t t = 0, run = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 v = __ldg(p + q);
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int b = sd_nt4((uint8_t)(w[i >> 2] >> (8 * (i & 3))));
+            if (b < 4) { t = (t << 2 | (uint32_t)b) & 63u; if (++run >= 3) seen |= 1ull << t; }
+            else run = 0;
+        }
+    }
+    flag[j] = (uint8_t)(__popcll(seen) <= 24);                       // random DNA shows ~40 distinct triplets in 62
+}
+
+__global__ void __launch_bounds__(256) k_sdust_order(const uint8_t *__restrict__ flag, uint32_t n_chunks, uint32_t n_warps,
+                                                     uint32_t *task_list, uint32_t *counters /* [0] front, [1] back */)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_warps) return;
+    bool heavy = false;
+    for (uint32_t l = 0; l < 32; ++l) {
+        const uint32_t j = l * n_warps + w;
+        if (j < n_chunks && flag[j]) { heavy = true; break; }
+    }
+    if (heavy) task_list[atomicAdd(&counters[0], 1u)] = w;
+    else       task_list[n_warps - 1u - atomicAdd(&counters[1], 1u)] = w;
+}
+
 // Persistent grid: warps claim warp-tasks from a counter, so the kernel ends one task -- not one wave
 // of blocks -- after the last claim.
 __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
@@ -337,7 +385,7 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
         if (lane == 0) w = atomicAdd(P.task_counter, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= n_warps) break;
-        sdust_warp_task(P, w, n_warps, smem, lay, cnt, lane);
+        sdust_warp_task(P, P.task_list[w], n_warps, smem, lay, cnt, lane);
         __syncwarp();
     }
 }
@@ -387,17 +435,18 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     ctx->timing.h2d_ms = keep_h2d;
     out->iv = NULL; out->rec_first = NULL; out->n_iv = 0; out->n_rec = db->n_rec; out->_owner = NULL;
 
-    // chunk length: 4096 bases for large batches (5 % warm-up overhead); smaller when that would leave
-    // the GPU with fewer than ~3 waves of threads.  Results do not depend on it.
+    // chunk length: 4096 bases for large batches (5 % warm-up overhead).  A chunk is a serial chain, and
+    // the chain of a chunk inside a tandem repeat is ~4x slower than the rest, so on a small batch the
+    // kernel lasts as long as that one chain: balance "all work / machine rate" against "C x slow-step
+    // time", which on a B200 puts C near n_bases / 270 000.  Results do not depend on it.
     const size_t smem = SdLayout(W).bytes();
     CORN_CUDA(ctx, cudaFuncSetAttribute(k_sdust_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sdust_scan, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
     int C = 4096;
     {
-        const uint64_t slots = (uint64_t)ctx->sm_count * blocks_per_sm * SD_BLOCK;
-        const uint64_t want = db->n_bases / (slots * 3 + 1);
-        if (want < 4096) C = (int)(want < 1024 ? 1024 : want / 64 * 64);
+        const uint64_t want = db->n_bases / ((uint64_t)ctx->sm_count * 1824u + 1);
+        if (want < 4096) C = (int)(want < 512 ? 512 : want / 64 * 64);
     }
     if (const char *e = getenv("CORNETTO_SDUST_CHUNK")) { int v = atoi(e); if (v >= 16 && v <= (1 << 20)) C = v; }
     const uint32_t n_rec = db->n_rec;
@@ -413,10 +462,13 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     for (uint32_t r = 0; r < n_rec; ++r) n_chunks64 += ((uint64_t)db->h_rec_len[r] + C - 1) / C;
     if (n_chunks64 > 0xFFFFFFF0ull) return corn_set_err(ctx, CORN_E_TOOBIG, "too many sdust chunks");
     const uint32_t n_chunks = (uint32_t)n_chunks64;
-    const size_t tab_words = 2 * ((size_t)n_rec + 1) + 3 * ((size_t)n_chunks + 1) + 16;
+    const uint32_t n_tasks = (n_chunks + 31u) / 32u;
+    const size_t tab_words = 2 * ((size_t)n_rec + 1) + 3 * ((size_t)n_chunks + 1) + (size_t)n_tasks + ((size_t)n_chunks + 3) / 4 + 32;
     CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_tab, tab_words * sizeof(uint32_t)));
     uint32_t *nch = (uint32_t *)ctx->sd_tab.p, *chunk_base = nch + n_rec + 1;
     uint32_t *cnt = chunk_base + n_rec + 1, *out_cnt = cnt + n_chunks + 1, *out_off = out_cnt + n_chunks + 1;
+    uint32_t *task_list = out_off + n_chunks + 1;
+    uint8_t *heavy_flag = (uint8_t *)(task_list + n_tasks + 1);
 
     uint64_t *h_first = (uint64_t *)corn_host_alloc(sizeof(uint64_t) * ((size_t)n_rec + 1));
     if (!h_first) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc");
@@ -440,6 +492,11 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     sp.slots = (uint64_t *)ctx->sd_slots.p; sp.cnt = cnt; sp.err = d_err; sp.task_counter = d_tot + 8;
     sp.gslots = (uint32_t *)((uint8_t *)ctx->sd_slots.p + iv_bytes);
     CORN_CUDA(ctx, cudaMemsetAsync(sp.gslots, 0, (size_t)n_chunks * slot_words * sizeof(uint32_t), st));
+    sp.task_list = task_list;
+    k_sdust_probe<<<(n_chunks + 255) / 256, 256, 0, st>>>(sp, heavy_flag);
+    k_sdust_order<<<(n_tasks + 255) / 256, 256, 0, st>>>(heavy_flag, n_chunks, n_tasks, task_list, d_tot + 9);
+    corn_count_launch(ctx, 2);
+    CORN_LAUNCH_CHECK(ctx);
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     {
         const unsigned want = (n_chunks + SD_BLOCK - 1) / SD_BLOCK, resident = (unsigned)(ctx->sm_count * blocks_per_sm);

@@ -16,9 +16,13 @@ lengths = [mb * 1_000_000 // 4] * 4
 ctx = capi.Context(0)
 db = ctx.alloc(lengths)
 ctx.fill_random(db, 42)
-tand, lower = bench.make_features(capi, lengths, 7)
-ctx.apply_features(db, tand)
-ctx.apply_features(db, lower)
+mode = sys.argv[3] if len(sys.argv) > 3 else "full"     # full | plain (random only) | notelo (no telomeric ends)
+if mode != "plain":
+    tand, lower = bench.make_features(capi, lengths, 7)
+    if mode == "notelo":
+        tand = tand[tand["len"] < 3000]
+    ctx.apply_features(db, tand)
+    ctx.apply_features(db, lower)
 for _ in range(reps):
     iv, first = ctx.sdust_dev(db)
     t = ctx.timing()

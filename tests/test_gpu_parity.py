@@ -210,12 +210,15 @@ def as_rows(runs):
     return np.stack([runs["rec"], runs["strand"], runs["start"], runs["end"]], axis=1).astype(np.uint64).reshape(-1, 4)
 
 
-@pytest.mark.parametrize("motif", ["TTAGGG", "TTTAGGG", "AAAAAA", "TATATA", "TTNGGG", "ACGTACGTACGTACGTACGTACGTACGTACGTACGT"])
+@pytest.mark.parametrize("motif", ["TTAGGG", "TTTAGGG", "AAAAAA", "TATATA", "TTNGGG", "ACGTACGTACGTACGTACGTACGTACGTACGTACGT",
+                                   "A", "GT", "CCCTAA", "GATTACAGATTACAGATTACAGATTACAGATT", "GATTACAGATTACAGATTACAGATTACAGATTA", "ttaggg", "TTAGGg"])
 def test_abi_telofind(ctx, capi, motif):
     rng = np.random.default_rng(21)
     recs = [synth.make_contig(rng, int(L), n_gaps=2, iupac_per_mb=300.0, telo=(30, 300)) for L in (70_000, 33, 0, 5, 6, 120_001, 1024, 31, 32, 64)]
     recs.append(np.frombuffer(b"TTAGGG" * 2000, dtype=np.uint8))           # one run across many tiles' worth of chunks
     recs.append(np.frombuffer((b"TTAGGGA" * 3000), dtype=np.uint8))        # dense start/end events
+    recs.append(np.frombuffer(b"GATTACAGATTACAGATTACAGATTACAGATTA" * 40 + b"gattacagattacagattacagattacagatt" * 3, dtype=np.uint8))
+    recs.append(np.frombuffer(b"GT" * 500 + b"AAAAAAAAAAAAA" + b"TG" * 77, dtype=np.uint8))
     hb = capi.HostBatch(recs)
     got = as_rows(ctx.telofind(hb, motif))
     want = oracle_telofind(recs, motif)
