@@ -18,13 +18,15 @@ import bench  # noqa: E402
 from util import retab_telomere, lens_from_fa2bed  # noqa: E402
 
 div = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+diploid = len(sys.argv) > 2 and sys.argv[2] == "diploid"      # BASELINE.json configs[2]: 48 contigs, 6.2 Gb
 ours = os.path.join(ROOT, "cornetto_b200", "bin", "cornetto")
 ref, kind = bench.ref_binary()
 work = "/tmp/corn_full"
 os.makedirs(work, exist_ok=True)
 fa = os.path.join(work, "asm.fa")
 rng = np.random.default_rng(11)
-lengths = [L // div for L in bench.CHM13]
+lengths = [L // div for L in bench.CHM13] * (2 if diploid else 1)
+names = [f"chr{i % 24 + 1}" + (("_MATERNAL" if i < 24 else "_PATERNAL") if diploid else "") for i in range(len(lengths))]
 t0 = time.perf_counter()
 with open(fa, "wb") as f:
     pass
@@ -40,7 +42,7 @@ for i, L in enumerate(lengths):                       # contig by contig: bounde
         s[q:q + 2000] |= 0x20
     with open(fa, "ab") as f:
         tmp = os.path.join(work, "one.fa")
-        bench.write_fasta(tmp, [(f"chr{i + 1}", s)])
+        bench.write_fasta(tmp, [(names[i], s)])
         f.write(open(tmp, "rb").read())
 gen_s = time.perf_counter() - t0
 subprocess.run(["cat", fa], stdout=subprocess.DEVNULL)
@@ -53,7 +55,7 @@ def run(binary, args, out):
     return time.perf_counter() - t
 
 
-res = {"bases": int(sum(lengths)), "fasta_bytes": os.path.getsize(fa), "generate_s": round(gen_s, 1), "reference_kind": kind, "steps": {}}
+res = {"gpus": os.environ.get("CORNETTO_GPUS", "1"), "contigs": len(lengths), "bases": int(sum(lengths)), "fasta_bytes": os.path.getsize(fa), "generate_s": round(gen_s, 1), "reference_kind": kind, "steps": {}}
 ok = True
 for tag, binary in (("ref", ref), ("ours", ours)):
     d = os.path.join(work, tag)
