@@ -259,7 +259,9 @@ __global__ void __launch_bounds__(256, 5) k_telofind_scan(const ScanParams P)
         {                                                                                                       \
             uint32_t c1, c2;                                                                                    \
             corn_planes32(buf, c1, c2);                                                                         \
-            if ((r) + 3 <= CORN_TILE_ROWS) ld256(lane_ptr + (size_t)((r) + 3) * CORN_ROW_BYTES, buf);           \
+            /* row CORN_TILE_ROWS belongs to the next tile: only its first chunk is needed (lane 0) */        \
+            if ((r) + 3 < CORN_TILE_ROWS || ((r) + 3 == CORN_TILE_ROWS && lane == 0))                           \
+                ld256(lane_ptr + (size_t)((r) + 3) * CORN_ROW_BYTES, buf);                                      \
             if ((r) > 0) {                                                                                      \
                 /* lane i needs the planes of the 32 bytes after its chunk of row r-1: lane i+1's previous  */ \
                 /* planes, or (lane 31) lane 0's current planes                                              */ \

@@ -13,12 +13,15 @@
  *     the input (-2, :214-223).
  */
 #include <ctype.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "cornetto.h"
 
 struct fastx {
-    gzFile   fp;
+    gzFile   fp;          /* gzip input (or stdin of unknown kind) */
+    int      fd;          /* plain file: read(2) straight into buf, no zlib copy */
     uint8_t *buf;
     size_t   cap, beg, end;
     int      eof;
@@ -32,12 +35,22 @@ struct fastx {
 
 fastx_t *fastx_open(const char *path)
 {
-    gzFile fp = strcmp(path, "-") ? gzopen(path, "r") : gzdopen(fileno(stdin), "r");
-    if (!fp) return NULL;
-    gzbuffer(fp, 1 << 20);
+    gzFile fp = NULL;
+    int fd = -1;
+    if (strcmp(path, "-") == 0) fp = gzdopen(fileno(stdin), "r");
+    else {
+        fd = open(path, O_RDONLY);
+        if (fd < 0) return NULL;
+        unsigned char magic[2] = { 0, 0 };
+        const ssize_t k = pread(fd, magic, 2, 0);
+        if (k == 2 && magic[0] == 0x1f && magic[1] == 0x8b) { fp = gzdopen(fd, "r"); fd = -1; }   /* gzip: through zlib */
+    }
+    if (!fp && fd < 0) return NULL;
+    if (fp) gzbuffer(fp, 1 << 20);
     fastx_t *fx = (fastx_t *)calloc(1, sizeof *fx);
     CORN_MALLOC_CHK(fx);
     fx->fp = fp;
+    fx->fd = fd;
     fx->cap = 4u << 20;
     fx->buf = (uint8_t *)malloc(fx->cap);
     fx->name_cap = 256;
@@ -51,7 +64,8 @@ fastx_t *fastx_open(const char *path)
 void fastx_close(fastx_t *fx)
 {
     if (!fx) return;
-    gzclose(fx->fp);
+    if (fx->fp) gzclose(fx->fp);
+    if (fx->fd >= 0) close(fx->fd);
     free(fx->buf); free(fx->name); free(fx);
 }
 
@@ -59,7 +73,9 @@ static int fill(fastx_t *fx)
 {
     if (fx->beg < fx->end) return 1;
     if (fx->eof) return 0;
-    int n = gzread(fx->fp, fx->buf, (unsigned)fx->cap);
+    long n;
+    if (fx->fp) n = gzread(fx->fp, fx->buf, (unsigned)fx->cap);
+    else do { n = (long)read(fx->fd, fx->buf, fx->cap); } while (n < 0 && errno == EINTR);
     fx->beg = 0;
     fx->end = n > 0 ? (size_t)n : 0;
     if (n <= 0) { fx->eof = 1; return 0; }
@@ -129,6 +145,19 @@ size_t fastx_seq(fastx_t *fx, uint8_t *dst, size_t cap, int *done)
         const size_t avail = fx->end - fx->beg;
         const uint8_t *q = (const uint8_t *)memchr(p, '\n', avail);
         const size_t seg = q ? (size_t)(q - p) : avail;
+        if (q && !fx->pending_cr) {
+            /* common case: the rest of the line, newline included, is in the buffer -- one step.
+             * A trailing '\r' goes unless it would be the only byte of the sequence so far (:138). */
+            size_t take = seg;
+            if (take && p[take - 1] == '\r' && fx->seq_len + seg > 1) --take;
+            if (take <= cap - w) {
+                memcpy(dst + w, p, take);
+                w += take; fx->seq_len += take;
+                fx->beg += seg + 1;
+                fx->at_line_start = 1;
+                continue;
+            }
+        }
         if (seg == 0) {                              /* the line ends here */
             if (fx->pending_cr) {
                 if (fx->seq_len >= 1) fx->pending_cr = 0;            /* stripped */
