@@ -88,6 +88,7 @@ struct corn_ctx {
     // (telofind_dev(out == NULL) returns without a host sync: `pending` marks results whose totals
     // and consistency flags have not been looked at yet; the next sync point resolves them)
     int       pending;
+    char      cached_motif[256];   // motif whose byte patterns are already in ctx->misc (skips a tiny H2D per call)
     char      pending_motif[256];
     uint32_t  pending_ev_cap, pending_run_cap;
     const corn_dbatch *last_db;

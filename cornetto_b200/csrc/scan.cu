@@ -79,6 +79,67 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_block_scan(const T *in, T *out
 template <typename T>
 __global__ void k_zero_total(T *t) { *t = zero_of(T()); }
 
+// Single-launch scan for tables of up to ~1M entries (the per-tile counts of a 4 GiB batch are 131 072):
+// one block of 32 warps; warp w owns a contiguous slice and walks it 32 entries at a time (coalesced),
+// first to get its total, then -- after the 32 totals have been scanned -- to write the prefixes.
+// The table is read twice from L2; what is saved is two launches and their drain/fill latency.
+template <typename T>
+__device__ __forceinline__ T warp_inclusive(T v, int lane);
+template <>
+__device__ __forceinline__ uint32_t warp_inclusive<uint32_t>(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    return v;
+}
+template <>
+__device__ __forceinline__ uint4 warp_inclusive<uint4>(uint4 v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, v.x, o), b = __shfl_up_sync(0xffffffffu, v.y, o);
+        const uint32_t c = __shfl_up_sync(0xffffffffu, v.z, o), d = __shfl_up_sync(0xffffffffu, v.w, o);
+        if (lane >= o) { v.x += a; v.y += b; v.z += c; v.w += d; }
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t bcast31(uint32_t v) { return __shfl_sync(0xffffffffu, v, 31); }
+__device__ __forceinline__ uint4 bcast31(uint4 v)
+{
+    return make_uint4(__shfl_sync(0xffffffffu, v.x, 31), __shfl_sync(0xffffffffu, v.y, 31), __shfl_sync(0xffffffffu, v.z, 31), __shfl_sync(0xffffffffu, v.w, 31));
+}
+__device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) { return a - b; }
+__device__ __forceinline__ uint4 sub(uint4 a, uint4 b) { return make_uint4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
+template <typename T>
+__global__ void __launch_bounds__(1024) k_scan_single(const T *in, T *out, size_t n, T *total_out)
+{
+    __shared__ T wtot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t per = ((n + 31) / 32 + 31) / 32 * 32;           // slice length, multiple of 32
+    const size_t lo = (size_t)warp * per, hi = lo + per < n ? lo + per : n;
+    T acc = zero_of(T());
+    for (size_t i = lo + lane; i < hi; i += 32) acc = add(acc, in[i]);
+    acc = bcast31(warp_inclusive<T>(acc, lane));
+    if (lane == 0) wtot[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        const T v = wtot[lane];
+        const T inc = warp_inclusive<T>(v, lane);
+        wtot[lane] = sub(inc, v);                                  // exclusive base of every warp's slice
+        if (lane == 31 && total_out) *total_out = inc;
+    }
+    __syncthreads();
+    T base = wtot[warp];
+    for (size_t i0 = lo; i0 < hi; i0 += 32) {
+        const size_t i = i0 + lane;
+        const T v = i < hi ? in[i] : zero_of(T());
+        const T inc = warp_inclusive<T>(v, lane);
+        if (i < hi) out[i] = add(base, sub(inc, v));
+        base = add(base, bcast31(inc));
+    }
+}
+
 template <typename T>
 int scan_impl(corn_ctx *ctx, const T *d_in, T *d_out, size_t n, T *d_total)
 {
@@ -87,6 +148,12 @@ int scan_impl(corn_ctx *ctx, const T *d_in, T *d_out, size_t n, T *d_total)
         return CORN_OK;
     }
     size_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (nb > 1 && n <= (1u << 20)) {
+        k_scan_single<T><<<1, 1024, 0, ctx->stream>>>(d_in, d_out, n, d_total);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+        return CORN_OK;
+    }
     if (nb == 1) {
         k_block_scan<T><<<1, SCAN_THREADS, 0, ctx->stream>>>(d_in, d_out, n, (const T *)NULL, d_total);
         corn_count_launch(ctx);

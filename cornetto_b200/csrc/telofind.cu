@@ -605,12 +605,17 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
     sp.pat = d_pat;
     sp.fc = mi.fc; sp.rc = mi.rc; sp.m = mi.m; sp.bordered = mi.bordered;
 
-    // pattern upload (pageable -> staged by the runtime; 512 bytes)
-    uint8_t hpat[512];
-    memset(hpat, 0, sizeof hpat);
-    memcpy(hpat, mi.fwd, mi.m); memcpy(hpat + 256, mi.rev, mi.m);
-    memcpy(ctx->h_pinned_small, hpat, 512);
-    CORN_CUDA(ctx, cudaMemcpyAsync(d_pat, ctx->h_pinned_small, 512, cudaMemcpyHostToDevice, st));
+    // pattern upload (512 bytes), only when the motif changed since the last call on this context
+    if (strcmp(ctx->cached_motif, motif) != 0 || ctx->cached_motif[0] == 0) {
+        uint8_t hpat[512];
+        memset(hpat, 0, sizeof hpat);
+        memcpy(hpat, mi.fwd, mi.m); memcpy(hpat + 256, mi.rev, mi.m);
+        CORN_CUDA(ctx, cudaStreamSynchronize(st));           // h_pinned_small may still be the target of an earlier readback
+        memcpy(ctx->h_pinned_small, hpat, 512);
+        CORN_CUDA(ctx, cudaMemcpyAsync(d_pat, ctx->h_pinned_small, 512, cudaMemcpyHostToDevice, st));
+        CORN_CUDA(ctx, cudaStreamSynchronize(st));
+        snprintf(ctx->cached_motif, sizeof ctx->cached_motif, "%s", motif);
+    }
     k_reset_counter<<<1, 32, 0, st>>>(sp.tile_counter, 3);
     corn_count_launch(ctx);
 
