@@ -148,7 +148,7 @@ int scan_impl(corn_ctx *ctx, const T *d_in, T *d_out, size_t n, T *d_total)
         return CORN_OK;
     }
     size_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    if (nb > 1 && n <= (1u << 20)) {
+    if (nb > 1 && n * sizeof(T) <= (128u << 10)) {   /* one SM streams ~50 GB/s: beyond this the 3-launch scan wins */
         k_scan_single<T><<<1, 1024, 0, ctx->stream>>>(d_in, d_out, n, d_total);
         corn_count_launch(ctx);
         CORN_LAUNCH_CHECK(ctx);
