@@ -232,6 +232,11 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
 }
 
 // one warp-task: 32 chunks (one per lane) stepped in lockstep
+// NB = 32-position blocks covering the window (2 for W <= 66, else 4); COOP = warp-cooperative
+// find_perfect (T >= 5; below that a candidate can have new_l == 0 and the serial form is used).
+// Template parameters rather than run-time switches: the register allocation of the default
+// W = 64 kernel is then not sized by the four-block arrays of the W = 128 one.
+template <int NB, bool COOP>
 __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp_id, uint32_t n_warps, uint32_t *smem, const SdLayout &lay,
                                                 uint8_t *cnt, int lane)
 {
@@ -272,7 +277,6 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
         const int stop = c1 < len ? c1 : len;
         n_steps = (stop - p0) + (c1 >= len ? 1 : 0);  // + the reference's i == l_seq iteration for the record's last chunk
     }
-    const bool coop = T >= 5;                         // (below that a candidate can have new_l == 0: serial form)
 
     for (int step = 0;; ++step) {
         const bool live = step < n_steps;
@@ -301,20 +305,18 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
         while (todo) {
             const int leader = __ffs(todo) - 1;
             todo &= todo - 1;
-            if (W <= 66) pop_coop<2>(leader, lane, s, (int)s.t, smem, lay, W);
-            else         pop_coop<4>(leader, lane, s, (int)s.t, smem, lay, W);
+            pop_coop<NB>(leader, lane, s, (int)s.t, smem, lay, W);
         }
         bool trig = false;
         if (emit && s.rw * 10 > s.L * T) {
-            if (!coop) sd_find_perfect(s, m, T, start, W);
+            if (!COOP) sd_find_perfect(s, m, T, start, W);
             else trig = s.wn - s.L - 1 >= 0;          // no index to examine otherwise
         }
         todo = __ballot_sync(FULL, trig);
         while (todo) {
             const int leader = __ffs(todo) - 1;
             todo &= todo - 1;
-            if (W <= 66) fp_coop<2>(leader, lane, s, start, smem, lay, my_slots, cnt, T, W);
-            else         fp_coop<4>(leader, lane, s, start, smem, lay, my_slots, cnt, T, W);
+            if (COOP) fp_coop<NB>(leader, lane, s, start, smem, lay, my_slots, cnt, T, W);
         }
     }
     sd_sink_close(sink);
@@ -373,7 +375,8 @@ __global__ void __launch_bounds__(256) k_sdust_order(const uint8_t *__restrict__
 
 // Persistent grid: warps claim warp-tasks from a counter, so the kernel ends one task -- not one wave
 // of blocks -- after the last claim.
-__global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
+template <int NB, bool COOP>
+__global__ void __launch_bounds__(SD_BLOCK, (NB == 2 && COOP) ? 8 : 5) k_sdust_scan(const SdParams P)
 {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31;
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(SD_BLOCK) k_sdust_scan(const SdParams P)
         if (lane == 0) w = atomicAdd(P.task_counter, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= n_warps) break;
-        sdust_warp_task(P, P.task_list[w], n_warps, smem, lay, cnt, lane);
+        sdust_warp_task<NB, COOP>(P, P.task_list[w], n_warps, smem, lay, cnt, lane);
         __syncwarp();
     }
 }
@@ -440,9 +443,12 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     // kernel lasts as long as that one chain: balance "all work / machine rate" against "C x slow-step
     // time", which on a B200 puts C near n_bases / 270 000.  Results do not depend on it.
     const size_t smem = SdLayout(W).bytes();
-    CORN_CUDA(ctx, cudaFuncSetAttribute(k_sdust_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    typedef void (*sd_kernel_t)(const SdParams);
+    const sd_kernel_t kern = W <= 66 ? (T >= 5 ? k_sdust_scan<2, true> : k_sdust_scan<2, false>)
+                                     : (T >= 5 ? k_sdust_scan<4, true> : k_sdust_scan<4, false>);
+    CORN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sdust_scan, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
     int C = 4096;
     {
         const uint64_t want = db->n_bases / ((uint64_t)ctx->sm_count * 1824u + 1);
@@ -500,7 +506,7 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     {
         const unsigned want = (n_chunks + SD_BLOCK - 1) / SD_BLOCK, resident = (unsigned)(ctx->sm_count * blocks_per_sm);
-        k_sdust_scan<<<want < resident ? want : resident, SD_BLOCK, smem, st>>>(sp);
+        kern<<<want < resident ? want : resident, SD_BLOCK, smem, st>>>(sp);
     }
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
