@@ -44,6 +44,11 @@ class Intervals(C.Structure):
                 ("_owner", C.c_void_p)]
 
 
+class Ingest(C.Structure):
+    _fields_ = [("db", C.c_void_p), ("n_rec", C.c_uint32), ("hdr_off", C.c_void_p), ("length", C.c_void_p),
+                ("consumed", C.c_uint64), ("irregular", C.c_int), ("_owner", C.c_void_p)]
+
+
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("scan_ms", C.c_float), ("post_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("launches", C.c_uint32), ("out_bytes", C.c_uint64)]
@@ -60,6 +65,7 @@ SYMBOLS = [
     "corn_gpu_telofind", "corn_gpu_telofind_dev", "corn_gpu_hits_free",
     "corn_gpu_telowin", "corn_gpu_windows_free",
     "corn_gpu_sdust", "corn_gpu_sdust_dev", "corn_gpu_intervals_free",
+    "corn_gpu_ingest", "corn_gpu_ingest_free", "corn_gpu_host_register", "corn_gpu_host_unregister",
     "corn_gpu_last_timing", "corn_gpu_total_launches",
     "corn_bench_fill_random", "corn_bench_apply_features", "corn_bench_download_all", "corn_bench_flush_l2",
 ]
@@ -120,6 +126,12 @@ def load() -> C.CDLL:
     L.corn_gpu_sdust_dev.argtypes = [vp, vp, i32, i32, C.POINTER(Intervals)]
     L.corn_gpu_intervals_free.argtypes = [C.POINTER(Intervals)]
     L.corn_gpu_intervals_free.restype = None
+    L.corn_gpu_ingest.argtypes = [vp, vp, u64, i32, C.POINTER(Ingest)]
+    L.corn_gpu_ingest_free.argtypes = [C.POINTER(Ingest)]
+    L.corn_gpu_ingest_free.restype = None
+    L.corn_gpu_host_register.argtypes = [vp, u64]
+    L.corn_gpu_host_unregister.argtypes = [vp]
+    L.corn_gpu_host_unregister.restype = None
     L.corn_gpu_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.corn_gpu_total_launches.argtypes = [vp]
     L.corn_gpu_total_launches.restype = u64
@@ -271,6 +283,46 @@ class Context:
         iv = Intervals()
         _check(self.ctx, self.L.corn_gpu_sdust_dev(self.ctx, db, T, W, C.byref(iv)), "corn_gpu_sdust_dev")
         return self._intervals(iv)
+
+    def ingest(self, text, final: bool = True, keep_db: bool = False, pin: bool = False):
+        """corn_gpu_ingest on a block of FASTA/FASTQ text (bytes or a uint8 array).  Returns a dict: irregular,
+        consumed, hdr_off, length and -- unless keep_db -- the record bytes (`seq`, a list) downloaded again;
+        with keep_db the resident batch handle is returned as `db` (free with free_dbatch)."""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
+        if pin and len(buf):
+            self.L.corn_gpu_host_register(buf.ctypes.data, len(buf))
+        ing = Ingest()
+        try:
+            _check(self.ctx, self.L.corn_gpu_ingest(self.ctx, buf.ctypes.data if len(buf) else None, len(buf), int(final), C.byref(ing)),
+                   "corn_gpu_ingest")
+        finally:
+            if pin and len(buf):
+                self.L.corn_gpu_host_unregister(buf.ctypes.data)
+        n = int(ing.n_rec)
+        res = {"irregular": bool(ing.irregular), "consumed": int(ing.consumed), "n_rec": n,
+               "hdr_off": np.ctypeslib.as_array(C.cast(ing.hdr_off, C.POINTER(C.c_uint64)), (n,)).copy() if n else np.zeros(0, np.uint64),
+               "length": np.ctypeslib.as_array(C.cast(ing.length, C.POINTER(C.c_uint32)), (n,)).copy() if n else np.zeros(0, np.uint32)}
+        db = ing.db
+        self.L.corn_gpu_ingest_free(C.byref(ing))
+        if keep_db:
+            res["db"] = db
+            return res
+        if db:
+            flat = self.download_all(db)
+            off = 0
+            seqs = []
+            for ln in res["length"]:
+                ln = int(ln)
+                seqs.append(flat[off:off + ln].tobytes())
+                span = (ln + 1 + 31) // 32 * 32
+                assert not flat[off + ln:off + span].any(), "padding not zero"
+                off += span
+            assert off == len(flat)
+            res["seq"] = seqs
+            self.free(db)
+        else:
+            res["seq"] = []
+        return res
 
     def timing(self) -> dict:
         t = Timing()

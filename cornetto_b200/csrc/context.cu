@@ -2,6 +2,8 @@
 #include <pthread.h>
 #include <stdarg.h>
 
+#include <thread>
+
 #include "corn_internal.cuh"
 
 // --------------------------------------------------------------------------------------------
@@ -86,11 +88,17 @@ extern "C" void corn_gpu_destroy(corn_ctx_t *ctx)
     corn_ctx_adopt(ctx, NULL);
     if (ctx->spare_base) cudaFree(ctx->spare_base);
     corn_dbuf *bufs[] = { &ctx->cand, &ctx->tile_tab, &ctx->events, &ctx->runs, &ctx->misc, &ctx->scan_tmp,
-                          &ctx->bins, &ctx->bitmap, &ctx->wins, &ctx->sd_slots, &ctx->sd_out, &ctx->sd_tab };
+                          &ctx->bins, &ctx->bitmap, &ctx->wins, &ctx->sd_slots, &ctx->sd_out, &ctx->sd_tab,
+                          &ctx->ing_text, &ctx->ing_tab, &ctx->ing_lines, &ctx->ing_rec };
     for (size_t i = 0; i < sizeof bufs / sizeof bufs[0]; ++i) dbuf_free(bufs[i]);
     for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->own_stream);
     cudaFreeHost(ctx->h_pinned_small);
+    if (ctx->stage) {
+        cudaFreeHost(ctx->stage);
+        for (int i = 0; i < CORN_STAGE_THREADS; ++i) cudaStreamDestroy(ctx->stage_stream[i]);
+        for (int i = 0; i < CORN_STAGE_THREADS * CORN_STAGE_SLOTS; ++i) cudaEventDestroy(ctx->stage_ev[i]);
+    }
     free(ctx);
 }
 
@@ -98,6 +106,64 @@ extern "C" int corn_gpu_set_stream(corn_ctx_t *ctx, void *s)
 {
     if (!ctx) return CORN_E_ARG;
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return CORN_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// host -> device copies
+// --------------------------------------------------------------------------------------------
+static void stage_worker(corn_ctx *ctx, int t, uint8_t *d_dst, const uint8_t *h_src, size_t bytes, cudaError_t *err)
+{
+    cudaSetDevice(ctx->device);
+    const size_t n_piece = (bytes + CORN_STAGE_BYTES - 1) / CORN_STAGE_BYTES;
+    int use = 0;
+    for (size_t p = (size_t)t; p < n_piece; p += CORN_STAGE_THREADS, ++use) {
+        const int slot = t * CORN_STAGE_SLOTS + (use % CORN_STAGE_SLOTS);
+        uint8_t *buf = ctx->stage + (size_t)slot * CORN_STAGE_BYTES;
+        const size_t off = p * CORN_STAGE_BYTES, len = bytes - off < CORN_STAGE_BYTES ? bytes - off : CORN_STAGE_BYTES;
+        cudaError_t e = use >= CORN_STAGE_SLOTS ? cudaEventSynchronize(ctx->stage_ev[slot]) : cudaSuccess;   // slot drained?
+        if (e == cudaSuccess) {
+            memcpy(buf, h_src + off, len);
+            e = cudaMemcpyAsync(d_dst + off, buf, len, cudaMemcpyHostToDevice, ctx->stage_stream[t]);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->stage_ev[slot], ctx->stage_stream[t]);
+        if (e != cudaSuccess) { *err = e; return; }
+    }
+}
+
+int corn_h2d(corn_ctx *ctx, void *d_dst, const void *h_src, size_t bytes)
+{
+    if (!bytes) return CORN_OK;
+    cudaPointerAttributes at;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&at, h_src) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+    if (pinned || bytes < 4 * (size_t)CORN_STAGE_BYTES) {
+        CORN_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return CORN_OK;
+    }
+    if (!ctx->stage) {
+        CORN_CUDA(ctx, cudaMallocHost((void **)&ctx->stage, (size_t)CORN_STAGE_THREADS * CORN_STAGE_SLOTS * CORN_STAGE_BYTES));
+        for (int i = 0; i < CORN_STAGE_THREADS; ++i) CORN_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stage_stream[i], cudaStreamNonBlocking));
+        for (int i = 0; i < CORN_STAGE_THREADS * CORN_STAGE_SLOTS; ++i) CORN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    }
+    // the copy streams start after whatever ctx->stream has queued so far (e.g. a kernel still reading d_dst)
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[15], ctx->stream));
+    for (int i = 0; i < CORN_STAGE_THREADS; ++i) CORN_CUDA(ctx, cudaStreamWaitEvent(ctx->stage_stream[i], ctx->ev[15], 0));
+    cudaError_t err[CORN_STAGE_THREADS];
+    std::thread th[CORN_STAGE_THREADS - 1];
+    for (int t = 0; t < CORN_STAGE_THREADS; ++t) err[t] = cudaSuccess;
+    for (int t = 1; t < CORN_STAGE_THREADS; ++t)
+        th[t - 1] = std::thread(stage_worker, ctx, t, (uint8_t *)d_dst, (const uint8_t *)h_src, bytes, &err[t]);
+    stage_worker(ctx, 0, (uint8_t *)d_dst, (const uint8_t *)h_src, bytes, &err[0]);
+    for (int t = 1; t < CORN_STAGE_THREADS; ++t) th[t - 1].join();
+    for (int t = 0; t < CORN_STAGE_THREADS; ++t)
+        if (err[t] != cudaSuccess) return corn_set_err(ctx, CORN_E_CUDA, "staged host->device copy: %s", cudaGetErrorString(err[t]));
+    // ... and ctx->stream continues after the last piece of every copy stream
+    for (int t = 0; t < CORN_STAGE_THREADS; ++t) {
+        CORN_CUDA(ctx, cudaEventRecord(ctx->ev[15], ctx->stage_stream[t]));
+        CORN_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[15], 0));
+    }
     return CORN_OK;
 }
 
@@ -395,8 +461,8 @@ extern "C" int corn_gpu_upload(corn_ctx_t *ctx, const corn_batch_t *b, corn_dbat
     // the layout contract makes the caller responsible for the zero padding between records.
     if (e == cudaSuccess) e = cudaMemsetAsync(db->d_base, 0, CORN_GUARD_BYTES, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(db->d_seq + b->total_bytes, 0, db->span_bytes - CORN_GUARD_BYTES - b->total_bytes, ctx->stream);
-    if (e == cudaSuccess && b->total_bytes) e = cudaMemcpyAsync(db->d_seq, b->seq, b->total_bytes, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) r = dbatch_tables_to_device(ctx, db);
+    if (e == cudaSuccess && b->total_bytes) r = corn_h2d(ctx, db->d_seq, b->seq, b->total_bytes);
+    if (e == cudaSuccess && r == CORN_OK) r = dbatch_tables_to_device(ctx, db);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[1], ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess || r != CORN_OK) {
@@ -427,6 +493,29 @@ extern "C" int corn_gpu_dbatch_alloc(corn_ctx_t *ctx, const uint32_t *length, ui
     if (e != cudaSuccess || r != CORN_OK) {
         corn_gpu_dbatch_free(ctx, db);
         return r != CORN_OK ? r : corn_set_err(ctx, CORN_E_CUDA, "dbatch_alloc: %s", cudaGetErrorString(e));
+    }
+    *out = db;
+    return CORN_OK;
+}
+
+// ingest.cu: a batch whose record bytes (and padding inside [0, total_bytes)) a kernel is about to
+// write; only the guard and the area behind total_bytes are zeroed here.  No host sync.
+int corn_dbatch_from_lengths(corn_ctx *ctx, const uint32_t *length, uint32_t n_rec, corn_dbatch **out)
+{
+    uint64_t *off = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)n_rec + 1));
+    if (!off) return CORN_E_NOMEM;
+    uint64_t used = 0;
+    for (uint32_t i = 0; i < n_rec; ++i) { off[i] = used; used += align_up((uint64_t)length[i] + 1, CORN_ALIGN); }
+    corn_dbatch *db = NULL;
+    int r = dbatch_new(ctx, off, length, n_rec, used, &db);
+    free(off);
+    if (r != CORN_OK) return r;
+    cudaError_t e = cudaMemsetAsync(db->d_base, 0, CORN_GUARD_BYTES, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(db->d_seq + used, 0, db->span_bytes - CORN_GUARD_BYTES - used, ctx->stream);
+    if (e == cudaSuccess) r = dbatch_tables_to_device(ctx, db);
+    if (e != cudaSuccess || r != CORN_OK) {
+        corn_gpu_dbatch_free(ctx, db);
+        return r != CORN_OK ? r : corn_set_err(ctx, CORN_E_CUDA, "dbatch_from_lengths: %s", cudaGetErrorString(e));
     }
     *out = db;
     return CORN_OK;

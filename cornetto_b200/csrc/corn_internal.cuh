@@ -53,6 +53,10 @@ struct corn_dbuf {         // grow-only device scratch
     size_t cap;
 };
 
+#define CORN_STAGE_THREADS 8
+#define CORN_STAGE_SLOTS   2
+#define CORN_STAGE_BYTES   (8u << 20)
+
 struct corn_ctx {
     int          device;
     int          sm_count;
@@ -75,6 +79,10 @@ struct corn_ctx {
     corn_dbuf sd_slots;    // sdust per-chunk interval slots
     corn_dbuf sd_out;      // sdust compacted output
     corn_dbuf sd_tab;      // sdust chunk tables
+    corn_dbuf ing_text;    // ingest: raw text block
+    corn_dbuf ing_tab;     // ingest: per-tile newline counts / bases
+    corn_dbuf ing_lines;   // ingest: line tables
+    corn_dbuf ing_rec;     // ingest: record table
 
     // one retired sequence buffer kept for the next upload (cudaMalloc/cudaFree of GBs cost milliseconds)
     uint8_t *spare_base;
@@ -98,7 +106,18 @@ struct corn_ctx {
     int       last_motif_len;
 
     void     *h_pinned_small;      // 4 KiB pinned scratch for small readbacks
+
+    // staging ring for host->device copies from pageable memory (corn_h2d)
+    uint8_t     *stage;            // CORN_STAGE_THREADS * CORN_STAGE_SLOTS slots of CORN_STAGE_BYTES, page-locked
+    cudaStream_t stage_stream[CORN_STAGE_THREADS];
+    cudaEvent_t  stage_ev[CORN_STAGE_THREADS * CORN_STAGE_SLOTS];
 };
+
+
+// Host->device copy ordered on ctx->stream.  Page-locked sources are copied directly; pageable ones
+// go through a small page-locked ring filled by CORN_STAGE_THREADS host threads (page-locking a
+// multi-GB buffer costs 0.1-0.4 s/GB and as much again to release: more than the copy itself).
+int corn_h2d(corn_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 
 // --------------------------------------------------------------------------------------------
 // error plumbing

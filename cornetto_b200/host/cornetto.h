@@ -43,10 +43,15 @@ corn_ctx_t *cornetto_gpu(void);
 void        cornetto_gpu_release(void);
 /* prints the library error and exits */
 void        cornetto_gpu_die(const char *what, int status);
+/* 1 (default): the process ends with _exit() once its output is flushed and skips freeing GPU
+ * contexts and large buffers; $CORNETTO_FAST_EXIT=0 restores the orderly teardown (leak checkers). */
+int         cornetto_fast_exit(void);
 
 /* ---- FASTA/FASTQ reader with kseq_read() semantics (src/kseq.h:184-224) -------------------- */
 typedef struct fastx fastx_t;
 fastx_t *fastx_open(const char *path);        /* "-" = stdin; plain or gzip; NULL if it cannot be opened */
+/* plain (uncompressed, seekable) files only: starts reading at a byte offset that is a record boundary */
+fastx_t *fastx_open_at(const char *path, uint64_t offset);
 void     fastx_close(fastx_t *fx);
 /* Advances to the next record header.  1 = a record begins (fastx_name() valid), 0 = end of input. */
 int      fastx_next(fastx_t *fx);
@@ -60,11 +65,24 @@ int      fastx_finish(fastx_t *fx);
 
 /* ---- record batches: names + pinned sequence bytes in the CORN_ALIGN layout ------------------ */
 typedef struct {
-    corn_hbatch_t *hb;
-    char   **name;        /* [n] strdup'ed */
+    corn_hbatch_t *hb;    /* host batch filled by the serial reader (NULL for device-parsed batches) */
+    char   **name;        /* [n] strdup'ed (serial reader) or pointers into name_arena (device-parsed) */
     uint32_t n, max_rec;
     int      eof;         /* input exhausted (or stopped at a malformed FASTQ record) */
+    /* device-parsed batches (ingest.c): the records are already resident */
+    corn_dbatch_t  *db;
+    const uint32_t *length;      /* [n] */
+    char           *name_arena;
 } rec_batch_t;
+
+/* record lengths of a batch, whichever way it was built */
+static inline const uint32_t *rec_batch_lengths(const rec_batch_t *b)
+{
+    if (b->db) return b->length;
+    corn_batch_t v;
+    corn_hbatch_view(b->hb, &v);
+    return v.length;
+}
 
 rec_batch_t *rec_batch_create(uint64_t capacity_bytes, uint32_t max_rec);
 void         rec_batch_destroy(rec_batch_t *b);
@@ -90,6 +108,16 @@ void outbuf_chr(outbuf_t *o, char c);
  * $CORNETTO_GPUS = number of devices to use (default 1; batches go round-robin over them). */
 typedef void (*batch_fn)(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *out, void *arg);
 void run_batch_pipeline(fastx_t *fx, const char *path, batch_fn fn, void *arg);
+
+/* ---- device-side parsing for plain files (ingest.c) --------------------------------------------
+ * Reads the file in large blocks, hands each block to corn_gpu_ingest() and calls fn with a
+ * device-parsed batch (b->db set).  Returns 1 when the whole input was handled this way.  Returns 0
+ * when the input is not eligible (stdin, gzip, $CORNETTO_INGEST=0) or turned out to be irregular
+ * text: everything before *resume has been processed and written, and the caller continues with the
+ * serial reader from byte offset *resume. */
+int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resume);
+/* length of a record name starting at p: up to the first isspace() byte or max (src/kseq.h:195) */
+size_t cornetto_name_len(const uint8_t *p, size_t max);
 
 /* ---- khash iteration order (src/khash.h:230-348,395-400), for telobreaks' output order -------- */
 size_t khash_str_order(const char *const *names, size_t n, size_t *order);

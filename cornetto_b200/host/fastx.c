@@ -61,6 +61,15 @@ fastx_t *fastx_open(const char *path)
     return fx;
 }
 
+fastx_t *fastx_open_at(const char *path, uint64_t offset)
+{
+    fastx_t *fx = fastx_open(path);
+    if (fx && offset) {
+        if (fx->fd < 0 || lseek(fx->fd, (off_t)offset, SEEK_SET) < 0) { fastx_close(fx); return NULL; }
+    }
+    return fx;
+}
+
 void fastx_close(fastx_t *fx)
 {
     if (!fx) return;

@@ -1,0 +1,302 @@
+/* cornetto_b200/host/ingest.c -- feeder for plain FASTA/FASTQ files that parses on the GPU.
+ *
+ * The reference reads every input through kseq (src/kseq.h:184-224), one byte loop on one thread;
+ * cornetto_b200/host/fastx.c is that loop, restated, and stays the reader for stdin, gzip and
+ * irregular text.  For plain files this feeder skips it: the calling thread only read(2)s the file
+ * in large blocks; a worker thread per GPU context hands each block to corn_gpu_ingest(), which
+ * ships the raw bytes over PCIe, finds the records on the device and leaves them resident, and then
+ * runs the scan (telofind / sdust callback) on that resident batch.  Blocks are cut where the device
+ * says the last complete record ended (`consumed`); the unconsumed tail is carried into the next
+ * block.  Output is written strictly in block order, so stdout is byte-identical to the sequential
+ * reference loop.
+ *
+ * If a block is outside the regular subset (include/corn_gpu.h: corn_gpu_ingest), or holds a record
+ * larger than the block, run_ingest_pipeline() stops, reports the file offset of that block and the
+ * caller continues from there with the serial reader. */
+#include <ctype.h>
+#include <fcntl.h>
+#include <pthread.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "cornetto.h"
+
+size_t cornetto_name_len(const uint8_t *p, size_t max)
+{
+    size_t k = 0;
+    while (k < max && !isspace(p[k])) ++k;
+    return k;
+}
+
+typedef struct {
+    pthread_t       th;
+    pthread_mutex_t mu;
+    pthread_cond_t  cv;
+    int             state;       /* 0 idle (output, if any, ready), 1 has a block, 2 quit */
+    int             ingested;    /* the current block's consumed / irregular are valid */
+    int             device;
+    corn_ctx_t     *ctx;
+    uint8_t        *text;        /* block buffer (page-locked by the worker on first use) */
+    uint64_t        cap, n;
+    int             final, teardown;
+    uint64_t        consumed;
+    int             irregular;
+    outbuf_t        out;
+    batch_fn        fn;
+    void           *arg;
+} iworker_t;
+
+static void build_names(rec_batch_t *b, const uint8_t *text, uint64_t n, const corn_ingest_t *ing)
+{
+    size_t total = 0;
+    b->name = (char **)malloc(sizeof(char *) * ((size_t)ing->n_rec + 1));
+    CORN_MALLOC_CHK(b->name);
+    size_t *len = (size_t *)malloc(sizeof(size_t) * ((size_t)ing->n_rec + 1));
+    CORN_MALLOC_CHK(len);
+    for (uint32_t r = 0; r < ing->n_rec; ++r) {
+        const uint64_t at = ing->hdr_off[r] + 1;
+        len[r] = at < n ? cornetto_name_len(text + at, (size_t)(n - at)) : 0;
+        total += len[r] + 1;
+    }
+    b->name_arena = (char *)malloc(total + 1);
+    CORN_MALLOC_CHK(b->name_arena);
+    char *w = b->name_arena;
+    for (uint32_t r = 0; r < ing->n_rec; ++r) {
+        memcpy(w, text + ing->hdr_off[r] + 1, len[r]);
+        w[len[r]] = 0;
+        b->name[r] = w;
+        w += len[r] + 1;
+    }
+    free(len);
+}
+
+static int g_trace;     /* $CORNETTO_TRACE=1: phase times on stderr */
+static double g_t0;
+#define TRACE(...) do { if (g_trace) { fprintf(stderr, "[%7.3f] ", realtime() - g_t0); fprintf(stderr, __VA_ARGS__); } } while (0)
+
+static void *iworker_main(void *p)
+{
+    iworker_t *w = (iworker_t *)p;
+    double t0 = realtime();
+    int r = corn_gpu_init(w->device, &w->ctx);
+    TRACE("[ingest] worker dev %d: corn_gpu_init %.3f s\n", w->device, realtime() - t0);
+    if (r != CORN_OK) {
+        CORN_ERROR("cannot initialise the GPU (device %d): %s", w->device, corn_gpu_strerror(r));
+        exit(EXIT_FAILURE);
+    }
+    for (;;) {
+        pthread_mutex_lock(&w->mu);
+        while (w->state == 0) pthread_cond_wait(&w->cv, &w->mu);
+        const int st = w->state;
+        pthread_mutex_unlock(&w->mu);
+        if (st == 2) break;
+        /* (the block buffer stays pageable: the library stages the copy through its own small page-locked
+         *  ring, which is faster than page-locking and releasing GBs for a buffer that is used once or twice) */
+        t0 = realtime();
+        corn_ingest_t ing;
+        r = corn_gpu_ingest(w->ctx, w->text, w->n, w->final, &ing);
+        if (g_trace) {
+            corn_timing_t tm;
+            corn_gpu_last_timing(w->ctx, &tm);
+            TRACE("[ingest] corn_gpu_ingest %.3f s (h2d %.1f ms, tables %.1f ms, copy %.1f ms) %u records, irregular %d\n",
+                  realtime() - t0, tm.h2d_ms, tm.post_ms, tm.scan_ms, ing.n_rec, ing.irregular);
+        }
+        if (r != CORN_OK) {
+            CORN_ERROR("ingest: %s (%s)", corn_gpu_strerror(r), corn_gpu_last_error(w->ctx));
+            exit(EXIT_FAILURE);
+        }
+        pthread_mutex_lock(&w->mu);
+        w->consumed = ing.consumed; w->irregular = ing.irregular; w->ingested = 1;
+        pthread_cond_broadcast(&w->cv);
+        pthread_mutex_unlock(&w->mu);
+        if (!ing.irregular && ing.n_rec) {
+            rec_batch_t b;
+            memset(&b, 0, sizeof b);
+            b.n = ing.n_rec; b.db = ing.db; b.length = ing.length;
+            t0 = realtime();
+            build_names(&b, w->text, w->n, &ing);
+            w->fn(w->ctx, &b, &w->out, w->arg);
+            TRACE("[ingest] scan + format %.3f s\n", realtime() - t0);
+            free(b.name); free(b.name_arena);
+            corn_gpu_dbatch_free(w->ctx, ing.db);
+        }
+        corn_gpu_ingest_free(&ing);
+        pthread_mutex_lock(&w->mu);
+        w->state = 0;
+        pthread_cond_broadcast(&w->cv);
+        pthread_mutex_unlock(&w->mu);
+    }
+    if (w->teardown) corn_gpu_destroy(w->ctx);
+    return NULL;
+}
+
+static void wait_idle(iworker_t *w)
+{
+    pthread_mutex_lock(&w->mu);
+    while (w->state != 0) pthread_cond_wait(&w->cv, &w->mu);
+    pthread_mutex_unlock(&w->mu);
+}
+
+/* ---- file reading: the page cache delivers ~3 GB/s to one thread, so large blocks are read by four -- */
+typedef struct { int fd; uint8_t *dst; uint64_t off, n, got; pthread_t th; } slice_t;
+
+static uint64_t pread_full(int fd, uint8_t *dst, uint64_t off, uint64_t n)
+{
+    uint64_t got = 0;
+    while (got < n) {
+        const size_t want = n - got > (1u << 30) ? (1u << 30) : (size_t)(n - got);
+        const ssize_t k = pread(fd, dst + got, want, (off_t)(off + got));
+        if (k < 0) { if (errno == EINTR) continue; break; }
+        if (k == 0) break;
+        got += (uint64_t)k;
+    }
+    return got;
+}
+
+static void *slice_main(void *p)
+{
+    slice_t *s = (slice_t *)p;
+    s->got = pread_full(s->fd, s->dst, s->off, s->n);
+    return NULL;
+}
+
+static uint64_t read_block(int fd, uint8_t *dst, uint64_t off, uint64_t n)
+{
+    enum { PARTS = 4 };
+    if (n < (64u << 20)) return pread_full(fd, dst, off, n);
+    slice_t s[PARTS];
+    const uint64_t per = (n / PARTS + 4095) & ~4095ull;
+    int started = 0;
+    for (int i = 0; i < PARTS; ++i) {
+        const uint64_t a = per * (uint64_t)i;
+        if (a >= n) break;
+        s[i].fd = fd; s[i].dst = dst + a; s[i].off = off + a; s[i].n = a + per > n ? n - a : per; s[i].got = 0;
+        if (i == PARTS - 1 || pthread_create(&s[i].th, NULL, slice_main, &s[i]) != 0) { slice_main(&s[i]); s[i].th = 0; }
+        ++started;
+    }
+    uint64_t got = 0;
+    int short_read = 0;
+    for (int i = 0; i < started; ++i) {
+        if (s[i].th) pthread_join(s[i].th, NULL);
+        if (!short_read) got += s[i].got;
+        if (s[i].got < s[i].n) short_read = 1;
+    }
+    return got;
+}
+
+int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resume)
+{
+    *resume = 0;
+    g_trace = getenv("CORNETTO_TRACE") && atoi(getenv("CORNETTO_TRACE")) > 0;
+    g_t0 = realtime();
+    const char *off = getenv("CORNETTO_INGEST");
+    if (off && atoi(off) == 0) return 0;
+    if (strcmp(path, "-") == 0) return 0;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return 0;
+    struct stat sb;
+    unsigned char magic[2] = { 0, 0 };
+    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size < 2 || pread(fd, magic, 2, 0) != 2 ||
+        (magic[0] == 0x1f && magic[1] == 0x8b) || (magic[0] != '>' && magic[0] != '@')) {
+        close(fd);
+        return 0;
+    }
+    const uint64_t size = (uint64_t)sb.st_size;
+
+    int n_gpus = 1;
+    const char *e = getenv("CORNETTO_GPUS");
+    if (e && atoi(e) > 0) n_gpus = atoi(e);
+    if (n_gpus > 1) {
+        const int avail = corn_gpu_device_count();
+        if (avail <= 0) {
+            CORN_ERROR("cannot initialise the GPU: %s", corn_gpu_strerror(avail < 0 ? avail : CORN_E_NOGPU));
+            exit(EXIT_FAILURE);
+        }
+        if (n_gpus > avail) n_gpus = avail;
+    }
+    const int n_workers = n_gpus > 1 ? n_gpus : 2;
+    const char *dev0 = getenv("CORNETTO_GPU");
+    const int base_dev = (n_gpus == 1 && dev0) ? atoi(dev0) : 0;
+
+    /* block size: the whole file on one GPU, an n-th plus an eighth (room for the carried tail) on n */
+    const uint64_t max_block = 0xE0000000ull;
+    uint64_t block = n_gpus > 1 ? size / (uint64_t)n_gpus + size / (8ull * (uint64_t)n_gpus) + (1u << 16) : size;
+    const char *eb = getenv("CORNETTO_BATCH_BYTES"), *em = getenv("CORNETTO_BATCH_MB");
+    if (eb && atoll(eb) > 0) block = (uint64_t)atoll(eb);
+    else if (em && atoll(em) > 0) block = (uint64_t)atoll(em) << 20;
+    if (block > size) block = size;
+    if (block > max_block) block = max_block;
+    if (block < 64) block = 64;
+
+    iworker_t *w = (iworker_t *)calloc((size_t)n_workers, sizeof(iworker_t));
+    CORN_MALLOC_CHK(w);
+    for (int i = 0; i < n_workers; ++i) {
+        pthread_mutex_init(&w[i].mu, NULL);
+        pthread_cond_init(&w[i].cv, NULL);
+        w[i].device = base_dev + (i % n_gpus);
+        w[i].fn = fn; w[i].arg = arg;
+        outbuf_init(&w[i].out, NULL);
+        if (pthread_create(&w[i].th, NULL, iworker_main, &w[i]) != 0) { CORN_ERROR("%s", "pthread_create failed"); exit(EXIT_FAILURE); }
+    }
+
+    int dispatched = 0, written = 0, complete = 0;
+    uint64_t file_pos = 0;                 /* next byte to read from the file */
+    const uint8_t *carry = NULL;           /* unconsumed tail of the previous block (in that worker's buffer) */
+    uint64_t carry_len = 0;
+    for (;;) {
+        iworker_t *x = &w[dispatched % n_workers];
+        wait_idle(x);
+        if (dispatched - n_workers >= written) { outbuf_write(&x->out, stdout); written = dispatched - n_workers + 1; }
+        if (!x->text) {
+            void *p = NULL;
+            if (posix_memalign(&p, 2u << 20, block + 64) != 0) p = NULL;
+            CORN_MALLOC_CHK(p);
+            madvise(p, block + 64, MADV_HUGEPAGE);         /* fewer faults while reading, cheaper to release */
+            x->text = (uint8_t *)p; x->cap = block + 64;
+        }
+        if (carry_len >= block) { *resume = file_pos - carry_len; break; }      /* (cannot happen: a block with no record ends the loop below) */
+        if (carry_len) memcpy(x->text, carry, carry_len);
+        const uint64_t want = size - file_pos < block - carry_len ? size - file_pos : block - carry_len;
+        const double t_rd = realtime();
+        const uint64_t fresh = read_block(fd, x->text + carry_len, file_pos, want);
+        TRACE("[ingest] read %.1f MB in %.3f s\n", (double)fresh / 1e6, realtime() - t_rd);
+        const uint64_t block_off = file_pos - carry_len;
+        file_pos += fresh;
+        x->n = carry_len + fresh;
+        x->final = (fresh < want || file_pos >= size);
+        x->ingested = 0;
+        pthread_mutex_lock(&x->mu);
+        x->state = 1;
+        pthread_cond_broadcast(&x->cv);
+        while (!x->ingested) pthread_cond_wait(&x->cv, &x->mu);
+        pthread_mutex_unlock(&x->mu);
+        ++dispatched;
+        if (x->irregular || (x->consumed == 0 && !x->final)) { *resume = block_off; break; }
+        carry = x->text + x->consumed;
+        carry_len = x->n - x->consumed;
+        if (x->final) { complete = 1; break; }
+    }
+    for (; written < dispatched; ++written) {
+        iworker_t *y = &w[written % n_workers];
+        wait_idle(y);
+        const double t_wr = realtime();
+        outbuf_write(&y->out, stdout);
+        TRACE("[ingest] wrote output in %.3f s\n", realtime() - t_wr);
+    }
+    for (int i = 0; i < n_workers; ++i) {
+        pthread_mutex_lock(&w[i].mu);
+        w[i].teardown = !complete || !cornetto_fast_exit();      /* the serial reader continues: give the device memory back */
+        w[i].state = 2;
+        pthread_cond_broadcast(&w[i].cv);
+        pthread_mutex_unlock(&w[i].mu);
+        pthread_join(w[i].th, NULL);
+        outbuf_free(&w[i].out);
+        if (!complete || !cornetto_fast_exit()) free(w[i].text);
+    }
+    fflush(stdout);
+    free(w);
+    close(fd);
+    TRACE("[ingest] pipeline done (complete %d)\n", complete);
+    return complete;
+}

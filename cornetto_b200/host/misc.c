@@ -44,6 +44,12 @@ corn_ctx_t *cornetto_gpu(void)
     return g_ctx;
 }
 
+int cornetto_fast_exit(void)
+{
+    const char *e = getenv("CORNETTO_FAST_EXIT");
+    return !(e && atoi(e) == 0);
+}
+
 void cornetto_gpu_release(void)
 {
     if (g_ctx) corn_gpu_destroy(g_ctx);

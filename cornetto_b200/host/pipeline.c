@@ -38,14 +38,14 @@ static void *worker_main(void *p)
         const int st = w->state;
         pthread_mutex_unlock(&w->mu);
         if (st == 2) break;
-        corn_hbatch_pin(w->batch->hb);                  /* once per buffer; a failure only costs H2D speed */
+        /* (batch buffers stay pageable: corn_gpu_upload stages the copy through a small page-locked ring) */
         w->fn(w->ctx, w->batch, &w->out, w->arg);
         pthread_mutex_lock(&w->mu);
         w->state = 0;
         pthread_cond_broadcast(&w->cv);
         pthread_mutex_unlock(&w->mu);
     }
-    corn_gpu_destroy(w->ctx);
+    if (!cornetto_fast_exit()) corn_gpu_destroy(w->ctx);
     return NULL;
 }
 
@@ -115,7 +115,7 @@ void run_batch_pipeline(fastx_t *fx, const char *path, batch_fn fn, void *arg)
         pthread_mutex_unlock(&w[i].mu);
         pthread_join(w[i].th, NULL);
         outbuf_free(&w[i].out);
-        if (w[i].batch) rec_batch_destroy(w[i].batch);
+        if (w[i].batch && !cornetto_fast_exit()) rec_batch_destroy(w[i].batch);
     }
     fflush(stdout);
     free(w);

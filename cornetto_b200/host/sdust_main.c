@@ -11,10 +11,14 @@ typedef struct { int T, W; } sdust_arg_t;
 static void sdust_batch(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *ob, void *arg)
 {
     const sdust_arg_t *a = (const sdust_arg_t *)arg;
-    corn_batch_t view;
-    corn_hbatch_view(b->hb, &view);
     corn_intervals_t iv;
-    int r = corn_gpu_sdust(ctx, &view, a->T, a->W, &iv);
+    int r;
+    if (b->db) r = corn_gpu_sdust_dev(ctx, b->db, a->T, a->W, &iv);       /* parsed on the device: already resident */
+    else {
+        corn_batch_t view;
+        corn_hbatch_view(b->hb, &view);
+        r = corn_gpu_sdust(ctx, &view, a->T, a->W, &iv);
+    }
     if (r != CORN_OK) {
         CORN_ERROR("sdust: %s (%s)", corn_gpu_strerror(r), corn_gpu_last_error(ctx));
         exit(EXIT_FAILURE);
@@ -67,7 +71,11 @@ int sdust_main(int argc, char *argv[])
     if (!fx) return 0;     /* the reference reads nothing from an unopenable file and returns 0 */
     sdust_arg_t sa;
     sa.T = T; sa.W = W;
-    run_batch_pipeline(fx, file, sdust_batch, &sa);
+    uint64_t resume = 0;
+    if (!run_ingest_pipeline(file, sdust_batch, &sa, &resume)) {
+        if (resume) { fastx_close(fx); fx = fastx_open_at(file, resume); if (!fx) return 0; }
+        run_batch_pipeline(fx, file, sdust_batch, &sa);
+    }
     fastx_close(fx);
     return 0;
 }

@@ -10,10 +10,15 @@
 static void telofind_batch(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *ob, void *arg)
 {
     const char *query = (const char *)arg;
-    corn_batch_t view;
-    corn_hbatch_view(b->hb, &view);
+    const uint32_t *length = rec_batch_lengths(b);
     corn_hits_t hits;
-    int r = corn_gpu_telofind(ctx, &view, query, &hits);
+    int r;
+    if (b->db) r = corn_gpu_telofind_dev(ctx, b->db, query, &hits);     /* parsed on the device: already resident */
+    else {
+        corn_batch_t view;
+        corn_hbatch_view(b->hb, &view);
+        r = corn_gpu_telofind(ctx, &view, query, &hits);
+    }
     if (r != CORN_OK) {
         CORN_ERROR("telofind: %s (%s)", corn_gpu_strerror(r), corn_gpu_last_error(ctx));
         exit(EXIT_FAILURE);
@@ -22,7 +27,7 @@ static void telofind_batch(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *ob, void *
         const corn_run_t *h = &hits.run[i];
         const char *name = b->name[h->rec];
         outbuf_str(ob, name, strlen(name));
-        outbuf_chr(ob, '\t'); outbuf_u64(ob, view.length[h->rec]);
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, length[h->rec]);
         outbuf_chr(ob, '\t'); outbuf_u64(ob, h->strand);
         outbuf_chr(ob, '\t'); outbuf_u64(ob, h->start);
         outbuf_chr(ob, '\t'); outbuf_u64(ob, h->end);
@@ -49,7 +54,11 @@ int find_telomere_main(int argc, char *argv[])
         CORN_ERROR("%s", "empty motif");
         exit(EXIT_FAILURE);
     }
-    run_batch_pipeline(fx, fasta, telofind_batch, (void *)query);
+    uint64_t resume = 0;
+    if (!run_ingest_pipeline(fasta, telofind_batch, (void *)query, &resume)) {
+        if (resume) { fastx_close(fx); fx = fastx_open_at(fasta, resume); CORN_F_CHK(fx, fasta); }
+        run_batch_pipeline(fx, fasta, telofind_batch, (void *)query);
+    }
     fastx_close(fx);
     return EXIT_SUCCESS;
 }

@@ -164,6 +164,42 @@ int  corn_gpu_sdust(corn_ctx_t *ctx, const corn_batch_t *batch, int T, int W, co
 int  corn_gpu_sdust_dev(corn_ctx_t *ctx, const corn_dbatch_t *db, int T, int W, corn_intervals_t *out);
 void corn_gpu_intervals_free(corn_intervals_t *iv);
 
+/* ---- ingest: replaces the byte loop of kseq_read()/ks_getuntil2(), src/kseq.h:102-141,184-224 ---
+ * Parses plain FASTA/FASTQ TEXT on the device: ships the raw file bytes over PCIe once, finds the
+ * line structure, builds the record table and compacts the sequence bytes into the resident
+ * CORN_ALIGN layout that the *_dev entry points take.  `text` must start at a record boundary:
+ * its first byte is the '>' or '@' of a header (the start of the file, or where the previous call
+ * stopped: text + consumed).  `final` != 0 says the text ends at the end of the input, so the last
+ * record is complete; otherwise the trailing incomplete record is left to the next call.
+ *
+ * Only REGULAR text is parsed on the device -- the subset on which the result provably equals
+ * kseq_read()'s (cornetto_b200/csrc/ingest_core.cuh states the rules and why):
+ *   FASTA : every record is a '>' line followed by sequence lines, none of which starts with '@' or
+ *           '+' or consists of a lone '\r';
+ *   FASTQ : four lines per record, '@...' / sequence / '+...' / quality of the same length.
+ * Anything else (multi-line FASTQ, junk before the first header, NUL bytes, truncated quality, ...)
+ * sets out->irregular = 1 and nothing else; the caller then parses that text with its serial
+ * kseq-equivalent reader (cornetto_b200/host/fastx.c) and uploads batches as before.  That is a
+ * choice of FEEDER only: the scans themselves always run on the GPU. */
+typedef struct corn_ingest {
+    corn_dbatch_t *db;          /* resident batch of the n_rec complete records (NULL when n_rec == 0);
+                                   release with corn_gpu_dbatch_free() */
+    uint32_t   n_rec;
+    uint64_t  *hdr_off;         /* [n_rec] offset in text of each record's '>' / '@' (name starts one byte later,
+                                   ends before the first isspace() byte, src/kseq.h:195) */
+    uint32_t  *length;          /* [n_rec] sequence length (kseq's seq.l) */
+    uint64_t   consumed;        /* bytes of text covered by these records; the next call starts at text + consumed */
+    int        irregular;
+    void      *_owner;
+} corn_ingest_t;
+
+int  corn_gpu_ingest(corn_ctx_t *ctx, const uint8_t *text, uint64_t n_text, int final, corn_ingest_t *out);
+/* frees hdr_off / length (NOT out->db) */
+void corn_gpu_ingest_free(corn_ingest_t *ing);
+/* page-locks a caller-owned text buffer so that corn_gpu_ingest() copies it at full PCIe rate */
+int  corn_gpu_host_register(void *p, uint64_t bytes);
+void corn_gpu_host_unregister(void *p);
+
 /* ---- measurement hooks (CUDA events on the context's stream; bench.py reads them) ---------- */
 typedef struct corn_timing {
     float h2d_ms;       /* host->device copies of the last call */

@@ -79,6 +79,90 @@ def test_reader_matches_oracle(reader_dump, oracle_bin, tmp_path):
             assert b"BADPAD" not in got and b"BADALIGN" not in got
 
 
+@pytest.fixture(scope="session")
+def ingest_sim(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("ing") / "ingest_sim")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", out, os.path.join(ROOT, "tests", "sim", "ingest_sim.cpp")])
+    return out
+
+
+INGEST_EDGE = {
+    "fq_crlf_lone.fq": b"@a\r\n\r\n+\r\n\r\n@b\nAC\n+\nII\n", "fq_trailing_blank.fq": b"@a\nAC\n+\nII\n\n\r\n",
+    "fq_short_qual.fq": b"@a\nACGT\n+\nII\nII\n@b\nA\n+\nI\n", "fq_long_qual.fq": b"@a\nAC\n+\nIIII\n@b\nA\n+\nI\n",
+    "fq_multiline.fq": b"@a\nAC\nGT\n+\nII\nII\n@b\nA\n+\nI\n", "fq_empty_seq.fq": b"@a\n\n+\n\n@b\nA\n+\nI\n",
+    "fq_gt_seq.fq": b"@a\n>CGT\n+\nIIII\n", "fa_at_line.fa": b">a\nAC\n@b\nGG\n>c\nT\n", "fa_gt_eof.fa": b">a\nAC\n>",
+    "fa_gt_eof_nl.fa": b">a\nAC\n>\n", "fa_nul.fa": b">a\nAC\x00GT\n>b\nAA\n", "fa_blank_lines.fa": b">a\n\nAC\n\n\nGT\n\n>b\n\n",
+    "fa_crlf.fa": b">a x\r\nACGT\r\nAC\r\n>b\r\nT\r\n", "fa_no_final_nl.fa": b">a\nACGT\nAC", "fa_ws_name.fa": b">a\tb c\nAC\n>\nGG\n> x\nTT\n",
+    "fa_inner_cr.fa": b">a\nA\rC\nG\r\r\n", "fq_no_final_nl.fq": b"@a\nAC\n+\nII", "fq_hdr_only.fq": b"@a", "fa_long_line.fa": b">a\n" + b"ACGT" * 700 + b"\n>b\n" + b"T" * 33 + b"\n",
+}
+
+
+def test_ingest_rules_match_oracle(ingest_sim, oracle_bin, tmp_path):
+    """The device parser's line rules (ingest_core.cuh, walked on the CPU): whatever they accept must be
+    parsed exactly as the oracle's kseq restatement does, also across block seams, and text they reject
+    must be rejected at a record boundary from which the serial reader reproduces the rest."""
+    cases = {k: c["input"] for k, c in golden_util.load().items()}
+    cases.update(EDGE_FILES)
+    cases.update(INGEST_EDGE)
+    must_be_regular = {"asm_small.fa", "q1_ends.fa", "q2_case.fa", "q3_adjacent.fa", "q4_crlf.fa", "q4_single.fq", "q5_winsizes.fa",
+                       "q6_sdust.fa", "reads_small.fq"} | {"win.fq", "fq_at_in_qual.fq", "fa_crlf.fa", "fa_blank_lines.fa",
+                                                                        "fa_no_final_nl.fa", "fa_ws_name.fa", "fa_inner_cr.fa",
+                                                                        "fq_no_final_nl.fq", "fq_trailing_blank.fq", "fa_long_line.fa"}
+    n_regular = 0
+    for name, data in cases.items():
+        p = write(str(tmp_path / name), data)
+        want = oracle_records(p)
+        for block in (48, 200, 4096, 1 << 30):
+            got, _, _ = run([ingest_sim, p, str(block)])
+            lines = got.split(b"\n")
+            if len(lines) >= 2 and lines[-2].startswith(b"IRREGULAR\t"):
+                off = int(lines[-2].split(b"\t")[1])
+                head = b"\n".join(lines[:-2]) + (b"\n" if len(lines) > 2 else b"")
+                rest = oracle_records(write(str(tmp_path / (name + ".rest")), data[off:]))
+                assert head + rest == want, (name, block, off)
+                assert not (block == 1 << 30 and name in must_be_regular), name
+            else:
+                assert got == want, (name, block)
+                n_regular += 1
+    assert n_regular > 40
+
+
+def test_ingest_rules_fuzz(ingest_sim, oracle_bin, tmp_path):
+    """Random line soups over the alphabet that matters to kseq ('>', '@', '+', CR, blank lines, NUL):
+    accepted text parses like the oracle, rejected text is rejected at a valid resume point."""
+    rng = np.random.default_rng(11)
+    atoms = [b"ACGT", b"AC", b"A", b"", b"\r", b">", b"@", b"+", b">n1 c", b"@n2", b"+n2", b"IIII", b"II", b"AC\r", b"ACGT\r", b"\x00", b"A C"]
+    weights = np.array([8, 6, 3, 2, 1, 1, 1, 2, 4, 4, 2, 6, 4, 3, 3, 0.3, 1], dtype=float)
+    weights /= weights.sum()
+    n_irregular = n_regular = 0
+    for it in range(300):
+        n_lines = int(rng.integers(1, 14))
+        first = [b">x", b"@x", b">x y", b"@x y"][int(rng.integers(0, 4))] if rng.random() < 0.9 else b"junk"
+        lines = [first] + [atoms[int(rng.choice(len(atoms), p=weights))] for _ in range(n_lines)]
+        if rng.random() < 0.5:      # bias towards well-formed four-line groups
+            lines = []
+            for r in range(int(rng.integers(1, 5))):
+                s = atoms[int(rng.choice(len(atoms), p=weights))]
+                q = b"I" * len(s.rstrip(b"\r")) if rng.random() < 0.8 else atoms[int(rng.choice(len(atoms), p=weights))]
+                lines += [b"@r%d" % r, s, b"+", q]
+        data = b"\n".join(lines) + (b"\n" if rng.random() < 0.7 else b"")
+        p = write(str(tmp_path / "fz"), data)
+        want = oracle_records(p)
+        for block in (24, 1 << 20):
+            got, _, _ = run([ingest_sim, p, str(block)])
+            out = got.split(b"\n")
+            if len(out) >= 2 and out[-2].startswith(b"IRREGULAR\t"):
+                off = int(out[-2].split(b"\t")[1])
+                head = b"\n".join(out[:-2]) + (b"\n" if len(out) > 2 else b"")
+                rest = oracle_records(write(str(tmp_path / "fz.rest"), data[off:]))
+                assert head + rest == want, (data, block, off)
+                n_irregular += 1
+            else:
+                assert got == want, (data, block)
+                n_regular += 1
+    assert n_regular > 100 and n_irregular > 100
+
+
 def test_telobreaks_and_fa2bed_match_golden(built, tmp_path):
     for name, c in golden_util.load().items():
         fa = write(str(tmp_path / name), c["input"])
