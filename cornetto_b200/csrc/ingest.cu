@@ -132,6 +132,7 @@ struct CopyParams {
     uint32_t total_bytes;
     uint8_t *dst;
     uint32_t *flags;               // [0] |= 1 on a NUL byte inside a record
+    const uint32_t *tile_rec, *tile_line;   // [n_tiles + 1]: search results at the start of every 4 KiB output tile
 };
 
 // upper bound in a[lo, hi): first index with a[i] > x
@@ -145,14 +146,40 @@ __device__ __forceinline__ uint32_t ub_range(const uint32_t *__restrict__ a, uin
 }
 
 // The chunk positions of a warp ascend with the lane, so do the answers: the two end lanes search
-// the whole table, everybody else only between their results.
-__device__ __forceinline__ uint32_t ub_warp(const uint32_t *__restrict__ a, uint32_t n, uint32_t x, int lane)
+// the range [lo, hi] their 4 KiB tile is known to fall into (k_ing_tile_index), everybody else only
+// between their results.
+__device__ __forceinline__ uint32_t ub_warp(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi, uint32_t x, int lane)
 {
     uint32_t res = 0;
-    if (lane == 0 || lane == 31) res = ub_range(a, 0, n, x);
-    const uint32_t lo = __shfl_sync(0xffffffffu, res, 0), hi = __shfl_sync(0xffffffffu, res, 31);
-    if (lane != 0 && lane != 31) res = lo == hi ? lo : ub_range(a, lo, hi, x);
+    if (lane == 0 || lane == 31) res = ub_range(a, lo, hi, x);
+    const uint32_t l2 = __shfl_sync(0xffffffffu, res, 0), h2 = __shfl_sync(0xffffffffu, res, 31);
+    if (lane != 0 && lane != 31) res = l2 == h2 ? l2 : ub_range(a, l2, h2, x);
     return res;
+}
+
+// where a chunk's bytes come from: (record, position in cum[] units).  Padding chunks point at the last
+// byte of their record (any valid position keeps the searches monotone).
+__device__ __forceinline__ uint32_t chunk_g(const CopyParams &P, uint32_t r, uint32_t o, uint32_t *want)
+{
+    const uint32_t q = o - __ldg(P.rec_off + r), len = __ldg(P.rec_len + r);
+    *want = q < len ? min(16u, len - q) : 0u;
+    return __ldg(P.g0 + r) + (*want ? q : (len ? len - 1u : 0u));
+}
+
+// one full-table search per 4 KiB of output instead of two per warp: the copy kernel's searches then
+// stay inside a few cache lines
+__global__ void __launch_bounds__(256) k_ing_tile_index(const CopyParams P, uint32_t n_tiles, uint32_t *__restrict__ tile_rec,
+                                                        uint32_t *__restrict__ tile_line)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    if (t == n_tiles) { tile_rec[t] = P.n_rec; tile_line[t] = P.n_lines + 1u; return; }
+    const uint32_t o = t << 12;
+    const uint32_t rr = ub_range(P.rec_off, 0, P.n_rec + 1u, o);
+    uint32_t want;
+    const uint32_t g = chunk_g(P, rr - 1u, o, &want);
+    tile_rec[t] = rr;
+    tile_line[t] = ub_range(P.cum, 0, P.n_lines + 1u, g);
 }
 
 // 16 text bytes from an arbitrary address (4-byte aligned loads + byte funnel)
@@ -177,28 +204,39 @@ __global__ void __launch_bounds__(256) k_ing_copy(const CopyParams P)
     const bool live = c_raw < n_chunks;
     const uint32_t c = live ? c_raw : n_chunks - 1u;       // idle lanes shadow the last chunk (keeps the searches monotone)
     const uint32_t o = c << 4;
-    const uint32_t r = ub_warp(P.rec_off, P.n_rec + 1u, o, lane) - 1u;
-    const uint32_t q = o - __ldg(P.rec_off + r), len = __ldg(P.rec_len + r);
-    const uint32_t want = q < len ? min(16u, len - q) : 0u;
-    // chunks of padding search for the last byte of their record instead (any valid position will do)
-    uint32_t g = __ldg(P.g0 + r) + (want ? q : (len ? len - 1u : 0u));
-    uint32_t k = ub_warp(P.cum, P.n_lines + 1u, g, lane) - 1u;
+    const uint32_t tile = blockIdx.x;                      // 256 threads x 16 B = one 4 KiB tile per block
+    const uint32_t r = ub_warp(P.rec_off, __ldg(P.tile_rec + tile), __ldg(P.tile_rec + tile + 1), o, lane) - 1u;
+    uint32_t want;
+    uint32_t g = chunk_g(P, r, o, &want);
+    uint32_t k = ub_warp(P.cum, __ldg(P.tile_line + tile), __ldg(P.tile_line + tile + 1), g, lane) - 1u;
     uint32_t out[4] = { 0u, 0u, 0u, 0u };
     if (want) {
         uint32_t line_end_g = __ldg(P.cum + k + 1);
         uint32_t src = (k ? __ldg(P.nl + k - 1) + 1u : 0u) + (g - __ldg(P.cum + k));
-        if (line_end_g - g >= want) {                      // the common case: one source line
-            const uint4 v = load16_unaligned(P.text + src);
-            out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
-        } else {
+        // One or two source lines (every chunk of ordinary 60/80-column text): branch-free.  The second
+        // line's bytes are fetched from (its start - take), so that they already sit at byte positions
+        // >= take of the vector; a byte mask merges the two.
+        const uint32_t take = min(want, line_end_g - g);
+        const uint32_t next_len = take < want ? __ldg(P.cum + k + 2) - line_end_g : 0u;   // (cum has n_lines + 1 entries and g + want <= total)
+        if (take == want || next_len >= want - take) {
+            const uint32_t src_b = take < want ? __ldg(P.nl + k) + 1u - take : src;
+            const uint4 a = load16_unaligned(P.text + src), b = load16_unaligned(P.text + src_b);
+            const uint32_t av[4] = { a.x, a.y, a.z, a.w }, bv[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int keep = (int)take - 4 * w;        // bytes of this word that come from the first line
+                const uint32_t m = keep >= 4 ? 0xFFFFFFFFu : (keep <= 0 ? 0u : (1u << (8 * keep)) - 1u);
+                out[w] = (av[w] & m) | (bv[w] & ~m);
+            }
+        } else {                                            // three or more lines (lines shorter than 16 bytes, blank lines)
             uint32_t filled = 0;
             for (;;) {
-                const uint32_t take = min(want - filled, line_end_g - g);
-                for (uint32_t i = 0; i < take; ++i) {
+                const uint32_t tk = min(want - filled, line_end_g - g);
+                for (uint32_t i = 0; i < tk; ++i) {
                     const uint32_t b = __ldg(P.text + src + i), at = filled + i;
                     out[at >> 2] |= b << (8u * (at & 3u));
                 }
-                filled += take; g += take;
+                filled += tk; g += tk;
                 if (filled >= want) break;
                 ++k;                                        // next line (empty ones and headers contribute nothing)
                 while (__ldg(P.cum + k + 1) == g) ++k;
@@ -378,8 +416,13 @@ static int ingest_run(corn_ctx *ctx, const uint8_t *text, uint64_t n_text, int f
     cp.total_bytes = (uint32_t)db->total_bytes; cp.dst = db->d_seq; cp.flags = d_small + 4;
     const uint32_t n_chunks = cp.total_bytes >> 4;
     if (n_chunks) {
-        k_ing_copy<<<(n_chunks + 255) / 256, 256, 0, st>>>(cp);
-        corn_count_launch(ctx);
+        const uint32_t n_otiles = (n_chunks + 255) / 256;
+        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->ing_tab, sizeof(uint32_t) * 2 * ((size_t)n_otiles + 1)));   // (the newline tile counts are no longer needed)
+        uint32_t *tile_rec = (uint32_t *)ctx->ing_tab.p, *tile_line = tile_rec + n_otiles + 1;
+        cp.tile_rec = tile_rec; cp.tile_line = tile_line;
+        k_ing_tile_index<<<(n_otiles + 1 + 255) / 256, 256, 0, st>>>(cp, n_otiles, tile_rec, tile_line);
+        k_ing_copy<<<n_otiles, 256, 0, st>>>(cp);
+        corn_count_launch(ctx, 2);
         CORN_LAUNCH_CHECK(ctx);
     }
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
