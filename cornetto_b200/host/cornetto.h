@@ -40,6 +40,8 @@ long   peakrss(void);
 /* GPU context shared by the sub-commands: created on first use; exits with the reference's
  * ERROR style when no device is usable (there is no CPU fallback). */
 corn_ctx_t *cornetto_gpu(void);
+/* starts creating that context on a helper thread (cornetto_gpu() then waits for it); failures surface in cornetto_gpu() */
+void        cornetto_gpu_prefetch(void);
 void        cornetto_gpu_release(void);
 /* prints the library error and exits */
 void        cornetto_gpu_die(const char *what, int status);

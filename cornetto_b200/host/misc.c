@@ -1,5 +1,6 @@
 /* cornetto_b200/host/misc.c -- timing helpers for the stderr footer (reference: src/misc.c:48-70),
  * the shared GPU context, and buffered text output. */
+#include <pthread.h>
 #include <sys/resource.h>
 #include <sys/stat.h>
 #include <sys/time.h>
@@ -35,8 +36,30 @@ void cornetto_gpu_die(const char *what, int status)
     exit(EXIT_FAILURE);
 }
 
+/* CUDA start-up takes 0.4-2.5 s: commands that first parse text start it on a helper thread */
+static pthread_t g_init_thread;
+static int g_init_started, g_init_status;
+
+static void *gpu_init_main(void *arg)
+{
+    (void)arg;
+    g_init_status = corn_gpu_init(-1, &g_ctx);
+    return NULL;
+}
+
+void cornetto_gpu_prefetch(void)
+{
+    if (g_ctx || g_init_started) return;
+    if (pthread_create(&g_init_thread, NULL, gpu_init_main, NULL) == 0) g_init_started = 1;
+}
+
 corn_ctx_t *cornetto_gpu(void)
 {
+    if (g_init_started) {
+        pthread_join(g_init_thread, NULL);
+        g_init_started = 0;
+        if (g_init_status != CORN_OK) { g_ctx = NULL; cornetto_gpu_die("cannot initialise the GPU", g_init_status); }
+    }
     if (!g_ctx) {
         int r = corn_gpu_init(-1, &g_ctx);
         if (r != CORN_OK) cornetto_gpu_die("cannot initialise the GPU", r);
@@ -52,6 +75,7 @@ int cornetto_fast_exit(void)
 
 void cornetto_gpu_release(void)
 {
+    if (g_init_started) { pthread_join(g_init_thread, NULL); g_init_started = 0; }
     if (g_ctx) corn_gpu_destroy(g_ctx);
     g_ctx = NULL;
 }

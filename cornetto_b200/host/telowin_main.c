@@ -46,6 +46,7 @@ int telomere_windows_main(int argc, char *argv[])
 
     FILE *fp = fopen(input_file, "r");
     CORN_F_CHK(fp, input_file);
+    cornetto_gpu_prefetch();                 /* the driver starts up while the text is parsed */
 
     /* scaffolds in file order (a name that comes back later is a new scaffold, as in the reference) */
     char **names = NULL;
