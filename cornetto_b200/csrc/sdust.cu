@@ -21,11 +21,32 @@ __global__ void k_sdust_nchunks(const uint32_t *__restrict__ rec_len, uint32_t *
     if (r < n_rec) nch[r] = (rec_len[r] + C - 1) / C;
 }
 
+// seq_nt4_table (sdust_core.cuh: sd_nt4) for four bytes at once: 2-bit codes in bits 0..7, validity in
+// bits 0..3 of *valid4.  Letters: bits 2..1 of the byte give A 0, C 1, T 2, G 3; the byte must then equal
+// that letter once its case bit is cleared; Gray-decoding the index gives A 0, C 1, G 2, T 3.  Bytes
+// 0..3 are their own code.
+__device__ __forceinline__ uint32_t nt4x4(uint32_t w, uint32_t *valid4)
+{
+    const uint32_t g = (w >> 1) & 0x03030303u;
+    uint32_t sel = (g | (g >> 4)) & 0x00FF00FFu;
+    sel = (sel | (sel >> 8)) & 0xFFFFu;                         // one selector nibble per byte
+    const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);   // 'A','C','T','G' by index
+    const uint32_t is_letter = __vcmpeq4(w & 0xDFDFDFDFu, expect);
+    const uint32_t is_low = __vcmpltu4(w, 0x04040404u);
+    const uint32_t code = (is_letter & (g ^ ((g >> 1) & 0x01010101u))) | (is_low & w & 0x03030303u);
+    uint32_t p = (code | (code >> 6)) & 0x000F000Fu;
+    p = (p | (p >> 12)) & 0xFFu;                                // c0 | c1 << 2 | c2 << 4 | c3 << 6
+    *valid4 = (((is_letter | is_low) & 0x01010101u) * 0x01020408u) >> 24;
+    return p;
+}
+
 // byte stream over one record, 16 bytes per global load
 struct DevFetch {
     const uint8_t *seq;
     uint4 buf;
     int blk;
+    uint32_t codes, valid;          // the 16 bytes of block cblk, decoded (nt4)
+    int cblk;
     __device__ __forceinline__ uint8_t operator()(int i)
     {
         const int b = i >> 4;
@@ -35,6 +56,20 @@ struct DevFetch {
         const uint32_t k = (uint32_t)i & 15u;
         const uint32_t lo = __byte_perm(buf.x, buf.y, k & 7u), hi = __byte_perm(buf.z, buf.w, k & 7u);
         return (uint8_t)((k & 8u) ? hi : lo);
+    }
+    // sd_nt4(byte i), sixteen positions decoded per load
+    __device__ __forceinline__ int nt4(int i)
+    {
+        const int b = i >> 4;
+        if (b != cblk) {
+            const uint4 v = __ldg((const uint4 *)(seq + ((size_t)b << 4)));
+            uint32_t v0, v1, v2, v3;
+            codes = nt4x4(v.x, &v0) | (nt4x4(v.y, &v1) << 8) | (nt4x4(v.z, &v2) << 16) | (nt4x4(v.w, &v3) << 24);
+            valid = v0 | (v1 << 4) | (v2 << 8) | (v3 << 12);
+            cblk = b;
+        }
+        const uint32_t k = (uint32_t)i & 15u;
+        return ((valid >> k) & 1u) ? (int)((codes >> (2u * k)) & 3u) : 4;
     }
 };
 
@@ -227,7 +262,10 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
         }
         fresh += __popc(__ballot_sync(FULL, ins));
     }
-    if (lane == leader) s.nslot += (int)fresh;
+    if (lane == leader && fresh) {
+        if (s.nslot == 0) sd_anchor_pstart(s, start, base);      // first slot after a stretch without any
+        s.nslot += (int)fresh;
+    }
     __syncwarp();
 }
 
@@ -247,7 +285,7 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
     // warp with 32 of them as the kernel's tail.
     const uint32_t j = (uint32_t)lane * n_warps + warp_id;
     const bool have = j < P.n_chunks;                 // lanes without a chunk still serve the warp's cooperative calls
-    const int T = P.T, W = P.W;
+    const int T = P.T, W = P.W, cv_max = (P.T << 1) / 10;
     uint32_t *my_slots = P.gslots + (size_t)(have ? j : 0) * lay.slot_words;
     const sd_mem m = sd_mem_of(smem, lay, threadIdx.x, my_slots);
 
@@ -264,8 +302,9 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
     sd_sink_init(sink, P.slots + (size_t)(have ? j : 0) * P.cap, P.cap);
     DevFetch fetch;
     fetch.seq = P.seq + (have ? P.rec_off[rec] : 0);
-    fetch.blk = -1;
+    fetch.blk = -1; fetch.cblk = -1;
     fetch.buf = make_uint4(0, 0, 0, 0);
+    fetch.codes = 0; fetch.valid = 0;
 
     sd_state s;
     sd_reset_counters(s, m);                          // (the slot rows were zeroed by a memset before the launch)
@@ -286,14 +325,14 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
         if (live) {
             const int i = p0 + step;
             if (i >= c0) sink.on = 1;
-            const int b = i < len ? sd_nt4(fetch(i)) : 4;
+            const int b = i < len ? fetch.nt4(i) : 4;
             if (b < 4) {
                 ++s.l;
                 s.t = (s.t << 2 | (unsigned)b) & 63u;
                 if (s.l >= 3) {
                     start = (s.l - W > 0 ? s.l - W : 0) + (i + 1 - s.l);
                     sd_save(s, m, sink, start, W);
-                    need_pop = sd_shift_window_push(s, m, (int)s.t, T, W);
+                    need_pop = sd_shift_window_push(s, m, (int)s.t, cv_max, W);
                     emit = true;
                 }
             } else {

@@ -149,7 +149,8 @@ SD_HD int sd_ring_idx(const sd_state &s, int i, int W)
 // shift_window(): sdust.c:66-86, in two halves so that the device can run the second one
 // (a data-dependent loop) cooperatively.  _push does everything up to and including the counter
 // updates for the new triplet and reports whether the suffix v must shrink; _pop is that loop.
-SD_HD bool sd_shift_window_push(sd_state &s, const sd_mem &m, int t, int T, int W)
+// cv_max = floor(2T / 10): the largest count a triplet may have inside the suffix v (:79)
+SD_HD bool sd_shift_window_push(sd_state &s, const sd_mem &m, int t, int cv_max, int W)
 {
     if (s.wn >= W - 2) {
         const int x = SD_RING(s.whead);
@@ -174,7 +175,7 @@ SD_HD bool sd_shift_window_push(sd_state &s, const sd_mem &m, int t, int T, int 
     const int d = SD_U8(m.cv, t);
     s.rv += d;
     SD_U8(m.cv, t) = (uint8_t)(d + 1);
-    return (d + 1) * 10 > T << 1;
+    return d + 1 > cv_max;                           // (d + 1) * 10 > 2 * T
 }
 
 SD_HD void sd_shift_window_pop(sd_state &s, const sd_mem &m, int t, int W)
@@ -191,32 +192,31 @@ SD_HD void sd_shift_window_pop(sd_state &s, const sd_mem &m, int t, int W)
 
 SD_HD void sd_shift_window(sd_state &s, const sd_mem &m, int t, int T, int W)
 {
-    if (sd_shift_window_push(s, m, t, T, W)) sd_shift_window_pop(s, m, t, W);
+    if (sd_shift_window_push(s, m, t, (T << 1) / 10, W)) sd_shift_window_pop(s, m, t, W);
 }
 
 // save_masked_regions(): sdust.c:88-102.  If the smallest start is below `start`, that ONE slot
 // is saved and every slot below `start` is dropped -- including, when `start` advanced by more
 // than one (it does by two at a flush with l >= W), slots that were never saved.  That loss is
 // reference behaviour and is reproduced here.
-SD_HD void sd_set_pstart(sd_state &s, int start, int W)
+// (pstart, pslot) are only meaningful while some slot is valid: with none, they are left stale
+// (always pslot == pstart mod W) and re-anchored by the insertion that creates the first slot
+// (sd_anchor_pstart) -- the common per-base path then has nothing to maintain.
+SD_HD void sd_anchor_pstart(sd_state &s, int start, int base)
 {
-    // called only when no slot is valid: a jump of `start` (after an N) is the one place a division remains
-    const int d = start - s.pstart;
-    if (d >= 0 && d < W) { s.pslot += d; if (s.pslot >= W) s.pslot -= W; }
-    else s.pslot = (int)((uint32_t)start % (uint32_t)W);
-    s.pstart = start;
+    s.pstart = start; s.pslot = base;            // base == start mod W, computed by the caller
 }
 
 SD_HD void sd_save(sd_state &s, const sd_mem &m, sd_sink &k, int start, int W)
 {
-    if (s.nslot == 0) { if (s.pstart != start) sd_set_pstart(s, start, W); return; }
+    if (s.nslot == 0) return;
     while (s.pstart < start && !(SD_SLOT(s.pslot) & SD_SLOT_VALID)) { ++s.pstart; if (++s.pslot == W) s.pslot = 0; }
     if (s.pstart >= start) return;                       // smallest start >= start: nothing to do
     sd_sink_put(k, s.pstart, s.pstart + sd_slot_flen(SD_SLOT(s.pslot)));
     while (s.pstart < start) {
         if (SD_SLOT(s.pslot) & SD_SLOT_VALID) {
             SD_SLOT(s.pslot) = 0;
-            if (--s.nslot == 0) { sd_set_pstart(s, start, W); return; }
+            if (--s.nslot == 0) return;
         }
         ++s.pstart; if (++s.pslot == W) s.pslot = 0;
     }
@@ -266,7 +266,7 @@ SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W
         if (new_r * 10 > T * new_l) {
             if (max_r == 0 || new_r * max_l >= max_r * new_l) {
                 max_r = new_r; max_l = new_l;
-                if (!(v & SD_SLOT_VALID)) ++s.nslot;
+                if (!(v & SD_SLOT_VALID)) { if (s.nslot == 0) sd_anchor_pstart(s, start, base); ++s.nslot; }
                 SD_SLOT(si) = sd_slot_pack(new_r, new_l, s.wn + 2 - i);
             }
         }
@@ -325,7 +325,7 @@ SD_HD void sd_find_perfect_vec(sd_state &s, const sd_mem &m, int T, int start, i
             sd_fracmax(Mr, Ml, pr[i], pl[i]);
             if (nr[i] * Ml >= Mr * new_l) {
                 int si = base + i; if (si >= W) si -= W;
-                if (!sv[i]) ++s.nslot;
+                if (!sv[i]) { if (s.nslot == 0) sd_anchor_pstart(s, start, base); ++s.nslot; }
                 SD_SLOT(si) = sd_slot_pack(nr[i], new_l, wn + 2 - i);
             }
         }

@@ -204,18 +204,11 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
     }
     const uint64_t size = (uint64_t)sb.st_size;
 
-    int n_gpus = 1;
+    int n_gpus = 1;                        /* requested; clipped to the devices present once the driver is up */
     const char *e = getenv("CORNETTO_GPUS");
     if (e && atoi(e) > 0) n_gpus = atoi(e);
-    if (n_gpus > 1) {
-        const int avail = corn_gpu_device_count();
-        if (avail <= 0) {
-            CORN_ERROR("cannot initialise the GPU: %s", corn_gpu_strerror(avail < 0 ? avail : CORN_E_NOGPU));
-            exit(EXIT_FAILURE);
-        }
-        if (n_gpus > avail) n_gpus = avail;
-    }
-    const int n_workers = n_gpus > 1 ? n_gpus : 2;
+    const int n_req = n_gpus;
+    int n_workers = n_gpus > 1 ? n_gpus : 2;
     const char *dev0 = getenv("CORNETTO_GPU");
     const int base_dev = (n_gpus == 1 && dev0) ? atoi(dev0) : 0;
 
@@ -229,16 +222,22 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
     if (block > max_block) block = max_block;
     if (block < 64) block = 64;
 
+    /* Worker 0 starts the driver at once; the others are created while it works on the first block (asking
+     * for the device count first would put a second of CUDA start-up in front of everything). */
     iworker_t *w = (iworker_t *)calloc((size_t)n_workers, sizeof(iworker_t));
     CORN_MALLOC_CHK(w);
-    for (int i = 0; i < n_workers; ++i) {
-        pthread_mutex_init(&w[i].mu, NULL);
-        pthread_cond_init(&w[i].cv, NULL);
-        w[i].device = base_dev + (i % n_gpus);
-        w[i].fn = fn; w[i].arg = arg;
-        outbuf_init(&w[i].out, NULL);
-        if (pthread_create(&w[i].th, NULL, iworker_main, &w[i]) != 0) { CORN_ERROR("%s", "pthread_create failed"); exit(EXIT_FAILURE); }
+    int n_spawned = 0;
+#define SPAWN_WORKERS(upto)                                                                              \
+    for (; n_spawned < (upto); ++n_spawned) {                                                            \
+        iworker_t *nw = &w[n_spawned];                                                                   \
+        pthread_mutex_init(&nw->mu, NULL);                                                               \
+        pthread_cond_init(&nw->cv, NULL);                                                                \
+        nw->device = base_dev + (n_spawned % n_gpus);                                                    \
+        nw->fn = fn; nw->arg = arg;                                                                      \
+        outbuf_init(&nw->out, NULL);                                                                     \
+        if (pthread_create(&nw->th, NULL, iworker_main, nw) != 0) { CORN_ERROR("%s", "pthread_create failed"); exit(EXIT_FAILURE); } \
     }
+    SPAWN_WORKERS(1);
 
     int dispatched = 0, written = 0, complete = 0;
     uint64_t file_pos = 0;                 /* next byte to read from the file */
@@ -269,6 +268,19 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
         pthread_mutex_lock(&x->mu);
         x->state = 1;
         pthread_cond_broadcast(&x->cv);
+        pthread_mutex_unlock(&x->mu);
+        if (n_spawned < n_workers) {                     /* first block is on its way: bring up the rest */
+            if (n_req > 1) {
+                const int avail = corn_gpu_device_count();
+                if (avail <= 0) {
+                    CORN_ERROR("cannot initialise the GPU: %s", corn_gpu_strerror(avail < 0 ? avail : CORN_E_NOGPU));
+                    exit(EXIT_FAILURE);
+                }
+                if (n_gpus > avail) { n_gpus = avail; n_workers = n_gpus > 1 ? n_gpus : 2; }
+            }
+            SPAWN_WORKERS(n_workers);
+        }
+        pthread_mutex_lock(&x->mu);
         while (!x->ingested) pthread_cond_wait(&x->cv, &x->mu);
         pthread_mutex_unlock(&x->mu);
         ++dispatched;
@@ -284,7 +296,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
         outbuf_write(&y->out, stdout);
         TRACE("[ingest] wrote output in %.3f s\n", realtime() - t_wr);
     }
-    for (int i = 0; i < n_workers; ++i) {
+    for (int i = 0; i < n_spawned; ++i) {
         pthread_mutex_lock(&w[i].mu);
         w[i].teardown = !complete || !cornetto_fast_exit();      /* the serial reader continues: give the device memory back */
         w[i].state = 2;
