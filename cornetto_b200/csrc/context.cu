@@ -60,15 +60,17 @@ extern "C" int corn_gpu_init(int device, corn_ctx_t **out)
         device = e ? atoi(e) : 0;
     }
     if (device >= n) return CORN_E_ARG;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CORN_E_NOGPU;
-    if (prop.major < 10) return CORN_E_NOGPU;   // kernels are built for sm_100a only
+    // (attribute queries, not cudaGetDeviceProperties: that one reads every property and costs tens of ms)
+    int cc_major = 0, sm_count = 0;
+    if (cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return CORN_E_NOGPU;
+    if (cc_major < 10) return CORN_E_NOGPU;     // kernels are built for sm_100a only
     if (cudaSetDevice(device) != cudaSuccess) return CORN_E_NOGPU;
 
     corn_ctx *ctx = (corn_ctx *)calloc(1, sizeof(corn_ctx));
     if (!ctx) return CORN_E_NOMEM;
     ctx->device = device;
-    ctx->sm_count = prop.multiProcessorCount;
+    ctx->sm_count = sm_count;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return CORN_E_CUDA; }
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < 16; ++i)

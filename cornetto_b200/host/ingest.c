@@ -269,7 +269,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
         x->state = 1;
         pthread_cond_broadcast(&x->cv);
         pthread_mutex_unlock(&x->mu);
-        if (n_spawned < n_workers) {                     /* first block is on its way: bring up the rest */
+        if (n_spawned < n_workers && !x->final) {        /* first block is on its way and there is more: bring up the rest */
             if (n_req > 1) {
                 const int avail = corn_gpu_device_count();
                 if (avail <= 0) {
