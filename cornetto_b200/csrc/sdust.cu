@@ -73,6 +73,8 @@ struct DevFetch {
     }
 };
 
+#define SD_QUICK_POPS 4
+
 struct SdParams {
     const uint8_t  *seq;
     const uint32_t *rec_off, *rec_len;
@@ -341,6 +343,24 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
             }
         }
         uint32_t todo = __ballot_sync(FULL, need_pop);
+        if (todo) {
+            // Inside a tandem repeat the first element of v IS the triplet that just went over the limit, so the
+            // shrink loop (sd_shift_window_pop) ends after one pop -- at every step.  SD_QUICK_POPS pops are tried per
+            // lane, all lanes at once; only what is left (ordinary sequence needs ~10) goes to the cooperative form.
+            // Measured at 3 Gb (Gbases/s, assembly / plain): 0 -> 55.7 / 87.5, 1 -> 66.6 / 92.9, 4 -> 67.2 / 96.7, 8 -> 66.2 / 97.9.
+#pragma unroll
+            for (int q = 0; q < SD_QUICK_POPS; ++q) {
+                if (need_pop) {
+                    const int x = SD_RING(sd_ring_idx(s, s.wn - s.L, W));
+                    const int e2 = SD_U8(m.cv, x) - 1;
+                    SD_U8(m.cv, x) = (uint8_t)e2;
+                    s.rv -= e2;
+                    --s.L;
+                    need_pop = x != (int)s.t;
+                }
+            }
+            todo = __ballot_sync(FULL, need_pop);
+        }
         while (todo) {
             const int leader = __ffs(todo) - 1;
             todo &= todo - 1;
