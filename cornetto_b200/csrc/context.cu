@@ -123,7 +123,8 @@ static void stage_worker(corn_ctx *ctx, int t, uint8_t *d_dst, const uint8_t *h_
         const int slot = t * CORN_STAGE_SLOTS + (use % CORN_STAGE_SLOTS);
         uint8_t *buf = ctx->stage + (size_t)slot * CORN_STAGE_BYTES;
         const size_t off = p * CORN_STAGE_BYTES, len = bytes - off < CORN_STAGE_BYTES ? bytes - off : CORN_STAGE_BYTES;
-        cudaError_t e = use >= CORN_STAGE_SLOTS ? cudaEventSynchronize(ctx->stage_ev[slot]) : cudaSuccess;   // slot drained?
+        // slot drained?  (also covers a copy left in flight by a previous call; an event never recorded is "complete")
+        cudaError_t e = cudaEventSynchronize(ctx->stage_ev[slot]);
         if (e == cudaSuccess) {
             memcpy(buf, h_src + off, len);
             e = cudaMemcpyAsync(d_dst + off, buf, len, cudaMemcpyHostToDevice, ctx->stage_stream[t]);
