@@ -240,6 +240,28 @@ def bench_ingest(ctx, peak, mbases=800, width=60, n_rec=8):
             "bound": "PCIe (the H2D copy of the text); the device phase runs at HBM-class rates"}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Runs this rank on the CPUs of the NUMA node its GPU hangs off, so that the page-locked staging buffers of
+    the e2e leg are allocated (first touch) in memory local to the GPU's PCIe root.  Returns the node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def host_random_contig(rng, L):
     """numpy stand-in of the GPU generator for the reference arm (same composition, other bytes)."""
     s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=L, dtype=np.uint8)]
@@ -359,6 +381,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the scan path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(torch, local)
     ctx = capi.Context(local)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -448,7 +471,8 @@ def main():
             "config": {"workload": f"{args.workload}: telofind(TTAGGG)+telowin(0.4, 99.9) on a synthetic {n_bases / 1e9:.2f} Gb T2T-like haploid assembly per GPU",
                        "contigs": len(lengths), "bases_per_gpu": n_bases, "hbm_bytes_per_gpu": total_bytes,
                        "l2_policy": "input (3.1 GB) is far larger than the 126 MB L2: every step streams it from HBM",
-                       "windows_found": n_win, "parallelism": f"{world} independent shards, no collective"},
+                       "windows_found": n_win, "parallelism": f"{world} independent shards, no collective",
+                       "host_numa_node": numa_node},
             "roofline": roofline, "clocks": clk, "gpu_launches": int(launches)}
 
     if args.profile_only:
