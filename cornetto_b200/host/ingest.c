@@ -37,7 +37,8 @@ typedef struct {
     int             ingested;    /* the current block's consumed / irregular are valid */
     int             device;
     corn_ctx_t     *ctx;
-    uint8_t        *text;        /* block buffer (page-locked by the worker on first use) */
+    uint8_t        *text;        /* block buffer: [reserve for a carried tail | bytes read from the file] */
+    uint8_t        *blk;         /* where the current block starts inside it */
     uint64_t        cap, n;
     int             final, teardown;
     uint64_t        consumed;
@@ -95,7 +96,7 @@ static void *iworker_main(void *p)
          *  ring, which is faster than page-locking and releasing GBs for a buffer that is used once or twice) */
         t0 = realtime();
         corn_ingest_t ing;
-        r = corn_gpu_ingest(w->ctx, w->text, w->n, w->final, &ing);
+        r = corn_gpu_ingest(w->ctx, w->blk, w->n, w->final, &ing);
         if (g_trace) {
             corn_timing_t tm;
             corn_gpu_last_timing(w->ctx, &tm);
@@ -115,7 +116,7 @@ static void *iworker_main(void *p)
             memset(&b, 0, sizeof b);
             b.n = ing.n_rec; b.db = ing.db; b.length = ing.length;
             t0 = realtime();
-            build_names(&b, w->text, w->n, &ing);
+            build_names(&b, w->blk, w->n, &ing);
             w->fn(w->ctx, &b, &w->out, w->arg);
             TRACE("[ingest] scan + format %.3f s\n", realtime() - t0);
             free(b.name); free(b.name_arena);
@@ -239,29 +240,47 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
     }
     SPAWN_WORKERS(1);
 
+    /* A block is cut where the device says its last complete record ends, so block i+1 begins with a tail
+     * carried over from block i.  To keep the file read going while block i is being shipped and parsed, the
+     * bytes that follow block i in the file are read ahead into the NEXT worker's buffer behind a reserve of
+     * `reserve` bytes; once the tail is known it is copied in front of them.  (A tail larger than the reserve
+     * -- a record of hundreds of MB cut by a block end -- drops the read-ahead and re-reads.) */
+    const uint64_t reserve = block >= size ? 0 : (block / 4 < (256ull << 20) ? block / 4 : (256ull << 20));
     int dispatched = 0, written = 0, complete = 0;
     uint64_t file_pos = 0;                 /* next byte to read from the file */
     const uint8_t *carry = NULL;           /* unconsumed tail of the previous block (in that worker's buffer) */
     uint64_t carry_len = 0;
+    int ahead_for = -1;                    /* block index whose fresh bytes are already in its worker's buffer */
+    uint64_t ahead_bytes = 0;
     for (;;) {
         iworker_t *x = &w[dispatched % n_workers];
         wait_idle(x);
         if (dispatched - n_workers >= written) { outbuf_write(&x->out, stdout); written = dispatched - n_workers + 1; }
         if (!x->text) {
             void *p = NULL;
-            if (posix_memalign(&p, 2u << 20, block + 64) != 0) p = NULL;
+            if (posix_memalign(&p, 2u << 20, reserve + block + 64) != 0) p = NULL;
             CORN_MALLOC_CHK(p);
-            madvise(p, block + 64, MADV_HUGEPAGE);         /* fewer faults while reading, cheaper to release */
-            x->text = (uint8_t *)p; x->cap = block + 64;
+            madvise(p, reserve + block + 64, MADV_HUGEPAGE);       /* fewer faults while reading, cheaper to release */
+            x->text = (uint8_t *)p; x->cap = reserve + block + 64;
         }
         if (carry_len >= block) { *resume = file_pos - carry_len; break; }      /* (cannot happen: a block with no record ends the loop below) */
-        if (carry_len) memcpy(x->text, carry, carry_len);
-        const uint64_t want = size - file_pos < block - carry_len ? size - file_pos : block - carry_len;
-        const double t_rd = realtime();
-        const uint64_t fresh = read_block(fd, x->text + carry_len, file_pos, want);
-        TRACE("[ingest] read %.1f MB in %.3f s\n", (double)fresh / 1e6, realtime() - t_rd);
-        const uint64_t block_off = file_pos - carry_len;
-        file_pos += fresh;
+        uint64_t fresh, want;
+        if (ahead_for == dispatched && carry_len <= reserve) {                   /* read ahead: only the tail is missing */
+            x->blk = x->text + reserve - carry_len;
+            if (carry_len) memcpy(x->blk, carry, carry_len);
+            fresh = want = ahead_bytes;
+        } else {
+            if (ahead_for == dispatched) file_pos -= ahead_bytes;                /* tail too large: read again behind it */
+            x->blk = x->text;
+            if (carry_len) memcpy(x->blk, carry, carry_len);
+            want = size - file_pos < block - carry_len ? size - file_pos : block - carry_len;
+            const double t_rd = realtime();
+            fresh = read_block(fd, x->blk + carry_len, file_pos, want);
+            TRACE("[ingest] read %.1f MB in %.3f s\n", (double)fresh / 1e6, realtime() - t_rd);
+            file_pos += fresh;
+        }
+        ahead_for = -1;
+        const uint64_t block_off = file_pos - fresh - carry_len;
         x->n = carry_len + fresh;
         x->final = (fresh < want || file_pos >= size);
         x->ingested = 0;
@@ -280,12 +299,30 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
             }
             SPAWN_WORKERS(n_workers);
         }
+        if (!x->final && reserve) {                      /* read ahead for the next block while this one is shipped and parsed */
+            iworker_t *y = &w[(dispatched + 1) % n_workers];
+            wait_idle(y);
+            if (dispatched + 1 - n_workers >= written) { outbuf_write(&y->out, stdout); written = dispatched + 1 - n_workers + 1; }
+            if (!y->text) {
+                void *p = NULL;
+                if (posix_memalign(&p, 2u << 20, reserve + block + 64) != 0) p = NULL;
+                CORN_MALLOC_CHK(p);
+                madvise(p, reserve + block + 64, MADV_HUGEPAGE);
+                y->text = (uint8_t *)p; y->cap = reserve + block + 64;
+            }
+            const uint64_t w2 = size - file_pos < block - reserve ? size - file_pos : block - reserve;
+            const double t_rd = realtime();
+            ahead_bytes = read_block(fd, y->text + reserve, file_pos, w2);
+            TRACE("[ingest] read ahead %.1f MB in %.3f s\n", (double)ahead_bytes / 1e6, realtime() - t_rd);
+            file_pos += ahead_bytes;
+            ahead_for = dispatched + 1;
+        }
         pthread_mutex_lock(&x->mu);
         while (!x->ingested) pthread_cond_wait(&x->cv, &x->mu);
         pthread_mutex_unlock(&x->mu);
         ++dispatched;
         if (x->irregular || (x->consumed == 0 && !x->final)) { *resume = block_off; break; }
-        carry = x->text + x->consumed;
+        carry = x->blk + x->consumed;
         carry_len = x->n - x->consumed;
         if (x->final) { complete = 1; break; }
     }
