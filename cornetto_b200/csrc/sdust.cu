@@ -508,10 +508,14 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     CORN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
-    int C = 4096;
+    // Chunk length.  Every chunk pays ~3W warm-up positions, which favours long chunks; but the kernel cannot end
+    // before its most expensive warp-task does (one with a lane inside a tandem repeat runs 3-4x as long), which
+    // favours many short tasks when the batch is small.  Measured optimum (scripts/chunk_sweep.sh, Gbases/s):
+    // 200 Mb: 512 -> 42, 768 -> 32, 2048 -> 17;  1 Gb: 1024..1536 -> 60, 4096 -> 47;  3 Gb: 3072 -> 69, 512 -> 57.
+    int C = 3072;
     {
-        const uint64_t want = db->n_bases / ((uint64_t)ctx->sm_count * 1824u + 1);
-        if (want < 4096) C = (int)(want < 512 ? 512 : want / 64 * 64);
+        const uint64_t want = db->n_bases / 1000000u;
+        if (want < 3072) C = (int)(want < 512 ? 512 : want / 64 * 64);
     }
     if (const char *e = getenv("CORNETTO_SDUST_CHUNK")) { int v = atoi(e); if (v >= 16 && v <= (1 << 20)) C = v; }
     const uint32_t n_rec = db->n_rec;
