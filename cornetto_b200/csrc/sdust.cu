@@ -191,10 +191,14 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
 
     int c[NB];
     bool valid[NB];
+    const int nb_c = (i0 >> 5) + 1;                   // blocks that hold an index <= i0: the others contribute no c_i
+                                                      // (after a long shrink on ordinary sequence i0 < 32: half the work)
 #pragma unroll
     for (int b = 0; b < NB; ++b) {                    // ranks, ascending blocks
         const int i = 32 * b + lane;
         valid[b] = i < wn;
+        c[b] = 0;
+        if (b >= nb_c) continue;                      // (warp-uniform)
         int ri = whead + i; if (ri >= W) ri -= W;
         const int t = valid[b] ? (int)SD_RING(ri) : 64 + lane;
         const int before = valid[b] ? (int)cnt[t] : 0;
@@ -212,6 +216,8 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
     bool any_cand = false;
 #pragma unroll
     for (int b = NB - 1; b >= 0; --b) {
+        nr[b] = 0; cand[b] = false;
+        if (b >= nb_c) continue;                      // no candidate up there, nothing to add to the carry
         int x = c[b];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_down_sync(FULL, x, o); if (lane + o < 32) x += y; }
