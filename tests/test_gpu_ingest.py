@@ -109,6 +109,22 @@ def test_ingest_synthetic_assembly_and_reads(ctx):
     assert t["launches"] >= 5 and t["scan_ms"] > 0
 
 
+def test_ingest_large_pageable_text_uses_staged_copy(ctx):
+    """70 MB of text in ordinary (pageable) memory: the host->device copy goes through the library's page-locked
+    staging ring (corn_h2d) instead of one cudaMemcpyAsync; the parsed records must be the bytes that went in."""
+    rng = np.random.default_rng(41)
+    lens = [30_000_001, 25_000_000, 14_999_999, 64, 0]
+    seqs = [np.frombuffer(b"ACGTNacgt", dtype=np.uint8)[rng.integers(0, 9, size=n)] for n in lens]
+    for width in (0, 61):
+        data = synth.fasta_bytes([(f"big{i} w{width}", s) for i, s in enumerate(seqs)], width=width)
+        assert len(data) > 4 * (8 << 20)                    # above the staging threshold
+        res = ctx.ingest(np.frombuffer(data, dtype=np.uint8).copy(), final=True)     # a fresh pageable array
+        assert not res["irregular"] and [int(x) for x in res["length"]] == lens
+        for got, want in zip(res["seq"], seqs):
+            assert got == want.tobytes()
+        assert [n for n, _ in records_of(res, data)] == [b"big%d" % i for i in range(len(lens))]
+
+
 def test_ingest_feeds_resident_scans(ctx, capi):
     """The resident batch the parser leaves behind gives the same telofind / sdust results as the host-batch path."""
     recs = synth.assembly(23, [400_000, 90_000, 5_000], n_gaps=2, iupac_per_mb=20.0, p_lower=0.05)
