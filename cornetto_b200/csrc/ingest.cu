@@ -132,7 +132,7 @@ struct CopyParams {
     uint32_t total_bytes;
     uint8_t *dst;
     uint32_t *flags;               // [0] |= 1 on a NUL byte inside a record
-    const uint32_t *tile_rec, *tile_line;   // [n_tiles + 1]: search results at the start of every 4 KiB output tile
+    const uint32_t *tile_rec, *tile_line;   // [n_tiles + 1]: search results at the start of every 512 B output tile
 };
 
 // upper bound in a[lo, hi): first index with a[i] > x
@@ -145,18 +145,6 @@ __device__ __forceinline__ uint32_t ub_range(const uint32_t *__restrict__ a, uin
     return lo;
 }
 
-// The chunk positions of a warp ascend with the lane, so do the answers: the two end lanes search
-// the range [lo, hi] their 4 KiB tile is known to fall into (k_ing_tile_index), everybody else only
-// between their results.
-__device__ __forceinline__ uint32_t ub_warp(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi, uint32_t x, int lane)
-{
-    uint32_t res = 0;
-    if (lane == 0 || lane == 31) res = ub_range(a, lo, hi, x);
-    const uint32_t l2 = __shfl_sync(0xffffffffu, res, 0), h2 = __shfl_sync(0xffffffffu, res, 31);
-    if (lane != 0 && lane != 31) res = l2 == h2 ? l2 : ub_range(a, l2, h2, x);
-    return res;
-}
-
 // where a chunk's bytes come from: (record, position in cum[] units).  Padding chunks point at the last
 // byte of their record (any valid position keeps the searches monotone).
 __device__ __forceinline__ uint32_t chunk_g(const CopyParams &P, uint32_t r, uint32_t o, uint32_t *want)
@@ -166,15 +154,16 @@ __device__ __forceinline__ uint32_t chunk_g(const CopyParams &P, uint32_t r, uin
     return __ldg(P.g0 + r) + (*want ? q : (len ? len - 1u : 0u));
 }
 
-// one full-table search per 4 KiB of output instead of two per warp: the copy kernel's searches then
-// stay inside a few cache lines
+// One full-table search per 512 B of output (= per warp of the copy kernel): the per-chunk searches of that
+// kernel then run over the handful of records / lines between two consecutive index entries (positions, and
+// therefore answers, ascend with the chunk).
 __global__ void __launch_bounds__(256) k_ing_tile_index(const CopyParams P, uint32_t n_tiles, uint32_t *__restrict__ tile_rec,
                                                         uint32_t *__restrict__ tile_line)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
     if (t == n_tiles) { tile_rec[t] = P.n_rec; tile_line[t] = P.n_lines + 1u; return; }
-    const uint32_t o = t << 12;
+    const uint32_t o = t << 9;
     const uint32_t rr = ub_range(P.rec_off, 0, P.n_rec + 1u, o);
     uint32_t want;
     const uint32_t g = chunk_g(P, rr - 1u, o, &want);
@@ -204,11 +193,11 @@ __global__ void __launch_bounds__(256) k_ing_copy(const CopyParams P)
     const bool live = c_raw < n_chunks;
     const uint32_t c = live ? c_raw : n_chunks - 1u;       // idle lanes shadow the last chunk (keeps the searches monotone)
     const uint32_t o = c << 4;
-    const uint32_t tile = blockIdx.x;                      // 256 threads x 16 B = one 4 KiB tile per block
-    const uint32_t r = ub_warp(P.rec_off, __ldg(P.tile_rec + tile), __ldg(P.tile_rec + tile + 1), o, lane) - 1u;
+    const uint32_t tile = c_raw >> 5;                      // 32 lanes x 16 B = one 512 B index tile per warp
+    const uint32_t r = ub_range(P.rec_off, __ldg(P.tile_rec + tile), __ldg(P.tile_rec + tile + 1), o) - 1u;
     uint32_t want;
     uint32_t g = chunk_g(P, r, o, &want);
-    uint32_t k = ub_warp(P.cum, __ldg(P.tile_line + tile), __ldg(P.tile_line + tile + 1), g, lane) - 1u;
+    uint32_t k = ub_range(P.cum, __ldg(P.tile_line + tile), __ldg(P.tile_line + tile + 1), g) - 1u;
     uint32_t out[4] = { 0u, 0u, 0u, 0u };
     if (want) {
         uint32_t line_end_g = __ldg(P.cum + k + 1);
@@ -244,23 +233,18 @@ __global__ void __launch_bounds__(256) k_ing_copy(const CopyParams P)
                 src = __ldg(P.nl + k - 1) + 1u;
             }
         }
-        if (want < 16u) {                                   // tail of the record: zero what follows it
+        // a NUL inside the record is outside the regular subset; behind the record's last byte the chunk is zeroed
+        uint32_t z;
+        if (want == 16u) z = has_zero_byte(out[0]) | has_zero_byte(out[1]) | has_zero_byte(out[2]) | has_zero_byte(out[3]);
+        else {
+            z = 0;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
-                const int keep = (int)want - 4 * w;
-                if (keep <= 0) out[w] = 0u;
-                else if (keep < 4) out[w] &= (1u << (8 * keep)) - 1u;
+                const int keep = (int)want - 4 * w;        // bytes of this word that belong to the record
+                const uint32_t m = keep >= 4 ? 0xFFFFFFFFu : (keep <= 0 ? 0u : (1u << (8 * keep)) - 1u);
+                z |= has_zero_byte(out[w] | ~m);
+                out[w] &= m;
             }
-        }
-        // a NUL inside the record (possible only in the first `want` bytes) is outside the regular subset
-        uint32_t z = 0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const int keep = (int)want - 4 * w;
-            uint32_t v = out[w];
-            if (keep <= 0) v = 0x01010101u;
-            else if (keep < 4) v |= ~((1u << (8 * keep)) - 1u);
-            z |= has_zero_byte(v);
         }
         if (z) atomicOr(P.flags, 1u);
     }
@@ -416,12 +400,12 @@ static int ingest_run(corn_ctx *ctx, const uint8_t *text, uint64_t n_text, int f
     cp.total_bytes = (uint32_t)db->total_bytes; cp.dst = db->d_seq; cp.flags = d_small + 4;
     const uint32_t n_chunks = cp.total_bytes >> 4;
     if (n_chunks) {
-        const uint32_t n_otiles = (n_chunks + 255) / 256;
+        const uint32_t n_otiles = (n_chunks + 31) / 32;
         CORN_TRY(corn_dbuf_reserve(ctx, &ctx->ing_tab, sizeof(uint32_t) * 2 * ((size_t)n_otiles + 1)));   // (the newline tile counts are no longer needed)
         uint32_t *tile_rec = (uint32_t *)ctx->ing_tab.p, *tile_line = tile_rec + n_otiles + 1;
         cp.tile_rec = tile_rec; cp.tile_line = tile_line;
         k_ing_tile_index<<<(n_otiles + 1 + 255) / 256, 256, 0, st>>>(cp, n_otiles, tile_rec, tile_line);
-        k_ing_copy<<<n_otiles, 256, 0, st>>>(cp);
+        k_ing_copy<<<(n_chunks + 255) / 256, 256, 0, st>>>(cp);
         corn_count_launch(ctx, 2);
         CORN_LAUNCH_CHECK(ctx);
     }
