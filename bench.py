@@ -21,6 +21,11 @@ collective on the data path -- so scaling is weak and `value` is the whole-job a
   cpu_baseline   the reference's own C implementation (oracle/_ref/cornetto, compiled from the
                  unmodified sources) or the oracle port, single thread as shipped, on a bounded
                  sample of the same assembly
+  sdust          (extra) `sdust -w 64 -t 20` kernel time on the same resident assembly (BASELINE.json configs[3])
+  ingest         (extra) device-side FASTA parsing of 0.8 GB of text: PCIe copy, line tables, gather kernel
+  cli            (extra) wall clock of the drop-in `cornetto telofind` + `cornetto telowin` commands on the
+                 cpu_baseline's FASTA sample and on the whole assembly written as FASTA (parse, CUDA start-up
+                 and text output included); best of a few runs
 
 `--impl reference` times the reference's CPU implementation alone (rank 0 only) on the host cores:
 P independent processes over contig-split FASTAs, P = usable cores.
@@ -550,7 +555,7 @@ def main():
             write_fasta(fa, sample)
             tf, tw = cpu_pipeline_seconds(binary, fa, td)
             # the drop-in binary on the same file, same two commands (process start, CUDA start-up, file read,
-            # device-side parsing, scan and text output all inside the wall clock; second of two runs)
+            # device-side parsing, scan and text output all inside the wall clock)
             runs3 = [cpu_pipeline_seconds(ours, fa, td) for _ in range(3)]      # CUDA start-up of a fresh process is noisy: best of 3
             of, ow = min(r[0] for r in runs3), min(r[1] for r in runs3)
             cli = {"sample": {"bases": int(got), "telofind_s": of, "telowin_s": ow, "gbases_per_s": got / (of + ow) / 1e9,
