@@ -98,8 +98,8 @@ extern "C" void corn_gpu_destroy(corn_ctx_t *ctx)
     cudaFreeHost(ctx->h_pinned_small);
     if (ctx->stage) {
         cudaFreeHost(ctx->stage);
-        for (int i = 0; i < CORN_STAGE_THREADS; ++i) cudaStreamDestroy(ctx->stage_stream[i]);
-        for (int i = 0; i < CORN_STAGE_THREADS * CORN_STAGE_SLOTS; ++i) cudaEventDestroy(ctx->stage_ev[i]);
+        for (int i = 0; i < ctx->stage_threads; ++i) cudaStreamDestroy(ctx->stage_stream[i]);
+        for (int i = 0; i < ctx->stage_threads * CORN_STAGE_SLOTS; ++i) cudaEventDestroy(ctx->stage_ev[i]);
     }
     free(ctx);
 }
@@ -119,7 +119,7 @@ static void stage_worker(corn_ctx *ctx, int t, uint8_t *d_dst, const uint8_t *h_
     cudaSetDevice(ctx->device);
     const size_t n_piece = (bytes + CORN_STAGE_BYTES - 1) / CORN_STAGE_BYTES;
     int use = 0;
-    for (size_t p = (size_t)t; p < n_piece; p += CORN_STAGE_THREADS, ++use) {
+    for (size_t p = (size_t)t; p < n_piece; p += (size_t)ctx->stage_threads, ++use) {
         const int slot = t * CORN_STAGE_SLOTS + (use % CORN_STAGE_SLOTS);
         uint8_t *buf = ctx->stage + (size_t)slot * CORN_STAGE_BYTES;
         const size_t off = p * CORN_STAGE_BYTES, len = bytes - off < CORN_STAGE_BYTES ? bytes - off : CORN_STAGE_BYTES;
@@ -146,24 +146,28 @@ int corn_h2d(corn_ctx *ctx, void *d_dst, const void *h_src, size_t bytes)
         return CORN_OK;
     }
     if (!ctx->stage) {
-        CORN_CUDA(ctx, cudaMallocHost((void **)&ctx->stage, (size_t)CORN_STAGE_THREADS * CORN_STAGE_SLOTS * CORN_STAGE_BYTES));
-        for (int i = 0; i < CORN_STAGE_THREADS; ++i) CORN_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stage_stream[i], cudaStreamNonBlocking));
-        for (int i = 0; i < CORN_STAGE_THREADS * CORN_STAGE_SLOTS; ++i) CORN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+        int nt = 8;
+        if (const char *e = getenv("CORNETTO_STAGE_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= CORN_STAGE_THREADS) nt = v; }
+        CORN_CUDA(ctx, cudaMallocHost((void **)&ctx->stage, (size_t)nt * CORN_STAGE_SLOTS * CORN_STAGE_BYTES));
+        ctx->stage_threads = nt;
+        for (int i = 0; i < nt; ++i) CORN_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stage_stream[i], cudaStreamNonBlocking));
+        for (int i = 0; i < nt * CORN_STAGE_SLOTS; ++i) CORN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
     }
+    const int NT = ctx->stage_threads;
     // the copy streams start after whatever ctx->stream has queued so far (e.g. a kernel still reading d_dst)
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[15], ctx->stream));
-    for (int i = 0; i < CORN_STAGE_THREADS; ++i) CORN_CUDA(ctx, cudaStreamWaitEvent(ctx->stage_stream[i], ctx->ev[15], 0));
+    for (int i = 0; i < NT; ++i) CORN_CUDA(ctx, cudaStreamWaitEvent(ctx->stage_stream[i], ctx->ev[15], 0));
     cudaError_t err[CORN_STAGE_THREADS];
     std::thread th[CORN_STAGE_THREADS - 1];
-    for (int t = 0; t < CORN_STAGE_THREADS; ++t) err[t] = cudaSuccess;
-    for (int t = 1; t < CORN_STAGE_THREADS; ++t)
+    for (int t = 0; t < NT; ++t) err[t] = cudaSuccess;
+    for (int t = 1; t < NT; ++t)
         th[t - 1] = std::thread(stage_worker, ctx, t, (uint8_t *)d_dst, (const uint8_t *)h_src, bytes, &err[t]);
     stage_worker(ctx, 0, (uint8_t *)d_dst, (const uint8_t *)h_src, bytes, &err[0]);
-    for (int t = 1; t < CORN_STAGE_THREADS; ++t) th[t - 1].join();
-    for (int t = 0; t < CORN_STAGE_THREADS; ++t)
+    for (int t = 1; t < NT; ++t) th[t - 1].join();
+    for (int t = 0; t < NT; ++t)
         if (err[t] != cudaSuccess) return corn_set_err(ctx, CORN_E_CUDA, "staged host->device copy: %s", cudaGetErrorString(err[t]));
     // ... and ctx->stream continues after the last piece of every copy stream
-    for (int t = 0; t < CORN_STAGE_THREADS; ++t) {
+    for (int t = 0; t < NT; ++t) {
         CORN_CUDA(ctx, cudaEventRecord(ctx->ev[15], ctx->stage_stream[t]));
         CORN_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[15], 0));
     }

@@ -53,7 +53,7 @@ struct corn_dbuf {         // grow-only device scratch
     size_t cap;
 };
 
-#define CORN_STAGE_THREADS 8
+#define CORN_STAGE_THREADS 16     /* upper bound; ctx->stage_threads are used */
 #define CORN_STAGE_SLOTS   2
 #define CORN_STAGE_BYTES   (8u << 20)
 
@@ -108,14 +108,15 @@ struct corn_ctx {
     void     *h_pinned_small;      // 4 KiB pinned scratch for small readbacks
 
     // staging ring for host->device copies from pageable memory (corn_h2d)
-    uint8_t     *stage;            // CORN_STAGE_THREADS * CORN_STAGE_SLOTS slots of CORN_STAGE_BYTES, page-locked
+    uint8_t     *stage;            // stage_threads * CORN_STAGE_SLOTS slots of CORN_STAGE_BYTES, page-locked
+    int          stage_threads;    // host threads filling the ring (8; $CORNETTO_STAGE_THREADS)
     cudaStream_t stage_stream[CORN_STAGE_THREADS];
     cudaEvent_t  stage_ev[CORN_STAGE_THREADS * CORN_STAGE_SLOTS];
 };
 
 
 // Host->device copy ordered on ctx->stream.  Page-locked sources are copied directly; pageable ones
-// go through a small page-locked ring filled by CORN_STAGE_THREADS host threads (page-locking a
+// go through a small page-locked ring filled by ctx->stage_threads host threads (page-locking a
 // multi-GB buffer costs 0.1-0.4 s/GB and as much again to release: more than the copy itself).
 int corn_h2d(corn_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 

@@ -102,6 +102,10 @@ void outbuf_str(outbuf_t *o, const char *s, size_t len);
 void outbuf_u64(outbuf_t *o, uint64_t v);
 void outbuf_i32(outbuf_t *o, int32_t v);
 void outbuf_chr(outbuf_t *o, char c);
+/* formats items [0, n) with fn(ob, begin, end, arg) -- on several threads when there are many -- and appends
+ * the text to ob in item order */
+typedef void (*format_range_fn)(outbuf_t *ob, uint64_t begin, uint64_t end, void *arg);
+void outbuf_format_parallel(outbuf_t *ob, uint64_t n_items, format_range_fn fn, void *arg);
 
 /* ---- batch pipeline: one parser thread, one worker thread per GPU context --------------------
  * Records are parsed into pinned batches by the calling thread while worker threads run the GPU

@@ -8,6 +8,29 @@
 
 typedef struct { int T, W; } sdust_arg_t;
 
+typedef struct { const corn_intervals_t *iv; const rec_batch_t *b; } sdust_fmt_t;
+
+/* items are intervals; the record of an interval k is the r with rec_first[r] <= k < rec_first[r + 1] */
+static void sdust_format(outbuf_t *ob, uint64_t begin, uint64_t end, void *arg)
+{
+    const sdust_fmt_t *f = (const sdust_fmt_t *)arg;
+    const uint64_t *first = f->iv->rec_first;
+    if (begin >= end) return;
+    uint32_t lo = 0, hi = f->iv->n_rec;              /* last r with first[r] <= begin */
+    while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (first[mid] <= begin) lo = mid; else hi = mid; }
+    uint32_t rec = lo;
+    const char *name = NULL;
+    size_t nl = 0;
+    for (uint64_t k = begin; k < end; ++k) {
+        while (k >= first[rec + 1]) { ++rec; name = NULL; }
+        if (!name) { name = f->b->name[rec]; nl = strlen(name); }
+        outbuf_str(ob, name, nl);
+        outbuf_chr(ob, '\t'); outbuf_i32(ob, (int32_t)(f->iv->iv[k] >> 32));
+        outbuf_chr(ob, '\t'); outbuf_i32(ob, (int32_t)f->iv->iv[k]);
+        outbuf_chr(ob, '\n');
+    }
+}
+
 static void sdust_batch(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *ob, void *arg)
 {
     const sdust_arg_t *a = (const sdust_arg_t *)arg;
@@ -23,16 +46,9 @@ static void sdust_batch(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *ob, void *arg
         CORN_ERROR("sdust: %s (%s)", corn_gpu_strerror(r), corn_gpu_last_error(ctx));
         exit(EXIT_FAILURE);
     }
-    for (uint32_t rec = 0; rec < iv.n_rec; ++rec) {
-        const char *name = b->name[rec];
-        const size_t nl = strlen(name);
-        for (uint64_t k = iv.rec_first[rec]; k < iv.rec_first[rec + 1]; ++k) {
-            outbuf_str(ob, name, nl);
-            outbuf_chr(ob, '\t'); outbuf_i32(ob, (int32_t)(iv.iv[k] >> 32));
-            outbuf_chr(ob, '\t'); outbuf_i32(ob, (int32_t)iv.iv[k]);
-            outbuf_chr(ob, '\n');
-        }
-    }
+    sdust_fmt_t f;
+    f.iv = &iv; f.b = b;
+    outbuf_format_parallel(ob, iv.n_iv, sdust_format, &f);
     corn_gpu_intervals_free(&iv);
 }
 

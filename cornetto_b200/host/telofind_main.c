@@ -7,6 +7,24 @@
  * by corn_gpu_telofind() on batches of records. */
 #include "cornetto.h"
 
+typedef struct { const corn_hits_t *hits; const rec_batch_t *b; const uint32_t *length; } telofind_fmt_t;
+
+static void telofind_format(outbuf_t *ob, uint64_t begin, uint64_t end, void *arg)
+{
+    const telofind_fmt_t *f = (const telofind_fmt_t *)arg;
+    for (uint64_t i = begin; i < end; ++i) {
+        const corn_run_t *h = &f->hits->run[i];
+        const char *name = f->b->name[h->rec];
+        outbuf_str(ob, name, strlen(name));
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, f->length[h->rec]);
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->strand);
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->start);
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->end);
+        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->end - h->start);
+        outbuf_chr(ob, '\n');
+    }
+}
+
 static void telofind_batch(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *ob, void *arg)
 {
     const char *query = (const char *)arg;
@@ -23,17 +41,9 @@ static void telofind_batch(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *ob, void *
         CORN_ERROR("telofind: %s (%s)", corn_gpu_strerror(r), corn_gpu_last_error(ctx));
         exit(EXIT_FAILURE);
     }
-    for (uint64_t i = 0; i < hits.n_run; ++i) {
-        const corn_run_t *h = &hits.run[i];
-        const char *name = b->name[h->rec];
-        outbuf_str(ob, name, strlen(name));
-        outbuf_chr(ob, '\t'); outbuf_u64(ob, length[h->rec]);
-        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->strand);
-        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->start);
-        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->end);
-        outbuf_chr(ob, '\t'); outbuf_u64(ob, h->end - h->start);
-        outbuf_chr(ob, '\n');
-    }
+    telofind_fmt_t f;
+    f.hits = &hits; f.b = b; f.length = length;
+    outbuf_format_parallel(ob, hits.n_run, telofind_format, &f);
     corn_gpu_hits_free(&hits);
 }
 

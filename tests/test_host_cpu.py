@@ -163,6 +163,17 @@ def test_ingest_rules_fuzz(ingest_sim, oracle_bin, tmp_path):
     assert n_regular > 100 and n_irregular > 100
 
 
+def test_parallel_formatting_equals_serial(built, tmp_path):
+    """outbuf_format_parallel (host/misc.c): several threads, same bytes as the serial loop."""
+    exe = str(tmp_path / "format_check")
+    host = os.path.join(ROOT, "cornetto_b200", "host")
+    subprocess.check_call(["gcc", "-O2", "-std=c99", "-D_GNU_SOURCE", "-I" + INC, "-o", exe, os.path.join(ROOT, "tests", "sim", "format_check.c"),
+                           os.path.join(host, "misc.c"), "-L" + LIBDIR, "-lcorn_gpu", "-Wl,-rpath," + LIBDIR, "-lpthread", "-lm"])
+    for n in ("0", "7", "199999", "200000", "1000003"):
+        out, _, _ = run([exe, n])
+        assert out.startswith(b"OK "), (n, out)
+
+
 def test_telobreaks_and_fa2bed_match_golden(built, tmp_path):
     for name, c in golden_util.load().items():
         fa = write(str(tmp_path / name), c["input"])
