@@ -146,7 +146,7 @@ int corn_h2d(corn_ctx *ctx, void *d_dst, const void *h_src, size_t bytes)
         return CORN_OK;
     }
     if (!ctx->stage) {
-        int nt = 8;
+        int nt = 4;      // measured on the 32-vCPU VM, 3 GB: 4 threads 116-132 ms, 8: 144-158, 12: 144-192, 16: 177-212 (memory-bound)
         if (const char *e = getenv("CORNETTO_STAGE_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= CORN_STAGE_THREADS) nt = v; }
         CORN_CUDA(ctx, cudaMallocHost((void **)&ctx->stage, (size_t)nt * CORN_STAGE_SLOTS * CORN_STAGE_BYTES));
         ctx->stage_threads = nt;

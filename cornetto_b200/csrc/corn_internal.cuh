@@ -109,7 +109,7 @@ struct corn_ctx {
 
     // staging ring for host->device copies from pageable memory (corn_h2d)
     uint8_t     *stage;            // stage_threads * CORN_STAGE_SLOTS slots of CORN_STAGE_BYTES, page-locked
-    int          stage_threads;    // host threads filling the ring (8; $CORNETTO_STAGE_THREADS)
+    int          stage_threads;    // host threads filling the ring (4; $CORNETTO_STAGE_THREADS)
     cudaStream_t stage_stream[CORN_STAGE_THREADS];
     cudaEvent_t  stage_ev[CORN_STAGE_THREADS * CORN_STAGE_SLOTS];
 };
