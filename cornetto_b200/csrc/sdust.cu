@@ -212,7 +212,7 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
     // suffix sums (descending index): new_r(i) = rv + sum_{k >= i} c_k
     int nr[NB];
     bool cand[NB];
-    int carry = 0;
+    int carry = 0, fmin = 0x7fffffff;
     bool any_cand = false;
 #pragma unroll
     for (int b = NB - 1; b >= 0; --b) {
@@ -224,10 +224,18 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
         nr[b] = rv + x + carry;
         carry += __shfl_sync(FULL, x, 0);
         const int i = 32 * b + lane, new_l = wn - i - 1;
-        cand[b] = valid[b] && i <= i0 && nr[b] * 10 > T * new_l;
+        const bool eligible = valid[b] && i <= i0;
+        cand[b] = eligible && nr[b] * 10 > T * new_l;
         any_cand |= cand[b];
+        if (eligible) fmin = min(fmin, T * new_l - 10 * nr[b]);
     }
-    if (!__any_sync(FULL, any_cand)) return;          // nothing can be inserted: P is left untouched
+    if (!__any_sync(FULL, any_cand)) {                // nothing can be inserted: P is left untouched
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fmin = min(fmin, __shfl_xor_sync(FULL, fmin, o));
+        if (lane == leader) s.slack = min(fmin, 1 << 20);     // covers the following steps (sd_slack_push)
+        return;
+    }
+    if (lane == leader) sd_slack_unknown(s);
 
     // elements (existing slot, candidate) and their exclusive running maximum (descending index)
     int er[NB], el[NB], pr[NB], pl[NB], si[NB];
@@ -340,7 +348,7 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
                 if (s.l >= 3) {
                     start = (s.l - W > 0 ? s.l - W : 0) + (i + 1 - s.l);
                     sd_save(s, m, sink, start, W);
-                    need_pop = sd_shift_window_push(s, m, (int)s.t, cv_max, W);
+                    need_pop = sd_shift_window_push(s, m, (int)s.t, T, cv_max, W);
                     emit = true;
                 }
             } else {
@@ -348,6 +356,7 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
                 s.l = 0; s.t = 0;
             }
         }
+        if (need_pop) sd_slack_unknown(s);                  // L is about to shrink: new suffixes become eligible
         uint32_t todo = __ballot_sync(FULL, need_pop);
         if (todo) {
             // Inside a tandem repeat the first element of v IS the triplet that just went over the limit, so the
@@ -375,7 +384,7 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
         bool trig = false;
         if (emit && s.rw * 10 > s.L * T) {
             if (!COOP) sd_find_perfect(s, m, T, start, W);
-            else trig = s.wn - s.L - 1 >= 0;          // no index to examine otherwise
+            else trig = s.wn - s.L - 1 >= 0 && s.slack < 0;   // no index to examine / provably no candidate otherwise
         }
         todo = __ballot_sync(FULL, trig);
         while (todo) {

@@ -125,12 +125,15 @@ struct sd_state {
     int pslot;           // pstart mod W, kept incrementally (no integer division in the per-base path)
     int l;               // length of the current A/C/G/T run
     unsigned t;          // current triplet
+    int slack;           // >= 0: a lower bound of T*new_l - 10*new_r over every suffix find_perfect would examine,
+                         //       i.e. it would find no candidate and may be skipped; < 0: unknown (see sd_slack_*)
 };
 
 SD_HD void sd_reset_counters(sd_state &s, const sd_mem &m)
 {
     s.wn = s.whead = s.L = s.rw = s.rv = s.nslot = s.pstart = s.pslot = s.l = 0;
     s.t = 0;
+    s.slack = -1;
     for (int i = 0; i < 64; ++i) { SD_U8(m.cw, i) = 0; SD_U8(m.cv, i) = 0; }
 }
 
@@ -149,8 +152,26 @@ SD_HD int sd_ring_idx(const sd_state &s, int i, int W)
 // shift_window(): sdust.c:66-86, in two halves so that the device can run the second one
 // (a data-dependent loop) cooperatively.  _push does everything up to and including the counter
 // updates for the new triplet and reports whether the suffix v must shrink; _pop is that loop.
+// ---- skipping find_perfect calls that cannot find anything ------------------------------------------
+// find_perfect (:104-128) examines the window suffixes longer than L and inserts one only if
+// new_r*10 > T*new_l (:112); a call without such a candidate changes nothing.  Let
+//   f(a) = T*new_l(a) - 10*new_r(a)      for the suffix starting at window element a.
+// Pushing triplet t makes every suffix one element longer (new_l + 1) and adds to new_r the number of
+// t already in it, at most cw[t] before the push:  f'(a) >= f(a) + T - 10*cw[t].  The set of examined
+// starts only loses elements (the head that leaves the window) as long as L grows with the pushes; it
+// gains some only when the shrink loop shortens L.  So after a call that found no candidate,
+// slack = min f >= 0 is kept per chunk, updated by T - 10*cw[t] at every push, and reset to "unknown"
+// by a shrink or by a call that did find candidates; while it stays >= 0 the reference's own trigger
+// (rw*10 > L*T, :149) may fire but the call is skipped.  (Most triggers come in bursts after a shrink:
+// the first one evaluates, the following ones are usually covered.)
+#if defined(SD_SLACK_STATS)
+static unsigned long long sd_stat_eval, sd_stat_skip;     // host-only counters for tests/sim (how often the skip applies)
+#endif
+SD_HD void sd_slack_push(sd_state &s, int T, int cw_before) { if (s.slack >= 0) s.slack += T - 10 * cw_before; }
+SD_HD void sd_slack_unknown(sd_state &s) { s.slack = -1; }
+
 // cv_max = floor(2T / 10): the largest count a triplet may have inside the suffix v (:79)
-SD_HD bool sd_shift_window_push(sd_state &s, const sd_mem &m, int t, int cv_max, int W)
+SD_HD bool sd_shift_window_push(sd_state &s, const sd_mem &m, int t, int T, int cv_max, int W)
 {
     if (s.wn >= W - 2) {
         const int x = SD_RING(s.whead);
@@ -171,6 +192,7 @@ SD_HD bool sd_shift_window_push(sd_state &s, const sd_mem &m, int t, int cv_max,
     ++s.L;
     const int c = SD_U8(m.cw, t);
     s.rw += c;
+    sd_slack_push(s, T, c);
     SD_U8(m.cw, t) = (uint8_t)(c + 1);
     const int d = SD_U8(m.cv, t);
     s.rv += d;
@@ -192,7 +214,7 @@ SD_HD void sd_shift_window_pop(sd_state &s, const sd_mem &m, int t, int W)
 
 SD_HD void sd_shift_window(sd_state &s, const sd_mem &m, int t, int T, int W)
 {
-    if (sd_shift_window_push(s, m, t, (T << 1) / 10, W)) sd_shift_window_pop(s, m, t, W);
+    if (sd_shift_window_push(s, m, t, T, (T << 1) / 10, W)) { sd_shift_window_pop(s, m, t, W); sd_slack_unknown(s); }
 }
 
 // save_masked_regions(): sdust.c:88-102.  If the smallest start is below `start`, that ONE slot
@@ -308,6 +330,12 @@ SD_HD void sd_find_perfect_vec(sd_state &s, const sd_mem &m, int T, int start, i
     }
     int acc = 0;
     for (int i = wn - 1; i >= 0; --i) { acc += c[i]; nr[i] = s.rv + acc; }      // suffix sums
+    {
+        int fmin = 0x7fffffff;
+        for (int i = 0; i <= i0; ++i) { const int f = T * (wn - i - 1) - 10 * nr[i]; if (f < fmin) fmin = f; }
+        if (fmin >= 0) { s.slack = fmin < (1 << 20) ? fmin : (1 << 20); return; }   // no candidate: nothing to insert
+        sd_slack_unknown(s);
+    }
     for (int i = 0; i < wn; ++i) {                        // elements: slot and candidate
         int si = base + i; if (si >= W) si -= W;
         const uint32_t v = SD_SLOT(si);
@@ -346,7 +374,13 @@ SD_HD int sd_step(sd_state &s, const sd_mem &m, sd_sink &k, int i, int b, int T,
         sd_save(s, m, k, start, W);
         sd_shift_window(s, m, (int)s.t, T, W);
 #if defined(SD_USE_VEC)
-        if (s.rw * 10 > s.L * T) { if (T >= 5) sd_find_perfect_vec(s, m, T, start, W); else sd_find_perfect(s, m, T, start, W); }
+        if (s.rw * 10 > s.L * T) {
+#if defined(SD_SLACK_STATS)
+            if (T >= 5 && s.wn - s.L - 1 >= 0) { if (s.slack < 0) ++sd_stat_eval; else ++sd_stat_skip; }
+#endif
+            if (T >= 5) { if (s.slack < 0 && s.wn - s.L - 1 >= 0) sd_find_perfect_vec(s, m, T, start, W); }
+            else sd_find_perfect(s, m, T, start, W);
+        }
 #else
         if (s.rw * 10 > s.L * T) sd_find_perfect(s, m, T, start, W);
 #endif

@@ -172,6 +172,9 @@ static int sim_sdust(const char *path, int T, int W, int C)
         }
     }
     orc_free_recs(recs, n);
+#if defined(SD_SLACK_STATS)
+    fprintf(stderr, "find_perfect triggers with an index to examine: %llu evaluated, %llu skipped by the slack bound\n", sd_stat_eval, sd_stat_skip);
+#endif
     return 0;
 }
 

@@ -255,6 +255,43 @@ def test_sim_sdust_n_fuzz(sim_bin, oracle_bin, tmp_path):
                 assert a == b, (seed, opts, chunk)
 
 
+@pytest.fixture(scope="session")
+def sim_vec_bin(tmp_path_factory, oracle_bin):
+    """The simulator with the data-parallel find_perfect (what the warp-cooperative device routine evaluates) and the
+    slack bound that skips calls which cannot find a candidate."""
+    out = str(tmp_path_factory.mktemp("simv") / "sim_vec")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DSD_USE_VEC", "-DSD_SLACK_STATS", "-o", out, "-x", "c++",
+                           os.path.join(ROOT, "tests", "sim", "sim_main.cpp"), "-x", "c", os.path.join(ROOT, "oracle", "oracle.c"), "-lz", "-lm"],
+                          stderr=subprocess.DEVNULL)
+    return out
+
+
+def test_sim_sdust_vector_form_and_slack_skip(sim_vec_bin, oracle_bin, tmp_path):
+    """sd_find_perfect_vec + the slack bound (sdust_core.cuh) against the oracle: N-rich fuzz, several (T, W), chunk seams;
+    and the bound must actually skip calls on ordinary sequence."""
+    files = {}
+    for seed in range(4):
+        rng = np.random.default_rng(3000 + seed)
+        recs = []
+        for k in range(6):
+            L = int(rng.integers(100, 25000))
+            recs.append((f"v{k}", synth.make_contig(rng, L, telo=None, n_its=0, microsat_per_mb=float(rng.choice([50, 3000, 20000])),
+                                                     n_gaps=int(rng.integers(0, 30)), gap_len=(1, int(rng.choice([3, 60, 400]))),
+                                                     p_lower=0.1, iupac_per_mb=float(rng.choice([0, 2000])))))
+        files[f"vz{seed}.fa"] = synth.fasta_bytes(recs)
+    files["asm.fa"] = synth.fasta_bytes(synth.assembly(2, [150_000, 999, 7], n_gaps=4, microsat_per_mb=1500.0))
+    skipped = 0
+    for name, data in files.items():
+        p = write(str(tmp_path / name), data)
+        for opts in ([], ["-w", "32", "-t", "15"], ["-t", "5"], ["-w", "100", "-t", "25"]):
+            b, _, _ = run([oracle_bin, "sdust"] + opts + [p])
+            for chunk in ("64", "193", "4096"):
+                a, err, _ = run([sim_vec_bin, "sdust"] + opts + ["-c", chunk, p])
+                assert a == b, (name, opts, chunk)
+                skipped += int(err.split(b"evaluated,")[1].split()[0])
+    assert skipped > 1000
+
+
 def test_scan_commands_fail_loudly_without_gpu(built, tmp_path):
     import torch
     if torch.cuda.is_available():
