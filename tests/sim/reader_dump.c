@@ -7,7 +7,10 @@
 int main(int argc, char **argv)
 {
     if (argc < 3) return 2;
-    fastx_t *fx = fastx_open(argv[1]);
+    /* $READER_OFFSET: start at a byte offset that is a record boundary (what the CLI does when the device parser
+     * hands the rest of a file to the serial reader) */
+    const char *off = getenv("READER_OFFSET");
+    fastx_t *fx = off ? fastx_open_at(argv[1], (uint64_t)atoll(off)) : fastx_open(argv[1]);
     if (!fx) return 1;
     uint64_t cap = (uint64_t)atoll(argv[2]);
     rec_batch_t *b = rec_batch_create(cap, argc > 3 ? (uint32_t)atoi(argv[3]) : 1024);

@@ -174,6 +174,34 @@ def test_parallel_formatting_equals_serial(built, tmp_path):
         assert out.startswith(b"OK "), (n, out)
 
 
+def test_reader_resumes_at_record_boundaries(reader_dump, ingest_sim, oracle_bin, tmp_path):
+    """fastx_open_at(): the serial reader started where the device parser gave up (the offsets ingest_sim reports,
+    plus every header offset of a regular file) delivers what the oracle parses from that suffix of the file."""
+    cases = {k: c["input"] for k, c in golden_util.load().items() if not k.endswith(".gz")}
+    cases.update(EDGE_FILES)
+    cases.update(INGEST_EDGE)
+    n = 0
+    for name, data in cases.items():
+        p = write(str(tmp_path / name), data)
+        offsets = set()
+        for block in (48, 200, 1 << 30):
+            got, _, _ = run([ingest_sim, p, str(block)])
+            lines = got.split(b"\n")
+            if len(lines) >= 2 and lines[-2].startswith(b"IRREGULAR\t"):
+                offsets.add(int(lines[-2].split(b"\t")[1]))
+        if name in ("q3_adjacent.fa", "q4_single.fq", "fa_crlf.fa"):          # regular files: every line-initial header byte
+            offsets.update(i for i in range(len(data)) if data[i:i + 1] in (b">", b"@") and (i == 0 or data[i - 1:i] == b"\n")
+                           and (name.endswith(".fa") or data[i:i + 2] in (b"@s", b"@r")))
+        for off in sorted(offsets):
+            if off == 0:
+                continue
+            want = oracle_records(write(str(tmp_path / (name + ".rest")), data[off:]))
+            got, _, _ = run([reader_dump, p, "4096"], env=dict(os.environ, READER_OFFSET=str(off)))
+            assert got == want, (name, off)
+            n += 1
+    assert n >= 5
+
+
 def test_telobreaks_and_fa2bed_match_golden(built, tmp_path):
     for name, c in golden_util.load().items():
         fa = write(str(tmp_path / name), c["input"])
