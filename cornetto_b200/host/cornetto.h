@@ -30,6 +30,8 @@ int telomere_windows_main(int argc, char *argv[]);
 int telomere_breaks_main(int argc, char *argv[]);
 int sdust_main(int argc, char *argv[]);
 int assbed_main(int argc, char *argv[]);
+int nx_main(int argc, char *argv[]);
+int report_main(int argc, char *argv[]);
 
 /* misc.c */
 uint64_t cornetto_batch_capacity(const char *path, int n_parts);

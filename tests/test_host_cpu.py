@@ -202,6 +202,31 @@ def test_reader_resumes_at_record_boundaries(reader_dump, ingest_sim, oracle_bin
     assert n >= 5
 
 
+def test_nx_and_report_match_reference(built, ref_bin, tmp_path):
+    """`cornetto nx` / `cornetto report` (host-only by-products of the reader) against the compiled
+    reference: stdout byte for byte, exit codes, usage text; FASTA, FASTQ, gzip, options before and after the file."""
+    paths = []
+    for name, c in golden_util.load().items():
+        if name in ("q4_trunc.fq",):          # (the reference's live assert aborts on nothing here, but keep to well-formed files)
+            continue
+        paths.append(write(str(tmp_path / name), c["input"]))
+    big = write(str(tmp_path / "many.fa"), synth.fasta_bytes(synth.assembly(8, [5000, 1, 777, 120_000, 120_000, 31, 64_000, 9], telo=None)))
+    paths.append(big)
+    for p in paths:
+        for args in (["nx", p], ["nx", "-g", "1.5M", p], ["nx", p, "-g", "250k"], ["nx", "--genome-size", "3G", p], ["report", p]):
+            want = run([ref_bin] + args, check=False)
+            got = run([BIN] + args, check=False)
+            assert got[0] == want[0] and got[2] == want[2], (args, got[0][:200], want[0][:200])
+    for args in (["report"] + paths[:4], ["report", big, paths[0]]):
+        want, got = run([ref_bin] + args, check=False), run([BIN] + args, check=False)
+        assert got[0] == want[0] and got[2] == want[2], args
+    for args in (["nx"], ["nx", "-h"], ["report"], ["report", "-h"], ["nx", paths[0], paths[1]], ["nx", "-x", paths[0]]):
+        want, got = run([ref_bin] + args, check=False), run([BIN] + args, check=False)
+        assert got[0] == want[0] and got[2] == want[2], args
+        strip = lambda e: b"\n".join(l for l in e.split(b"\n") if not l.startswith(b"[main"))       # (footer: timings differ)
+        assert strip(got[1]) == strip(want[1]), args
+
+
 def test_telobreaks_and_fa2bed_match_golden(built, tmp_path):
     for name, c in golden_util.load().items():
         fa = write(str(tmp_path / name), c["input"])
