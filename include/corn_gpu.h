@@ -75,7 +75,9 @@ typedef struct corn_batch {
  * kstring_t buffer that kseq_read() grows with realloc (src/kseq.h:201-211).
  * corn_hbatch_create() touches no CUDA API, so parsing can start while the driver is still
  * initialising on another thread; corn_hbatch_pin() page-locks the buffer (cudaHostRegister, once;
- * needs a device) so that the H2D copy runs at full PCIe rate. */
+ * needs a device) so that the H2D copy runs at full PCIe rate.  Without it the library copies
+ * through its own small page-locked ring (~25 GB/s), which is the better deal for a buffer that is
+ * filled only once or twice: page-locking costs 0.1-0.4 s per GB and as much again to release. */
 typedef struct corn_hbatch corn_hbatch_t;
 int      corn_hbatch_create(uint64_t capacity_bytes, uint32_t max_records, corn_hbatch_t **hb);
 int      corn_hbatch_pin(corn_hbatch_t *hb);
