@@ -32,6 +32,7 @@ int sdust_main(int argc, char *argv[]);
 int assbed_main(int argc, char *argv[]);
 int nx_main(int argc, char *argv[]);
 int report_main(int argc, char *argv[]);
+int seq_main(int argc, char *argv[]);
 
 /* misc.c */
 uint64_t cornetto_batch_capacity(const char *path, int n_parts);

@@ -20,6 +20,7 @@ static int print_usage(FILE *fp)
     fprintf(fp, "       fa2bed          create a bed file with assembly contig lengths\n");
     fprintf(fp, "       nx              nx or ngx plot tables\n");
     fprintf(fp, "       report          generate a report table for one or more assemblies\n");
+    fprintf(fp, "       seq             print reads longer than a minimum length\n");
     fprintf(fp, "\n");
     fprintf(fp, "       --help, -h      print this help message\n");
     fprintf(fp, "       --version, -V   print version information\n");
@@ -39,6 +40,7 @@ int main(int argc, char *argv[])
     else if (strcmp(argv[1], "fa2bed") == 0) ret = assbed_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "nx") == 0) ret = nx_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "report") == 0) ret = report_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "seq") == 0) ret = seq_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "--version") == 0 || strcmp(argv[1], "-V") == 0) {
         fprintf(stdout, "cornetto %s\n", CORNETTO_VERSION);
         exit(EXIT_SUCCESS);

@@ -227,6 +227,28 @@ def test_nx_and_report_match_reference(built, ref_bin, tmp_path):
         assert strip(got[1]) == strip(want[1]), args
 
 
+def test_seq_matches_reference(built, ref_bin, tmp_path):
+    """`cornetto seq` (read-length filter, host only) against the compiled reference: stdout, the totals on stderr and
+    exit codes; FASTQ with comments / CRLF / multi-line records, FASTA (no quality: the reference prints what its
+    quality buffer held before), gzip, option errors."""
+    strip = lambda e: b"\n".join(l for l in e.split(b"\n") if not l.startswith(b"[main"))           # (footer: timings differ)
+    files = {k: c["input"] for k, c in golden_util.load().items()}
+    files.update({k: v for k, v in EDGE_FILES.items() if k not in ("empty.fa",)})
+    files.update({k: v for k, v in INGEST_EDGE.items() if k != "fa_nul.fa"})                            # (NUL: the reference's assert aborts)
+    files["mixed.fq"] = b"@a c1 c2\nACGTACGT\n+\nIIIIIIII\n>b fasta in between\nACGTAC\nGT\n@c\tx\r\nACGTACGTAC\r\n+\r\nJJJJJJJJJJ\r\n"
+    for name, data in files.items():
+        p = write(str(tmp_path / name), data)
+        for m in ("0", "7", "9", "30", "100000"):
+            want = run([ref_bin, "seq", "-m", m, p], check=False)
+            got = run([BIN, "seq", "-m", m, p], check=False)
+            assert got[0] == want[0] and got[2] == want[2] and strip(got[1]) == strip(want[1]), (name, m)
+    p = write(str(tmp_path / "r.fq"), files["reads_small.fq"])
+    for args in (["seq"], ["seq", "-h"], ["seq", p], ["seq", p, "-m", "500"], ["seq", "-m", "-3", p], ["seq", "-x", p], ["seq", "--verbose", "2", p],
+                 ["seq", "--min-len", "1000", p], ["seq", p, p]):
+        want, got = run([ref_bin] + args, check=False), run([BIN] + args, check=False)
+        assert got[0] == want[0] and got[2] == want[2] and strip(got[1]) == strip(want[1]), args
+
+
 def test_telobreaks_and_fa2bed_match_golden(built, tmp_path):
     for name, c in golden_util.load().items():
         fa = write(str(tmp_path / name), c["input"])
