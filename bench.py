@@ -283,7 +283,10 @@ def run_reference_arm(args):
         return 0
     binary, kind = ref_binary()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    scale = 4                                    # bounded sample: the c2 contig set at 1/4 length (779 Mb)
+    scale = 4                                    # bounded sample: the c2 contig set at 1/4 length (779 Mb), ~0.4 s per step
+    est = 0.4 * (args.steps + args.warmup)       # keep the whole run within a few minutes whatever K and W are
+    if est > 150:
+        scale = int(min(64, -(-4 * est // 150)))
     lengths = [L // scale for L in workload_lengths("c2")]
     P = max(1, min(cores, len(lengths)))
     rng = np.random.default_rng(1234)
