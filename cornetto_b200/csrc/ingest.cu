@@ -318,6 +318,9 @@ static int ingest_run(corn_ctx *ctx, const uint8_t *text, uint64_t n_text, int f
     const bool open_tail = text[n - 1] != '\n';             // bytes after the last newline
     const uint32_t n_lines = n_nl + ((final && open_tail) ? 1u : 0u);
     if (n_lines == 0) { out->consumed = 0; return CORN_OK; }   // not even one complete line yet
+    // text that is mostly newlines (lines of < 8 bytes on average) would need line tables several times its own
+    // size: not sequence data worth a device pass -- the serial reader takes it
+    if ((uint64_t)n_lines * 8u > (uint64_t)n + 4096u) { out->irregular = 1; return CORN_OK; }
 
     // line tables: nl | contrib | cum | (FASTA) hdr | hidx | hdr_line
     const size_t L1 = (size_t)n_lines + 1;

@@ -42,6 +42,7 @@ static Result ingest_block(const uint8_t *text, uint64_t n64, int final)
     if (final && text[n - 1] != '\n') nl.push_back(n);
     const uint32_t n_lines = (uint32_t)nl.size();
     if (n_lines == 0) return res;
+    if ((uint64_t)n_lines * 8u > (uint64_t)n + 4096u) { res.irregular = true; return res; }    // (same resource guard as ingest.cu)
     std::vector<uint32_t> contrib(n_lines), hdr(n_lines);
     for (uint32_t k = 0; k < n_lines; ++k) {
         const uint32_t s = k ? nl[k - 1] + 1 : 0, e = nl[k];
