@@ -24,6 +24,19 @@ def build(verbose: bool = False) -> None:
 
 
 def ensure_built() -> None:
-    """Build only if the artefacts are missing (the GPU box receives them prebuilt)."""
-    if not (os.path.exists(lib_path()) and os.path.exists(bin_path())):
+    """Brings the artefacts up to date with the sources (make is idempotent: a no-op when nothing changed, so a
+    stale library can never be measured).  On a box without nvcc the prebuilt files that travelled with the tree
+    are used as they are -- after checking that none of their sources is newer."""
+    import shutil
+    if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
         build()
+        return
+    if not (os.path.exists(lib_path()) and os.path.exists(bin_path())):
+        raise RuntimeError("libcorn_gpu.so / cornetto are missing and there is no nvcc to build them")
+    newest_src = 0.0
+    for sub in ("csrc", "host", os.path.join("..", "include")):
+        d = os.path.join(HERE, sub)
+        for f in os.listdir(d):
+            newest_src = max(newest_src, os.path.getmtime(os.path.join(d, f)))
+    if newest_src > min(os.path.getmtime(lib_path()), os.path.getmtime(bin_path())) + 1.0:
+        raise RuntimeError("prebuilt libcorn_gpu.so / cornetto are older than their sources and nvcc is not available")

@@ -65,6 +65,7 @@ SYMBOLS = [
     "corn_gpu_telofind", "corn_gpu_telofind_dev", "corn_gpu_hits_free",
     "corn_gpu_telowin", "corn_gpu_windows_free",
     "corn_gpu_sdust", "corn_gpu_sdust_dev", "corn_gpu_intervals_free",
+    "sdust", "sdust_buf_init", "sdust_buf_destroy", "sdust_core",
     "corn_gpu_ingest", "corn_gpu_ingest_free", "corn_gpu_host_register", "corn_gpu_host_unregister",
     "corn_gpu_last_timing", "corn_gpu_total_launches",
     "corn_bench_fill_random", "corn_bench_apply_features", "corn_bench_download_all", "corn_bench_flush_l2",
@@ -126,6 +127,15 @@ def load() -> C.CDLL:
     L.corn_gpu_sdust_dev.argtypes = [vp, vp, i32, i32, C.POINTER(Intervals)]
     L.corn_gpu_intervals_free.argtypes = [C.POINTER(Intervals)]
     L.corn_gpu_intervals_free.restype = None
+    # the reference's own library interface (src/sdust/sdust.h:16-21)
+    L.sdust.argtypes = [vp, C.c_char_p, i32, i32, i32, C.POINTER(i32)]
+    L.sdust.restype = C.POINTER(C.c_uint64)
+    L.sdust_buf_init.argtypes = [vp]
+    L.sdust_buf_init.restype = vp
+    L.sdust_buf_destroy.argtypes = [vp]
+    L.sdust_buf_destroy.restype = None
+    L.sdust_core.argtypes = [C.c_char_p, i32, i32, i32, C.POINTER(i32), vp]
+    L.sdust_core.restype = C.POINTER(C.c_uint64)
     L.corn_gpu_ingest.argtypes = [vp, vp, u64, i32, C.POINTER(Ingest)]
     L.corn_gpu_ingest_free.argtypes = [C.POINTER(Ingest)]
     L.corn_gpu_ingest_free.restype = None

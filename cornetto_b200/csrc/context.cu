@@ -71,11 +71,19 @@ extern "C" int corn_gpu_init(int device, corn_ctx_t **out)
     if (!ctx) return CORN_E_NOMEM;
     ctx->device = device;
     ctx->sm_count = sm_count;
+    int fail = CORN_OK;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return CORN_E_CUDA; }
     ctx->stream = ctx->own_stream;
-    for (int i = 0; i < 16; ++i)
-        if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { free(ctx); return CORN_E_CUDA; }
-    if (cudaMallocHost(&ctx->h_pinned_small, 4096) != cudaSuccess) { free(ctx); return CORN_E_NOMEM; }
+    for (int i = 0; i < 16 && fail == CORN_OK; ++i)
+        if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { ctx->ev[i] = NULL; fail = CORN_E_CUDA; }
+    if (fail == CORN_OK && cudaMallocHost(&ctx->h_pinned_small, 4096) != cudaSuccess) fail = CORN_E_NOMEM;
+    if (fail != CORN_OK) {                               // give back what was created so far
+        for (int i = 0; i < 16; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+        cudaStreamDestroy(ctx->own_stream);
+        cudaGetLastError();
+        free(ctx);
+        return fail;
+    }
     *out = ctx;
     return CORN_OK;
 }

@@ -175,6 +175,22 @@ int corn_telofind_resolve(corn_ctx *ctx);
 // same, with the first 32 bytes of ctx->misc (totals, counters) already read back by the caller
 int corn_telofind_resolve_with(corn_ctx *ctx, const uint32_t tot[8]);
 
+// sdust_wide.cu: the generic sdust instance for 128 < W <= CORN_SDUST_MAX_W (one thread per chunk, serial routines)
+#define CORN_SDUST_MAX_W 1024
+struct corn_sdust_wide_params {
+    const uint8_t  *seq;
+    const uint32_t *rec_off, *rec_len, *chunk_base;
+    uint32_t n_rec, n_chunks;
+    int T, W, C;
+    uint32_t cap;
+    uint64_t *slots;          // n_chunks * cap interval slots
+    uint32_t *cnt, *err;
+    uint8_t  *state;          // n_chunks rows of state_stride bytes (window ring, counters, perfect-interval slots)
+    size_t    state_stride;
+};
+size_t corn_sdust_wide_state_stride(int W);
+int corn_sdust_wide_scan(corn_ctx *ctx, const corn_sdust_wide_params &P);
+
 // pinned host result blocks handed to the caller (freed by corn_gpu_*_free)
 void *corn_host_alloc(size_t bytes);
 void  corn_host_free(void *p);

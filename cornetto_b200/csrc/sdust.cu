@@ -11,6 +11,8 @@
 #include "corn_internal.cuh"
 #include "sdust_core.cuh"
 
+using namespace sd_narrow;
+
 namespace {
 
 constexpr int SD_BLOCK = 128;
@@ -503,7 +505,14 @@ __global__ void k_sdust_rec_first(const uint32_t *__restrict__ chunk_base, const
 
 static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_intervals_t *out)
 {
-    if (W < 3 || W > SD_MAX_W) return corn_set_err(ctx, CORN_E_ARG, "sdust window %d outside [3,%d]", W, SD_MAX_W);
+    // Window range.  The reference accepts whatever atoi() returns (src/sdust/sdust.c:186-189):
+    //   W >= 3   works (W - 2 triplets per window);
+    //   W <  3   its window can never hold a triplet and kdq_shift() of the empty deque is dereferenced (:69-70) --
+    //            it crashes on the first triplet without printing anything.  Here: no interval, status OK.
+    //   W > 1024 its own 32-bit score products (r * l, :113-117) leave the int range inside long low-complexity
+    //            runs, so there is no defined result to reproduce: refused.
+    if (W > CORN_SDUST_MAX_W) return corn_set_err(ctx, CORN_E_ARG, "sdust window %d above %d (the reference's 32-bit score products overflow there)", W, CORN_SDUST_MAX_W);
+    const bool wide = W > SD_MAX_W;
     CORN_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ctx->pending) { CORN_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); CORN_TRY(corn_telofind_resolve(ctx)); }
     cudaStream_t st = ctx->stream;
@@ -516,13 +525,15 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     // the chain of a chunk inside a tandem repeat is ~4x slower than the rest, so on a small batch the
     // kernel lasts as long as that one chain: balance "all work / machine rate" against "C x slow-step
     // time", which on a B200 puts C near n_bases / 270 000.  Results do not depend on it.
-    const size_t smem = SdLayout(W).bytes();
+    const size_t smem = SdLayout(wide ? SD_MAX_W : W).bytes();
     typedef void (*sd_kernel_t)(const SdParams);
     const sd_kernel_t kern = W <= 66 ? (T >= 5 ? k_sdust_scan<2, true> : k_sdust_scan<2, false>)
                                      : (T >= 5 ? k_sdust_scan<4, true> : k_sdust_scan<4, false>);
-    CORN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
+    if (!wide) {
+        CORN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
+    }
     // Chunk length.  Every chunk pays ~3W warm-up positions, which favours long chunks; but the kernel cannot end
     // before its most expensive warp-task does (one with a lane inside a tandem repeat runs 3-4x as long), which
     // favours many short tasks when the batch is small.  Measured optimum (scripts/chunk_sweep.sh, Gbases/s):
@@ -532,6 +543,7 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
         const uint64_t want = db->n_bases / 1000000u;
         if (want < 3072) C = (int)(want < 512 ? 512 : want / 64 * 64);
     }
+    if (wide && C < 16 * W) C = 16 * W;          // the ~3W warm-up positions of a chunk stay below a fifth of it
     if (const char *e = getenv("CORNETTO_SDUST_CHUNK")) { int v = atoi(e); if (v >= 16 && v <= (1 << 20)) C = v; }
     const uint32_t n_rec = db->n_rec;
     const uint32_t cap = (uint32_t)(C + 2 * W) / 4 + 2;
@@ -557,13 +569,14 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     uint64_t *h_first = (uint64_t *)corn_host_alloc(sizeof(uint64_t) * ((size_t)n_rec + 1));
     if (!h_first) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc");
     out->rec_first = h_first;
-    if (n_chunks == 0) {
+    if (n_chunks == 0 || W < 3) {
         for (uint32_t r = 0; r <= n_rec; ++r) h_first[r] = 0;
         return CORN_OK;
     }
     const size_t slot_words = (size_t)(W | 1);
     const size_t iv_bytes = ((size_t)n_chunks * cap * sizeof(uint64_t) + 255) & ~(size_t)255;
-    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_slots, iv_bytes + (size_t)n_chunks * slot_words * sizeof(uint32_t)));
+    const size_t state_bytes = wide ? (size_t)n_chunks * corn_sdust_wide_state_stride(W) : (size_t)n_chunks * slot_words * sizeof(uint32_t);
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_slots, iv_bytes + state_bytes));
 
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     k_sdust_nchunks<<<(n_rec + 255) / 256, 256, 0, st>>>(db->d_rec_len, nch, n_rec, (uint32_t)C);
@@ -575,19 +588,27 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     sp.n_rec = n_rec; sp.n_chunks = n_chunks; sp.T = T; sp.W = W; sp.C = C; sp.cap = cap;
     sp.slots = (uint64_t *)ctx->sd_slots.p; sp.cnt = cnt; sp.err = d_err; sp.task_counter = d_tot + 8;
     sp.gslots = (uint32_t *)((uint8_t *)ctx->sd_slots.p + iv_bytes);
-    CORN_CUDA(ctx, cudaMemsetAsync(sp.gslots, 0, (size_t)n_chunks * slot_words * sizeof(uint32_t), st));
     sp.task_list = task_list;
-    k_sdust_probe<<<(n_chunks + 255) / 256, 256, 0, st>>>(sp, heavy_flag);
-    k_sdust_order<<<(n_tasks + 255) / 256, 256, 0, st>>>(heavy_flag, n_chunks, n_tasks, task_list, d_tot + 9);
-    corn_count_launch(ctx, 2);
-    CORN_LAUNCH_CHECK(ctx);
-    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    {
+    if (wide) {
+        corn_sdust_wide_params wp;
+        wp.seq = sp.seq; wp.rec_off = sp.rec_off; wp.rec_len = sp.rec_len; wp.chunk_base = chunk_base;
+        wp.n_rec = n_rec; wp.n_chunks = n_chunks; wp.T = T; wp.W = W; wp.C = C; wp.cap = cap;
+        wp.slots = sp.slots; wp.cnt = cnt; wp.err = d_err;
+        wp.state = (uint8_t *)sp.gslots; wp.state_stride = corn_sdust_wide_state_stride(W);
+        CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+        CORN_TRY(corn_sdust_wide_scan(ctx, wp));
+    } else {
+        CORN_CUDA(ctx, cudaMemsetAsync(sp.gslots, 0, (size_t)n_chunks * slot_words * sizeof(uint32_t), st));
+        k_sdust_probe<<<(n_chunks + 255) / 256, 256, 0, st>>>(sp, heavy_flag);
+        k_sdust_order<<<(n_tasks + 255) / 256, 256, 0, st>>>(heavy_flag, n_chunks, n_tasks, task_list, d_tot + 9);
+        corn_count_launch(ctx, 2);
+        CORN_LAUNCH_CHECK(ctx);
+        CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
         const unsigned want = (n_chunks + SD_BLOCK - 1) / SD_BLOCK, resident = (unsigned)(ctx->sm_count * blocks_per_sm);
         kern<<<want < resident ? want : resident, SD_BLOCK, smem, st>>>(sp);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
     }
-    corn_count_launch(ctx);
-    CORN_LAUNCH_CHECK(ctx);
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
 
     GatherParams gp;

@@ -40,7 +40,24 @@
 #define SD_HD static inline
 #endif
 
+// Two instances of this header exist.  The default ("narrow") one is the hot path: W <= 128, byte counters,
+// 32-bit slots, state in shared memory.  With SD_WIDE defined before inclusion the same code is compiled with
+// 16-bit counters and 64-bit slots for 128 < W <= SD_MAX_W = 1024 (csrc/sdust_wide.cu; `sdust -w 200`): the
+// reference takes any W (src/sdust/sdust.c:186-189), and up to there its own 32-bit arithmetic (score products
+// r * l in find_perfect, :113-117) is well defined.  Everything lives in a namespace per instance, so the two
+// can be linked into one library.
+#if defined(SD_WIDE)
+#define SD_MAX_W 1024
+#define SD_NS sd_wide
+typedef uint16_t sd_cnt_t;
+typedef uint64_t sd_slot_t;
+#else
 #define SD_MAX_W 128
+#define SD_NS sd_narrow
+typedef uint8_t  sd_cnt_t;
+typedef uint32_t sd_slot_t;
+#endif
+namespace SD_NS {
 
 // seq_nt4_table, src/sdust/sdust.c:23-40: A/a C/c G/g T/t -> 0..3, bytes 0..3 -> 0..3, rest 4
 // Branch-free on purpose: written as an if/else chain the four bases became four divergent paths that
@@ -64,22 +81,34 @@ SD_HD int sd_nt4(uint8_t c)
 //            for that access and for the warp-cooperative routines, where 32 lanes read 32
 //            consecutive entries of ONE thread's arrays.
 struct sd_mem {
-    uint8_t  *ring;    // W entries: triplet codes of the window deque
-    uint8_t  *cw;      // 64 window counters (column)
-    uint8_t  *cv;      // 64 suffix counters (column)
-    uint32_t *slot;    // W slots: valid:1 | flen:8 | l:8 | r:15
-    uint32_t  pitch;   // bytes, for cw / cv
+    uint8_t   *ring;   // W entries: triplet codes of the window deque
+    sd_cnt_t  *cw;     // 64 window counters (narrow: a column, see above)
+    sd_cnt_t  *cv;     // 64 suffix counters
+    sd_slot_t *slot;   // W slots: narrow valid:1 | flen:8 | l:8 | r:15, wide valid:1 | flen:11 | l:11 | r:32
+    uint32_t   pitch;  // bytes, for cw / cv (narrow only)
 };
 
+#if defined(SD_WIDE)
+#define SD_U8(base, i)  ((base)[(i)])                         /* plain per-thread arrays */
+#else
 #define SD_U8(base, i)  (*((base) + ((uint32_t)(i) >> 2) * m.pitch + ((uint32_t)(i) & 3u)))
+#endif
 #define SD_RING(i)      (m.ring[(i)])
 #define SD_SLOT(i)      (m.slot[(i)])
 
+#if defined(SD_WIDE)
+#define SD_SLOT_VALID 0x8000000000000000ull
+SD_HD sd_slot_t sd_slot_pack(int r, int l, int flen) { return SD_SLOT_VALID | ((uint64_t)flen << 43) | ((uint64_t)l << 32) | (uint32_t)r; }
+SD_HD int sd_slot_r(sd_slot_t s) { return (int)(uint32_t)s; }
+SD_HD int sd_slot_l(sd_slot_t s) { return (int)((s >> 32) & 0x7FFu); }
+SD_HD int sd_slot_flen(sd_slot_t s) { return (int)((s >> 43) & 0x7FFu); }
+#else
 #define SD_SLOT_VALID 0x80000000u
-SD_HD uint32_t sd_slot_pack(int r, int l, int flen) { return SD_SLOT_VALID | ((uint32_t)flen << 23) | ((uint32_t)l << 15) | (uint32_t)r; }
-SD_HD int sd_slot_r(uint32_t s) { return (int)(s & 0x7FFFu); }
-SD_HD int sd_slot_l(uint32_t s) { return (int)((s >> 15) & 0xFFu); }
-SD_HD int sd_slot_flen(uint32_t s) { return (int)((s >> 23) & 0xFFu); }
+SD_HD sd_slot_t sd_slot_pack(int r, int l, int flen) { return SD_SLOT_VALID | ((uint32_t)flen << 23) | ((uint32_t)l << 15) | (uint32_t)r; }
+SD_HD int sd_slot_r(sd_slot_t s) { return (int)(s & 0x7FFFu); }
+SD_HD int sd_slot_l(sd_slot_t s) { return (int)((s >> 15) & 0xFFu); }
+SD_HD int sd_slot_flen(sd_slot_t s) { return (int)((s >> 23) & 0xFFu); }
+#endif
 
 // interval sink = the reference's `res` vector for the save events this chunk owns.
 // save_masked_regions() appends an interval unless it starts at or before the finish of the
@@ -178,12 +207,12 @@ SD_HD bool sd_shift_window_push(sd_state &s, const sd_mem &m, int t, int T, int 
         s.whead = s.whead + 1 >= W ? 0 : s.whead + 1;
         --s.wn;
         const int c = SD_U8(m.cw, x) - 1;
-        SD_U8(m.cw, x) = (uint8_t)c;
+        SD_U8(m.cw, x) = (sd_cnt_t)c;
         s.rw -= c;
         if (s.L > s.wn) {
             --s.L;
             const int d = SD_U8(m.cv, x) - 1;
-            SD_U8(m.cv, x) = (uint8_t)d;
+            SD_U8(m.cv, x) = (sd_cnt_t)d;
             s.rv -= d;
         }
     }
@@ -193,10 +222,10 @@ SD_HD bool sd_shift_window_push(sd_state &s, const sd_mem &m, int t, int T, int 
     const int c = SD_U8(m.cw, t);
     s.rw += c;
     sd_slack_push(s, T, c);
-    SD_U8(m.cw, t) = (uint8_t)(c + 1);
+    SD_U8(m.cw, t) = (sd_cnt_t)(c + 1);
     const int d = SD_U8(m.cv, t);
     s.rv += d;
-    SD_U8(m.cv, t) = (uint8_t)(d + 1);
+    SD_U8(m.cv, t) = (sd_cnt_t)(d + 1);
     return d + 1 > cv_max;                           // (d + 1) * 10 > 2 * T
 }
 
@@ -206,7 +235,7 @@ SD_HD void sd_shift_window_pop(sd_state &s, const sd_mem &m, int t, int W)
     do {
         x = SD_RING(sd_ring_idx(s, s.wn - s.L, W));
         const int e = SD_U8(m.cv, x) - 1;
-        SD_U8(m.cv, x) = (uint8_t)e;
+        SD_U8(m.cv, x) = (sd_cnt_t)e;
         s.rv -= e;
         --s.L;
     } while (x != t);
@@ -265,7 +294,7 @@ SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W
     if (s.nslot)
         for (int i = s.wn - 1; i > i0; --i) {
             int si = base + i; if (si >= W) si -= W;
-            const uint32_t v = SD_SLOT(si);
+            const sd_slot_t v = SD_SLOT(si);
             if (v & SD_SLOT_VALID) {
                 const int pr = sd_slot_r(v), pl = sd_slot_l(v);
                 if (max_r == 0 || pr * max_l > max_r * pl) { max_r = pr; max_l = pl; }
@@ -277,10 +306,10 @@ SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W
         if (--ri < 0) ri = W - 1;
         const int c = SD_U8(m.cv, t);
         r += c;
-        SD_U8(m.cv, t) = (uint8_t)(c + 1);          // temporary; undone below (the reference copies cv)
+        SD_U8(m.cv, t) = (sd_cnt_t)(c + 1);          // temporary; undone below (the reference copies cv)
         const int new_r = r, new_l = s.wn - i - 1;
         int si = base + i; if (si >= W) si -= W;
-        const uint32_t v = SD_SLOT(si);
+        const sd_slot_t v = SD_SLOT(si);
         if (v & SD_SLOT_VALID) {                      // entries with this start join the running maximum
             const int pr = sd_slot_r(v), pl = sd_slot_l(v);
             if (max_r == 0 || pr * max_l > max_r * pl) { max_r = pr; max_l = pl; }
@@ -297,7 +326,7 @@ SD_HD void sd_find_perfect(sd_state &s, const sd_mem &m, int T, int start, int W
     for (int i = i0; i >= 0; --i) {
         const int t = SD_RING(ri);
         if (--ri < 0) ri = W - 1;
-        SD_U8(m.cv, t) = (uint8_t)(SD_U8(m.cv, t) - 1);
+        SD_U8(m.cv, t) = (sd_cnt_t)(SD_U8(m.cv, t) - 1);
     }
 }
 
@@ -338,7 +367,7 @@ SD_HD void sd_find_perfect_vec(sd_state &s, const sd_mem &m, int T, int start, i
     }
     for (int i = 0; i < wn; ++i) {                        // elements: slot and candidate
         int si = base + i; if (si >= W) si -= W;
-        const uint32_t v = SD_SLOT(si);
+        const sd_slot_t v = SD_SLOT(si);
         sv[i] = (v & SD_SLOT_VALID) != 0;
         pr[i] = sv[i] ? sd_slot_r(v) : 0; pl[i] = sv[i] ? sd_slot_l(v) : 1;
         er[i] = pr[i]; el[i] = pl[i];
@@ -500,3 +529,5 @@ SD_HD void sd_gather_write(const uint64_t *slots, const uint32_t *n, uint32_t ca
         *dst++ = iv;
     }
 }
+
+}  // namespace SD_NS

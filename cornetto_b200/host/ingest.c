@@ -142,17 +142,28 @@ static void wait_idle(iworker_t *w)
 /* ---- file reading: the page cache delivers ~3 GB/s to one thread, so large blocks are read by four -- */
 typedef struct { int fd; uint8_t *dst; uint64_t off, n, got; pthread_t th; } slice_t;
 
+/* A read that fails, or stops before the size fstat() reported (the file shrank under us), is an ERROR: the
+ * caller must not mistake it for the end of the input and print a truncated result with exit status 0. */
+static int g_read_errno;     /* first read error seen by any slice (0 = none); -1 = short read before st_size */
+
 static uint64_t pread_full(int fd, uint8_t *dst, uint64_t off, uint64_t n)
 {
     uint64_t got = 0;
     while (got < n) {
         const size_t want = n - got > (1u << 30) ? (1u << 30) : (size_t)(n - got);
         const ssize_t k = pread(fd, dst + got, want, (off_t)(off + got));
-        if (k < 0) { if (errno == EINTR) continue; break; }
-        if (k == 0) break;
+        if (k < 0) { if (errno == EINTR) continue; if (!g_read_errno) g_read_errno = errno ? errno : EIO; break; }
+        if (k == 0) { if (!g_read_errno) g_read_errno = -1; break; }      /* callers never ask beyond st_size */
         got += (uint64_t)k;
     }
     return got;
+}
+
+static void die_if_read_failed(const char *path)
+{
+    if (!g_read_errno) return;
+    CORN_ERROR("reading %s failed: %s", path, g_read_errno > 0 ? strerror(g_read_errno) : "the file is shorter than its size at open time");
+    exit(EXIT_FAILURE);
 }
 
 static void *slice_main(void *p)
@@ -276,6 +287,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
             want = size - file_pos < block - carry_len ? size - file_pos : block - carry_len;
             const double t_rd = realtime();
             fresh = read_block(fd, x->blk + carry_len, file_pos, want);
+            die_if_read_failed(path);
             TRACE("[ingest] read %.1f MB in %.3f s\n", (double)fresh / 1e6, realtime() - t_rd);
             file_pos += fresh;
         }
@@ -313,6 +325,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
             const uint64_t w2 = size - file_pos < block - reserve ? size - file_pos : block - reserve;
             const double t_rd = realtime();
             ahead_bytes = read_block(fd, y->text + reserve, file_pos, w2);
+            die_if_read_failed(path);
             TRACE("[ingest] read ahead %.1f MB in %.3f s\n", (double)ahead_bytes / 1e6, realtime() - t_rd);
             file_pos += ahead_bytes;
             ahead_for = dispatched + 1;

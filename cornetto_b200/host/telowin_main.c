@@ -57,7 +57,9 @@ int telomere_windows_main(int argc, char *argv[])
     char line[LINE_CAP];
     while (fgets(line, sizeof line, fp)) {
         char *t[6];
-        if (split_ws(line, t, 6) < 6) continue;
+        /* columns 1, 2, 4 and 5 are all the reference uses (sscanf takes whatever is there, src/telomere_windows.c:67-77):
+         * a line cut after the fifth column still paints */
+        if (split_ws(line, t, 6) < 5) continue;
         if (n_sc == 0 || strcmp(t[0], names[n_sc - 1]) != 0) {
             if (n_sc == m_sc) {
                 m_sc = m_sc ? m_sc * 2 : 64;

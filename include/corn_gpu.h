@@ -119,6 +119,8 @@ typedef struct corn_hits {
 } corn_hits_t;
 
 /* Host-buffer entry point (H2D + kernels + D2H). */
+/* motif: 1..255 bytes, used as given (never case-folded, src/find_telomere.c:90-91); longer motifs are refused with
+ * CORN_E_ARG (the reference has no bound; nothing biological comes near it). */
 int  corn_gpu_telofind(corn_ctx_t *ctx, const corn_batch_t *batch, const char *motif, corn_hits_t *out);
 /* Same on a resident batch.  out may be NULL: the runs then stay on the device only (they are
  * always kept there for a following corn_gpu_telowin(hits == NULL)). */
@@ -161,10 +163,28 @@ typedef struct corn_intervals {
     void     *_owner;
 } corn_intervals_t;
 
-/* 3 <= W <= 128 (default 64), any T (default 20). */
+/* Any T (default 20).  W (default 64) as the reference takes it (src/sdust/sdust.c:186-189, W = atoi()):
+ *   3 <= W <= 128    the tuned kernels (csrc/sdust.cu);
+ *   128 < W <= 1024  a generic instance (csrc/sdust_wide.cu), same results as the reference, not tuned;
+ *   W < 3            no interval, CORN_OK (the reference dereferences an empty deque there and crashes
+ *                    on the first triplet without printing anything);
+ *   W > 1024         CORN_E_ARG: the reference's own 32-bit score products (r * l, :113-117) overflow inside
+ *                    long low-complexity runs, so there is no defined result to reproduce. */
 int  corn_gpu_sdust(corn_ctx_t *ctx, const corn_batch_t *batch, int T, int W, corn_intervals_t *out);
 int  corn_gpu_sdust_dev(corn_ctx_t *ctx, const corn_dbatch_t *db, int T, int W, corn_intervals_t *out);
 void corn_gpu_intervals_free(corn_intervals_t *iv);
+
+/* The reference's own library interface for sdust, src/sdust/sdust.h:16-21 -- same names, same signatures,
+ * same ownership (csrc/sdust_api.cu): a program that links the reference's sdust.o can link this library
+ * instead.  sdust(): result malloc()ed, caller free()s, *n intervals, l_seq < 0 means strlen(seq), `km` is
+ * ignored (as by the reference's kalloc.h).  sdust_core(): result owned by `buf`, valid until the next call on
+ * it.  Uses one process-wide context on device $CORNETTO_GPU (default 0); on failure NULL and *n = -1. */
+struct sdust_buf_s;
+typedef struct sdust_buf_s sdust_buf_t;
+uint64_t       *sdust(void *km, const uint8_t *seq, int l_seq, int T, int W, int *n);
+sdust_buf_t    *sdust_buf_init(void *km);
+void            sdust_buf_destroy(sdust_buf_t *buf);
+const uint64_t *sdust_core(const uint8_t *seq, int l_seq, int T, int W, int *n, sdust_buf_t *buf);
 
 /* ---- ingest: replaces the byte loop of kseq_read()/ks_getuntil2(), src/kseq.h:102-141,184-224 ---
  * Parses plain FASTA/FASTQ TEXT on the device: ships the raw file bytes over PCIe once, finds the

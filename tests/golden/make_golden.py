@@ -25,11 +25,15 @@ REF = os.path.join(ROOT, "oracle", "_ref", "cornetto")
 
 MOTIFS = ["TTAGGG", "ttaggg", "TATATA", "AAAAAA", "CCCTAA", "TTAGGGTTAGGG", "ACGT", "TTNGGG"]
 TELOWIN = [["99.9", "0.4"], ["99.9", "0.1"], ["100"], ["95", "0.05"]]
-SDUST = [[], ["-w", "32", "-t", "15"], ["-t", "10"]]
+SDUST = [[], ["-w", "32", "-t", "15"], ["-t", "10"], ["-w", "3"], ["-t", "0"], ["-t", "-3"]]
+# windows beyond the tuned kernels' 128 (the generic instance, csrc/sdust_wide.cu); the reference needs O(W^2) and more
+# per base inside low-complexity sequence there, so these run on the two smallest sdust inputs only
+SDUST_WIDE = [["-w", "129"], ["-w", "200"], ["-w", "500", "-t", "30"]]
+SDUST_WIDE_CASES = ("q6_sdust.fa", "sdust_wide.fa")
 
 
 def ref(args, stdin=None):
-    p = subprocess.run([REF] + args, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    p = subprocess.run([REF] + args, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True, timeout=300)
     return p.stdout
 
 
@@ -42,6 +46,7 @@ def main():
     cases["asm_small.fa"] = synth.fasta_bytes(
         synth.assembly(42, [150_000, 60_000, 999, 1000, 1200, 7], n_gaps=2, iupac_per_mb=40.0))
     cases["reads_small.fq"] = synth.fastq_bytes(synth.reads(3, 12, n50=8_000, p_telo=0.4))
+    cases["sdust_wide.fa"] = synth.fasta_bytes(synth.assembly(77, [5000, 2500, 300], n_gaps=3, telo=(40, 120)))
     out = {}
     with tempfile.TemporaryDirectory() as td:
         for name, data in cases.items():
@@ -56,7 +61,7 @@ def main():
             lf = os.path.join(td, name + ".lens"); open(lf, "wb").write(lens_from_fa2bed(base64.b64decode(c["fa2bed"])))
             for a in TELOWIN:
                 c["telowin"][" ".join(a)] = b64(ref(["telowin", tf] + a))
-            for a in SDUST:
+            for a in SDUST + (SDUST_WIDE if name in SDUST_WIDE_CASES else []):
                 c["sdust"][" ".join(a)] = b64(ref(["sdust"] + a + [fa]))
             sf = os.path.join(td, name + ".sdust"); open(sf, "wb").write(base64.b64decode(c["sdust"][""]))
             c["telobreaks"] = b64(ref(["telobreaks", lf, sf, tf]))

@@ -7,7 +7,11 @@ import os
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json.gz")
 MOTIFS = ["TTAGGG", "ttaggg", "TATATA", "AAAAAA", "CCCTAA", "TTAGGGTTAGGG", "ACGT", "TTNGGG"]
 TELOWIN = [["99.9", "0.4"], ["99.9", "0.1"], ["100"], ["95", "0.05"]]
-SDUST = [[], ["-w", "32", "-t", "15"], ["-t", "10"]]
+SDUST = [[], ["-w", "32", "-t", "15"], ["-t", "10"], ["-w", "3"], ["-t", "0"], ["-t", "-3"]]
+# windows beyond the tuned kernels' 128 (the generic instance, csrc/sdust_wide.cu); the reference needs O(W^2) and more
+# per base inside low-complexity sequence there, so these run on the two smallest sdust inputs only
+SDUST_WIDE = [["-w", "129"], ["-w", "200"], ["-w", "500", "-t", "30"]]
+SDUST_WIDE_CASES = ("q6_sdust.fa", "sdust_wide.fa")
 
 
 def load():

@@ -21,6 +21,8 @@
 #include "../../cornetto_b200/csrc/telofind_core.cuh"
 #include "../../oracle/oracle.h"
 
+using namespace SD_NS;      // sd_narrow, or sd_wide when built with -DSD_WIDE (16-bit counters, 64-bit slots, W <= 1024)
+
 static uint64_t rng_state = 88172645463325252ull;
 static uint64_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return rng_state; }
 
@@ -153,8 +155,9 @@ static int sim_sdust(const char *path, int T, int W, int C)
         std::vector<uint64_t> slots((size_t)nch * cap + 1);
         std::vector<uint32_t> cnt(nch + 1, 0);
         for (uint32_t k = 0; k < nch; ++k) {
-            uint8_t ring[SD_MAX_W], cw[64], cv[64];
-            uint32_t slot[SD_MAX_W];
+            uint8_t ring[SD_MAX_W];
+            sd_cnt_t cw[64], cv[64];
+            sd_slot_t slot[SD_MAX_W];
             sd_mem m = { ring, cw, cv, slot, 4 };
             const int c0 = (int)k * C, c1 = std::min(len, (int)(k + 1) * C);
             sd_sink sink;

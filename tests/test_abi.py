@@ -23,7 +23,8 @@ def declared_symbols():
     for h in ("corn_gpu.h", "corn_bench.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-        names |= set(re.findall(r"\b(corn_(?:gpu|hbatch|bench)_\w+)\s*\(", src))
+        names |= set(re.findall(r"\b(corn_(?:gpu|hbatch|bench|shard)_\w+)\s*\(", src))
+        names |= set(re.findall(r"\b(sdust(?:_core|_buf_init|_buf_destroy)?)\s*\(", src))     # the reference's sdust.h interface
     return names
 
 

@@ -65,7 +65,7 @@ def test_cli_matches_golden(tmp_path):
         for a in (golden_util.TELOWIN[0], golden_util.TELOWIN[1 + k % 3]):
             out, _, _ = cornetto(["telowin", tf] + a)
             assert out == c["telowin"][" ".join(a)], ("telowin", name, a)
-        for a in (golden_util.SDUST[0], golden_util.SDUST[1 + k % 2]):
+        for a in [golden_util.SDUST[0], golden_util.SDUST[1 + k % (len(golden_util.SDUST) - 1)]] + (golden_util.SDUST_WIDE[1:2] if name in golden_util.SDUST_WIDE_CASES else []):
             out, _, _ = cornetto(["sdust"] + a + [fa])
             assert out == c["sdust"][" ".join(a)], ("sdust", name, a)
         sf = write(str(tmp_path / (name + ".sdust")), c["sdust"][""])
@@ -102,7 +102,7 @@ def test_abi_matches_golden(ctx, capi):
             runs = ctx.telofind(hb, m)
             got = b"".join(b"%s\t%d\t%d\t%d\t%d\t%d\n" % (recs[r["rec"]][0], len(recs[r["rec"]][1]), r["strand"], r["start"], r["end"], r["end"] - r["start"]) for r in runs)
             assert got == c["telofind"][m], ("telofind", name, m)
-        for a in golden_util.SDUST:
+        for a in golden_util.SDUST + (golden_util.SDUST_WIDE if name in golden_util.SDUST_WIDE_CASES else []):
             T, W = 20, 64
             if "-t" in a:
                 T = int(a[a.index("-t") + 1])
@@ -262,14 +262,45 @@ def test_abi_sdust(ctx, capi, tw):
     assert len(iv) == len(wiv) and (iv == wiv).all()
 
 
+def test_sdust_library_api(capi):
+    """sdust() / sdust_buf_init / sdust_core / sdust_buf_destroy with the reference's signatures and ownership rules
+    (src/sdust/sdust.h:16-21): l_seq < 0 means strlen, sdust()'s result is free()d by the caller, sdust_core()'s
+    belongs to the buffer and is replaced by the next call."""
+    import ctypes as C
+    L = capi.load()
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(9)
+    seqs = [synth.make_contig(rng, n, telo=None, n_its=0, microsat_per_mb=4000.0, n_gaps=g, gap_len=(1, 30)).tobytes()
+            for n, g in ((20_000, 3), (700, 1), (5, 0))] + [b"A" * 100 + b"N" + b"AAAAA", b""]
+    buf = L.sdust_buf_init(None)
+    assert buf
+    for T, W in ((20, 64), (12, 30), (20, 200)):
+        for sq in seqs:
+            want, _ = oracle_sdust([np.frombuffer(sq, dtype=np.uint8)], T, W)
+            n = C.c_int(-5)
+            p = L.sdust(None, sq, -1 if (len(sq) and 0 not in sq) else len(sq), T, W, C.byref(n))
+            assert bool(p) and n.value == len(want)
+            assert [int(p[i]) for i in range(n.value)] == [int(x) for x in want]
+            libc.free(C.cast(p, C.c_void_p))
+            n2 = C.c_int(-5)
+            q = L.sdust_core(sq, len(sq), T, W, C.byref(n2), buf)
+            assert bool(q) and n2.value == len(want) and [int(q[i]) for i in range(n2.value)] == [int(x) for x in want]
+    L.sdust_buf_destroy(buf)
+    L.sdust_buf_destroy(None)
+
+
 def test_abi_errors(ctx, capi):
     hb = capi.HostBatch([b"ACGT"])
     with pytest.raises(capi.CornError):
         ctx.telofind(hb, "")
+    # window sizes: whatever the reference runs with, runs (golden: -w 3, 129, 200, 500); below 3 the reference
+    # crashes without output and this returns no interval; above 1024 its 32-bit score products overflow: refused
+    for w in (2, 0, -7):
+        iv, first = ctx.sdust(capi.HostBatch([b"A" * 300, b"ACGT"]), 20, w)
+        assert len(iv) == 0 and list(first) == [0, 0, 0]
     with pytest.raises(capi.CornError):
-        ctx.sdust(hb, 20, 2)
-    with pytest.raises(capi.CornError):
-        ctx.sdust(hb, 20, 500)
+        ctx.sdust(hb, 20, 1025)
     # empty batch is fine
     e = capi.HostBatch([])
     assert len(ctx.telofind(e)) == 0

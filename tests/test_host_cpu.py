@@ -367,6 +367,31 @@ def test_sim_sdust_vector_form_and_slack_skip(sim_vec_bin, oracle_bin, tmp_path)
     assert skipped > 1000
 
 
+@pytest.fixture(scope="module")
+def sim_wide_bin(tmp_path_factory, oracle_bin):
+    """The simulator built on the WIDE instance of sdust_core.cuh (16-bit counters, 64-bit slots: what csrc/sdust_wide.cu runs)."""
+    out = str(tmp_path_factory.mktemp("simw") / "sim_wide")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DSD_WIDE", "-o", out, "-x", "c++",
+                           os.path.join(ROOT, "tests", "sim", "sim_main.cpp"), "-x", "c", os.path.join(ROOT, "oracle", "oracle.c"), "-lz", "-lm"],
+                          stderr=subprocess.DEVNULL)
+    return out
+
+
+def test_sim_sdust_wide_windows(sim_wide_bin, oracle_bin, tmp_path):
+    """Windows beyond 128 (`sdust -w 200`): the generic instance, chunked with seams, against the oracle; N-rich inputs."""
+    rng = np.random.default_rng(515)
+    recs = [(f"w{k}", synth.make_contig(rng, L, telo=None, n_its=0, microsat_per_mb=3000.0, n_gaps=g, gap_len=(1, gl), p_lower=0.1))
+            for k, (L, g, gl) in enumerate(((4000, 4, 300), (1500, 6, 3), (130, 0, 1), (3, 0, 1)))]
+    recs.append(("homo", np.frombuffer(b"A" * 400 + b"N" + b"AAAAA", dtype=np.uint8)))
+    p = write(str(tmp_path / "wide.fa"), synth.fasta_bytes(recs))
+    for opts in (["-w", "129"], ["-w", "200"], ["-w", "333", "-t", "12"]):
+        b, _, _ = run([oracle_bin, "sdust"] + opts + [p])
+        assert len(b) > 20
+        for chunk in ("700", "2048"):
+            a, _, _ = run([sim_wide_bin, "sdust"] + opts + ["-c", chunk, p])
+            assert a == b, (opts, chunk)
+
+
 def test_scan_commands_fail_loudly_without_gpu(built, tmp_path):
     import torch
     if torch.cuda.is_available():

@@ -22,7 +22,7 @@ def test_oracle_matches_golden(oracle_bin, tmp_path):
         for a in golden_util.TELOWIN:
             out, _, _ = run([oracle_bin, "telowin", tf] + a)
             assert out == c["telowin"][" ".join(a)], (name, a)
-        for a in golden_util.SDUST:
+        for a in golden_util.SDUST + (golden_util.SDUST_WIDE if name in golden_util.SDUST_WIDE_CASES else []):
             out, _, _ = run([oracle_bin, "sdust"] + a + [fa])
             assert out == c["sdust"][" ".join(a)], (name, a)
         sf = write(str(tmp_path / (name + ".sdust")), c["sdust"][""])
