@@ -3,29 +3,36 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-Workload (BASELINE.json configs[1], "c2"): telofind + telowin (threshold 0.4, identity 99.9) over
-a synthetic 3.1 Gb T2T-like haploid assembly (24 contigs with CHM13-like lengths, (CCCTAA)n /
-(TTAGGG)n ends with 2 % variant repeats, interstitial telomere blocks, microsatellites, 5 %
-soft-masked lower case), generated in place in HBM from a seeded counter-based generator.
-A "step" is one pass of the hot path over that assembly.  With N > 1 every rank (one process per
-GPU, torchrun) scans its own 3.1 Gb assembly -- the shards are independent, there is no
-collective on the data path -- so scaling is weak and `value` is the whole-job aggregate.
+N = 1 (BASELINE.json configs[1], "c2"): telofind + telowin (threshold 0.4, identity 99.9) over a synthetic 3.1 Gb
+T2T-like haploid assembly (24 contigs with CHM13-like lengths, (CCCTAA)n / (TTAGGG)n ends with 2 % variant
+repeats, interstitial telomere blocks, microsatellites, 5 % soft-masked lower case), generated in place in HBM
+from a seeded counter-based generator.  A "step" is one pass of the hot path over that assembly.
+
+N > 1 (BASELINE.json configs[2], "c3"): ONE 6.2 Gb diploid assembly (48 contigs, N gaps included) split over the
+N GPUs by the library's record partitioner (corn_shard_plan, csrc/shard.cu): one process per GPU (torchrun), each
+holding its shard resident; no collective on the data path (NCCL carries the barriers and the timing reduction
+only).  A step is one pass of every rank over its shard; `value` = 6.2 Gb x K / max-over-ranks time: STRONG
+scaling (the same total work for every N > 1).  Inside the run every rank checks one whole contig of its shard
+byte for byte against the compiled reference (telofind, telowin, sdust), and rank 0 merges the shards' results
+into file order (corn_shard_merge_*) and runs telobreaks on them beside the reference's.  The N = 1 line carries
+the same c3 job on one GPU (two resident batches) as `c3_1gpu`, the base of the strong-scaling curve.
 
   value          Gbases/s, all kernels of the step (scan + ordering + run assembly + bins + windows),
                  inputs resident in HBM, CUDA events on the launching stream, max over ranks
   roofline       dominant kernel (k_telofind_scan): algorithmic bytes = 1 byte per base + 16 bytes per
                  emitted run, divided by that kernel's event-timed duration, against the measured
-                 HBM copy bandwidth in MEASURED_PEAKS.json
-  e2e            same metric through the host-buffer C ABI call (corn_gpu_telofind + corn_gpu_telowin):
-                 H2D of the pinned sequence bytes and D2H of the runs/windows inside the timed region
+                 HBM copy bandwidth in MEASURED_PEAKS.json; step_frac = the same bytes over the whole step
+  e2e            same metric from FASTA TEXT in page-locked host memory through the C ABI: corn_gpu_ingest
+                 (H2D of the text, parsing on the device) + corn_gpu_telofind_dev + corn_gpu_telowin, runs and
+                 windows copied back -- every byte of input crosses PCIe inside the timed region
+  e2e_from_file  what a user of the drop-in binary waits for: `cornetto telofind x.fa > x.telomere` +
+                 `cornetto telowin x.telomere 99.9 0.4`, FASTA file (page cache) to text, process and CUDA
+                 start-up included; the reference binary on the same file beside it
   cpu_baseline   the reference's own C implementation (oracle/_ref/cornetto, compiled from the
                  unmodified sources) or the oracle port, single thread as shipped, on a bounded
                  sample of the same assembly
   sdust          (extra) `sdust -w 64 -t 20` kernel time on the same resident assembly (BASELINE.json configs[3])
   ingest         (extra) device-side FASTA parsing of 0.8 GB of text: PCIe copy, line tables, gather kernel
-  cli            (extra) wall clock of the drop-in `cornetto telofind` + `cornetto telowin` commands on the
-                 cpu_baseline's FASTA sample and on the whole assembly written as FASTA (parse, CUDA start-up
-                 and text output included); best of a few runs
 
 `--impl reference` times the reference's CPU implementation alone (rank 0 only) on the host cores:
 P independent processes over contig-split FASTAs, P = usable cores.
@@ -58,17 +65,30 @@ THR = 0.4 * (99.9 / 100.0) ** 6
 def workload_lengths(name: str):
     if name == "c2":
         return list(CHM13)
+    if name == "c3":                         # diploid: maternal set + a paternal set whose contigs differ by up to ~1 %
+        return list(CHM13) + [L - (L // 997) * ((i * 7) % 11) for i, L in enumerate(CHM13)]
     if name == "small":                      # 1/64 scale, for quick runs and CI-sized boxes
         return [max(1000, L // 64) for L in CHM13]
+    if name == "small3":
+        return [max(1000, L // 64) for L in workload_lengths("c3")]
     raise SystemExit(f"unknown workload {name}")
+
+
+def workload_names(name: str):
+    n = len(CHM13)
+    if name in ("c3", "small3"):
+        return [f"chr{i + 1}_MATERNAL" for i in range(n)] + [f"chr{i + 1}_PATERNAL" for i in range(n)]
+    return [f"chr{i + 1}" for i in range(n)]
 
 
 # ------------------------------------------------------------------------------------------------
 # synthetic features (host side: a few 10^5 small descriptors; the bytes are generated on the GPU)
 # ------------------------------------------------------------------------------------------------
-def make_features(capi, lengths, seed):
-    rng = np.random.default_rng(seed)
-    tand, lower = [], []
+def make_features(capi, lengths, seed, n_gaps=0):
+    """-> (tandem, lower, gaps) feature arrays over GLOBAL record numbers; every record draws from its own
+    generator keyed by (seed, record), so a record gets the same features whichever shard holds it.
+    n_gaps: N runs per contig (lengths log-uniform in 1..50 000), none inside the telomeric ends."""
+    tand, lower, gaps = [], [], []
 
     def unit8(b):
         u = np.zeros(8, dtype=np.uint8)
@@ -76,6 +96,7 @@ def make_features(capi, lengths, seed):
         return u
 
     for rec, L in enumerate(lengths):
+        rng = np.random.default_rng([seed, rec])
         occupied = []
         if L > 40_000:
             n5, n3 = int(rng.integers(500, 2501)), int(rng.integers(500, 2501))
@@ -106,13 +127,37 @@ def make_features(capi, lengths, seed):
                 ln = int(ls[k + 1] - st)
             if ln > 0:
                 lower.append((rec, int(st), ln, 2, 1, 0, 0.0, unit8(b"")))
+        if n_gaps and L > 200_000:
+            gs = np.sort(rng.integers(60_000, L - 120_000, size=n_gaps))
+            for k, st in enumerate(gs):
+                ln = int(np.exp(rng.uniform(0.0, np.log(50_000.0))))
+                if k + 1 < n_gaps and st + ln > gs[k + 1]:
+                    ln = int(gs[k + 1] - st)
+                if ln > 0:
+                    gaps.append((rec, int(st), ln, 1, 1, 0, 0.0, unit8(b"")))
 
     def pack(rows):
         a = np.zeros(len(rows), dtype=capi.FEAT_DTYPE)
         for i, (rec, st, ln, kind, period, sd, pv, unit) in enumerate(rows):
             a[i] = (rec, st, ln, kind, period, sd, pv, unit, 0)
         return a
-    return pack(tand), pack(lower)
+    return pack(tand), pack(lower), pack(gaps)
+
+
+def build_resident(ctx, capi, lengths, records, seed, feats):
+    """Resident batch holding the global records `records` (file order): bytes keyed by (seed, global record), then
+    the features of those records.  Returns the batch handle."""
+    records = np.asarray(records, dtype=np.uint32)
+    db = ctx.alloc([lengths[int(r)] for r in records])
+    ctx.fill_random(db, seed, rec_id=records)
+    local = np.full(len(lengths), -1, dtype=np.int64)
+    local[records] = np.arange(len(records))
+    for f in feats:                          # tandem, then lower case, then N gaps (successive calls are ordered)
+        mine = f[local[f["rec"]] >= 0].copy()
+        mine["rec"] = local[mine["rec"]]
+        if len(mine):
+            ctx.apply_features(db, mine)
+    return db
 
 
 # ------------------------------------------------------------------------------------------------
@@ -356,36 +401,105 @@ def load_traffic():
     return None
 
 
+def fasta_text(named_seqs, width=60):
+    """FASTA text of the records as one uint8 array (what a file of them holds)."""
+    parts = []
+    for name, a in named_seqs:
+        a = np.asarray(a, dtype=np.uint8)
+        parts.append(np.frombuffer(b">" + name.encode() + b"\n", dtype=np.uint8))
+        full = len(a) // width * width
+        if full:
+            body = np.empty((full // width, width + 1), dtype=np.uint8)
+            body[:, :width] = a[:full].reshape(-1, width)
+            body[:, width] = 10
+            parts.append(body.reshape(-1))
+        if full < len(a):
+            parts += [a[full:], np.frombuffer(b"\n", dtype=np.uint8)]
+    return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+
+
+def fmt_telofind(runs, names, lengths):
+    return b"".join(b"%s\t%d\t%d\t%d\t%d\t%d\n" % (names[r], lengths[r], st, a, b, b - a)
+                    for r, st, a, b in zip(runs["rec"].tolist(), runs["strand"].tolist(), runs["start"].tolist(), runs["end"].tolist()))
+
+
+def fmt_windows(wins, names, lengths):
+    return b"".join(b"Window\t%s\t%d\t%d\t%d\t%s\n" % (names[r], lengths[r], a, b, (b"%.3g" % (c / (b - a))))
+                    for r, a, b, c in zip(wins["rec"].tolist(), wins["start"].tolist(), wins["end"].tolist(), wins["car"].tolist()))
+
+
+def fmt_sdust(iv, first, names):
+    out = []
+    s = (iv >> np.uint64(32)).astype(np.int64).tolist()
+    f = (iv & np.uint64(0xFFFFFFFF)).astype(np.uint32).astype(np.int32).tolist()
+    for r in range(len(names)):
+        a, b = int(first[r]), int(first[r + 1])
+        out.append(b"".join(b"%s\t%d\t%d\n" % (names[r], s[k], f[k]) for k in range(a, b)))
+    return b"".join(out)
+
+
+def check_contig_against_reference(ctx, capi, db, local_rec, name, length, runs, wins, iv, first, workdir):
+    """One whole contig of a resident batch against the compiled reference (or the oracle port): telofind lines,
+    telowin (99.9, 0.4) lines and sdust lines byte for byte.  Returns (verdicts, reference seconds for telofind and
+    telowin, kind of checker)."""
+    binary, kind = ref_binary()
+    seq = ctx.download(db, int(local_rec), int(length))
+    fa = os.path.join(workdir, f"check_{name}.fa")
+    write_fasta(fa, [(name, seq)])
+    tf, tw = cpu_pipeline_seconds(binary, fa, workdir)            # leaves <fa>.telomere in workdir
+    tel = os.path.join(workdir, os.path.basename(fa) + ".telomere")
+    want_t = open(tel, "rb").read()
+    want_w = subprocess.run([binary, "telowin", tel, "99.9", "0.4"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    want_s = subprocess.run([binary, "sdust", fa], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    bname = [name.encode()]
+    mine = runs[runs["rec"] == local_rec].copy()
+    mine["rec"] = 0
+    mw = wins[wins["rec"] == local_rec].copy()
+    mw["rec"] = 0
+    a, b = int(first[local_rec]), int(first[local_rec + 1])
+    ok = {"telofind": fmt_telofind(mine, bname, [int(length)]) == want_t,
+          "telowin": fmt_windows(mw, bname, [int(length)]) == want_w,
+          "sdust": fmt_sdust(iv[a:b], np.array([0, b - a], dtype=np.uint64), bname) == want_s,
+          "lines": [want_t.count(b"\n"), want_w.count(b"\n"), want_s.count(b"\n")]}
+    return ok, tf, tw, kind
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("CORN_BENCH_WORKLOAD", "c2"))
+    ap.add_argument("--workload", default=os.environ.get("CORN_BENCH_WORKLOAD", ""),
+                    help="c2 (default at N=1), c3 (default at N>1), small, small3")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sdust", action="store_true")
     ap.add_argument("--no-ingest", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="N=1: skip the 6.2 Gb c3 job on one GPU (strong-scaling base)")
     ap.add_argument("--no-cli-full", action="store_true", help="skip the drop-in binary's run on the full-size FASTA")
+    ap.add_argument("--no-check", action="store_true", help="N>1: skip the per-rank contig check against the reference and telobreaks")
     ap.add_argument("--profile-only", action="store_true", help="warm-up + steps only (for ncu): no e2e, no CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    import ctypes as C
     import torch
     from cornetto_b200 import capi
     from cornetto_b200.build import ensure_built
-    ensure_built()
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
+    if rank == 0:
+        ensure_built()
+    dist = gloo = None
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")          # host-side gathers of result lists (outside the timed regions)
+        dist.barrier()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the scan path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -393,15 +507,8 @@ def main():
     ctx = capi.Context(local)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-
-    lengths = workload_lengths(args.workload)
-    n_bases = int(sum(lengths))
-    db = ctx.alloc(lengths)
-    ctx.fill_random(db, 42 + 1000 * rank)
-    tand, lower = make_features(capi, lengths, 7 + rank)
-    ctx.apply_features(db, tand)
-    ctx.apply_features(db, lower)
-    total_bytes = int(ctx.L.corn_gpu_dbatch_bytes(db))
+    Lc = ctx.L
+    peak, peak_src = load_peak()
 
     def barrier():
         torch.cuda.synchronize()
@@ -409,180 +516,323 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    import ctypes as C
-    Lc = ctx.L
+    def allmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- workload: which records this rank holds, in how many resident batches -------------------------------
+    wl = args.workload or ("c2" if world == 1 else "c3")
+    sharded = world > 1
+    lengths = workload_lengths(wl)
+    names = workload_names(wl)
+    n_bases_total = int(sum(lengths))
+    seed_bytes, seed_feat = 42, 7
+    feats = make_features(capi, lengths, seed_feat, n_gaps=3 if wl in ("c3", "small3") else 0)
+
+    def plan_batches(lens, n_ranks, my_rank):
+        """records of this rank, cut into batches of at most CORN_MAX_BATCH_BYTES (one batch unless a single GPU holds > 4 GiB)"""
+        shard_of = capi.shard_plan(lens, n_ranks)
+        mine = capi.shard_records(shard_of, my_rank)
+        my_bytes = sum(int(lens[int(r)]) + 64 for r in mine)
+        n_b = max(1, -(-my_bytes // 0xF0000000))
+        if n_b == 1:
+            return shard_of, [mine]
+        sub = capi.shard_plan([lens[int(r)] for r in mine], n_b)
+        return shard_of, [mine[capi.shard_records(sub, b)] for b in range(n_b)]
+
+    shard_of, my_batches = plan_batches(lengths, world, rank)
+    dbs = [build_resident(ctx, capi, lengths, recs, seed_bytes, feats) for recs in my_batches]
+    my_bases = int(sum(lengths[int(r)] for recs in my_batches for r in recs))
+    total_bytes = int(sum(Lc.corn_gpu_dbatch_bytes(db) for db in dbs))
+
     wins_s, tim_s = capi.Windows(), capi.Timing()
     p_wins, p_tim = C.byref(wins_s), C.byref(tim_s)
 
-    def step():
+    def step_on(batches):
         # resident batch, results stay on the device: telofind_dev(out=NULL) returns without a host sync
-        # and the fused telowin(hits=NULL) call is the step's single synchronisation point (it brings
+        # and the fused telowin(hits=NULL) call is the batch's single synchronisation point (it brings
         # the passing windows back to pinned host memory); last_timing then covers both calls
         # (scan_ms = k_telofind_scan, post_ms = every other kernel of the step).  Plain ctypes calls
         # on preallocated structs keep the harness's own per-step overhead to a few microseconds.
-        rc = Lc.corn_gpu_telofind_dev(ctx.ctx, db, b"TTAGGG", None)
-        if rc == 0:
-            rc = Lc.corn_gpu_telowin(ctx.ctx, None, None, THR, p_wins)
-        if rc != 0:
-            capi._check(ctx.ctx, rc, "fused step")
-        n = wins_s.n_win
-        Lc.corn_gpu_windows_free(p_wins)
-        Lc.corn_gpu_last_timing(ctx.ctx, p_tim)
-        return tim_s, n
+        scan = post = 0.0
+        out_b = n = 0
+        for db in batches:
+            rc = Lc.corn_gpu_telofind_dev(ctx.ctx, db, b"TTAGGG", None)
+            if rc == 0:
+                rc = Lc.corn_gpu_telowin(ctx.ctx, None, None, THR, p_wins)
+            if rc != 0:
+                capi._check(ctx.ctx, rc, "fused step")
+            n += wins_s.n_win
+            Lc.corn_gpu_windows_free(p_wins)
+            Lc.corn_gpu_last_timing(ctx.ctx, p_tim)
+            scan += tim_s.scan_ms
+            post += tim_s.post_ms
+            out_b += tim_s.out_bytes
+        return scan, post, out_b, n
+
+    def timed_run(batches, steps, warmup, clocks=None):
+        for _ in range(max(3, warmup)):
+            step_on(batches)
+        barrier()
+        launches0 = ctx.total_launches()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        scan_ms, post_ms, out_bytes, n_win = [], [], 0, 0
+        barrier()
+        if clocks:
+            clocks.mark_begin()
+        ev0.record(stream)
+        for _ in range(steps):
+            sc, po, out_bytes, n_win = step_on(batches)
+            scan_ms.append(sc)
+            post_ms.append(po)
+        ev1.record(stream)
+        barrier()
+        if clocks:
+            clocks.mark_end()
+        return {"elapsed_ms": allmax(ev0.elapsed_time(ev1)), "launches": ctx.total_launches() - launches0,
+                "scan_ms": sum(scan_ms) / len(scan_ms), "post_ms": sum(post_ms) / len(post_ms), "out_bytes": int(out_bytes), "n_win": int(n_win)}
 
     clocks = Clocks(local)
     clocks.start()
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
-    launches0 = ctx.total_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scan_ms, post_ms, out_bytes, n_win = [], [], 0, 0
-    barrier()
-    clocks.mark_begin()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        tm, n_win = step()
-        scan_ms.append(tm.scan_ms)
-        post_ms.append(tm.post_ms)
-        out_bytes = tm.out_bytes
-    ev1.record(stream)
-    barrier()
-    clocks.mark_end()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = ctx.total_launches() - launches0
+    res = timed_run(dbs, args.steps, args.warmup, clocks)
     clk = clocks.stop()
+    elapsed_ms = res["elapsed_ms"]
+    value = float(n_bases_total) * args.steps / (elapsed_ms * 1e-3) / 1e9
 
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-    units = torch.tensor([float(n_bases) * args.steps], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(units, op=dist.ReduceOp.SUM)
-    elapsed_ms = float(t.item())
-    value = float(units.item()) / (elapsed_ms * 1e-3) / 1e9
-
-    peak, peak_src = load_peak()
-    scan_avg_ms = sum(scan_ms) / len(scan_ms)
-    runs_bytes = int(out_bytes)
-    achieved = (n_bases + runs_bytes) / (scan_avg_ms * 1e-3) / 1e9
-    traffic = load_traffic()
+    # roofline of the dominant kernel on this rank's shard (max over ranks of the kernel time: the slowest shard)
+    scan_avg_ms = res["scan_ms"]
+    achieved = (my_bases + res["out_bytes"]) / (scan_avg_ms * 1e-3) / 1e9
+    traffic = load_traffic() if wl == "c2" else None
+    step_ms = elapsed_ms / args.steps
     roofline = {"bound": "hbm", "kernel": "k_telofind_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": n_bases + runs_bytes, "kernel_ms": scan_avg_ms,
-                "post_kernels_ms": sum(post_ms) / len(post_ms),
+                "algorithmic_bytes_per_launch": my_bases + res["out_bytes"], "kernel_ms": scan_avg_ms,
+                "post_kernels_ms": res["post_ms"],
+                "step_frac": (allsum(my_bases + res["out_bytes"]) / world) / (step_ms * 1e-3) / 1e9 / peak,
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
                 "traffic_source": traffic.get("source") if traffic else None}
+    loads = None
+    if sharded:
+        per = [int(sum(lengths[int(r)] for r in capi.shard_records(shard_of, k))) for k in range(world)]
+        loads = {"bases_per_gpu": per, "imbalance": max(per) / (sum(per) / world)}
+        # the slowest rank's event-timed kernels bound the step: report them beside this rank's
+        roofline["kernel_ms_max_over_ranks"] = allmax(scan_avg_ms)
+        roofline["post_kernels_ms_max_over_ranks"] = allmax(res["post_ms"])
 
+    what = {"c2": "telofind(TTAGGG)+telowin(0.4, 99.9) on a synthetic 3.12 Gb T2T-like haploid assembly, 1 GPU",
+            "c3": f"telofind(TTAGGG)+telowin(0.4, 99.9) on ONE synthetic 6.2 Gb diploid assembly (48 contigs, N gaps) sharded over {world} GPU(s) by corn_shard_plan"}.get(wl, wl)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: telofind(TTAGGG)+telowin(0.4, 99.9) on a synthetic {n_bases / 1e9:.2f} Gb T2T-like haploid assembly per GPU",
-                       "contigs": len(lengths), "bases_per_gpu": n_bases, "hbm_bytes_per_gpu": total_bytes,
-                       "l2_policy": "input (3.1 GB) is far larger than the 126 MB L2: every step streams it from HBM",
-                       "windows_found": n_win, "parallelism": f"{world} independent shards, no collective",
-                       "host_numa_node": numa_node},
-            "roofline": roofline, "clocks": clk, "gpu_launches": int(launches)}
+            "config": {"workload": f"{wl}: {what}", "contigs": len(lengths), "bases": n_bases_total,
+                       "bases_this_rank": my_bases, "hbm_bytes_this_rank": total_bytes, "resident_batches_this_rank": len(dbs),
+                       "l2_policy": "every shard (>= 0.78 GB) is far larger than the 126 MB L2: every step streams it from HBM",
+                       "windows_found_this_rank": res["n_win"],
+                       "parallelism": (f"{world} record shards (corn_shard_plan, longest-first), no collective on the data path" if sharded else "1 GPU"),
+                       "shards": loads, "host_numa_node": numa_node,
+                       "strong_scaling_note": "N>1 lines all scan the same 6.2 Gb (c3); the N=1 line scans c2 (3.1 Gb) per the bench contract "
+                                              "and carries c3 on one GPU as c3_1gpu"},
+            "roofline": roofline, "clocks": clk, "gpu_launches": int(res["launches"])}
 
     if args.profile_only:
         if rank == 0:
             print(json.dumps(line), flush=True)
         return 0
 
-    # ---- sdust over the same resident assembly (BASELINE.json configs[3]); reported beside the headline ----
-    if not args.no_sdust and rank == 0:
-        ctx.sdust_dev(db)                      # warm-up: sizes the per-chunk interval slots
-        iv, _ = ctx.sdust_dev(db)
-        ts = ctx.timing()
-        line["sdust"] = {"workload": f"sdust -w 64 -t 20 on the same {n_bases / 1e9:.2f} Gb assembly", "bases": n_bases, "intervals": int(len(iv)),
-                         "kernel_ms": ts["scan_ms"], "post_ms": ts["post_ms"],
-                         "gbases_per_s_kernel": n_bases / (ts["scan_ms"] * 1e-3) / 1e9,
-                         "hbm_frac": (n_bases + 8 * len(iv)) / (ts["scan_ms"] * 1e-3) / 1e9 / peak,
+    td_obj = tempfile.TemporaryDirectory(prefix=f"corn_bench_{rank}_")
+    td = td_obj.name
+
+    # ---- sdust over the same resident shard (BASELINE.json configs[3]); aggregate = total bases / slowest rank ----
+    sd_results = []
+    if not args.no_sdust:
+        sd_ms = sd_post = 0.0
+        for db in dbs:
+            ctx.sdust_dev(db)                      # warm-up: sizes the per-chunk interval slots
+            iv, first = ctx.sdust_dev(db)
+            ts = ctx.timing()
+            sd_ms += ts["scan_ms"]
+            sd_post += ts["post_ms"]
+            sd_results.append((iv, first))
+        n_iv = int(allsum(sum(len(iv) for iv, _ in sd_results)))
+        sd_max = allmax(sd_ms)
+        line["sdust"] = {"workload": f"sdust -w 64 -t 20 on the same {n_bases_total / 1e9:.2f} Gb assembly ({world} GPU(s))", "bases": n_bases_total,
+                         "intervals": n_iv, "kernel_ms": sd_max, "post_ms": allmax(sd_post),
+                         "gbases_per_s_kernel": n_bases_total / (sd_max * 1e-3) / 1e9,
+                         "hbm_frac": (n_bases_total + 8 * n_iv) / world / (sd_max * 1e-3) / 1e9 / peak,
                          "bound": "instruction issue / shared memory (serial state machine per chunk), not HBM"}
 
+    # ---- N > 1: every rank checks one whole contig against the reference; rank 0 merges and runs telobreaks ----
+    if sharded and not args.no_check:
+        per_batch = []
+        for db in dbs:
+            runs = ctx.telofind_dev(db, "TTAGGG")
+            wins = ctx.telowin(THR)
+            per_batch.append((runs, wins))
+        recs0 = my_batches[0]
+        pick = int(np.argmin([lengths[int(r)] for r in recs0]))            # shortest contig of this rank's (first) batch
+        g = int(recs0[pick])
+        iv0, first0 = sd_results[0] if sd_results else ctx.sdust_dev(dbs[0])
+        ok, tf, tw, kind = check_contig_against_reference(ctx, capi, dbs[0], pick, names[g], lengths[g], per_batch[0][0], per_batch[0][1], iv0, first0, td)
+        all_ok = all(v for k, v in ok.items() if k != "lines")
+        checks = [None] * world
+        dist.all_gather_object(checks, {"rank": rank, "contig": names[g], "bases": int(lengths[g]), **ok,
+                                        "reference_telofind_s": tf, "reference_telowin_s": tw}, group=gloo)
+        line["parity_in_run"] = {"what": "one whole contig per GPU, byte for byte against " + ("oracle/_ref/cornetto (unmodified reference)" if kind == "reference" else "the oracle port"),
+                                 "all_identical": all(c["telofind"] and c["telowin"] and c["sdust"] for c in checks), "per_rank": checks}
+        if not args.no_cpu_baseline:
+            c0 = checks[0]
+            line["cpu_baseline"] = {"value": c0["bases"] / (c0["reference_telofind_s"] + c0["reference_telowin_s"]) / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": f"contig {c0['contig']} ({c0['bases'] / 1e6:.0f} Mb) of the same assembly, FASTA on tmpfs/disk, page-cache warm",
+                                    "telofind_s": c0["reference_telofind_s"], "telowin_s": c0["reference_telowin_s"]}
+        # gather the sparse results of every shard on rank 0 (gloo, host memory), merge into file order with the
+        # library's own merge, and call breaks on the whole assembly beside the reference's telobreaks
+        gathered = [None] * world
+        payload = {"runs": per_batch[0][0], "iv": sd_results[0][0] if sd_results else None, "first": sd_results[0][1] if sd_results else None}
+        dist.gather_object(payload, gathered if rank == 0 else None, dst=0, group=gloo)
+        if rank == 0 and sd_results:
+            t0 = time.perf_counter()
+            runs_all = capi.shard_merge_runs([p["runs"] for p in gathered], shard_of)
+            iv_all, first_all = capi.shard_merge_intervals([(p["iv"], p["first"]) for p in gathered], shard_of)
+            t_merge = time.perf_counter() - t0
+            bnames = [n.encode() for n in names]
+            long_runs = runs_all[(runs_all["end"] - runs_all["start"]) >= 24]     # telobreaks ignores shorter runs (MIN_TEL, src/telomere_breaks.c:10,99)
+            tel = os.path.join(td, "asm.telomere"); open(tel, "wb").write(fmt_telofind(long_runs, bnames, lengths))
+            sdf = os.path.join(td, "asm.sdust"); open(sdf, "wb").write(fmt_sdust(iv_all, first_all, bnames))
+            lens = os.path.join(td, "asm.lens"); open(lens, "wb").write(b"".join(b"%s\t%d\n" % (n, L) for n, L in zip(bnames, lengths)))
+            ours = os.path.join(ROOT, "cornetto_b200", "bin", "cornetto")
+            binary, kind = ref_binary()
+            t0 = time.perf_counter()
+            a = subprocess.run([ours, "telobreaks", lens, sdf, tel], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+            t1 = time.perf_counter()
+            b = subprocess.run([binary, "telobreaks", lens, sdf, tel], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+            t2 = time.perf_counter()
+            line["telobreaks"] = {"what": "shards merged into file order (corn_shard_merge_*), then `cornetto telobreaks` on the whole assembly (host join) beside the reference's",
+                                  "runs_total": int(len(runs_all)), "runs_ge_24bp": int(len(long_runs)), "sdust_intervals": int(len(iv_all)),
+                                  "merge_s": t_merge, "ours_s": t1 - t0, "reference_s": t2 - t1, "breaks": a.count(b"\n"), "identical": a == b}
+
+    # ---- N = 1: the c3 job (6.2 Gb, two resident batches) on this one GPU: the base of the strong-scaling curve ----
+    if not sharded and wl == "c2" and not args.no_c3:
+        l3 = workload_lengths("c3")
+        f3 = make_features(capi, l3, seed_feat, n_gaps=3)
+        _, b3 = plan_batches(l3, 1, 0)
+        db3 = [build_resident(ctx, capi, l3, recs, seed_bytes, f3) for recs in b3]
+        r3 = timed_run(db3, min(args.steps, 50), 3)
+        line["c3_1gpu"] = {"workload": "c3 (6.2 Gb diploid, 48 contigs, N gaps) on ONE GPU: the N>1 lines' job unsharded", "bases": int(sum(l3)),
+                           "resident_batches": len(db3), "ms_per_step": r3["elapsed_ms"] / min(args.steps, 50),
+                           "value": float(sum(l3)) * min(args.steps, 50) / (r3["elapsed_ms"] * 1e-3) / 1e9, "unit": UNIT,
+                           "scan_ms": r3["scan_ms"], "post_kernels_ms": r3["post_ms"]}
+        for d in db3:
+            ctx.free(d)
+
     # ---- device-side FASTA parsing (SURVEY.md §8f rank 1): 60-column text of a bounded sample -> resident batch ----
-    if not args.no_ingest and rank == 0:
+    if not args.no_ingest and rank == 0 and not sharded:
         line["ingest"] = bench_ingest(ctx, peak)
 
-    # ---- e2e: host buffers through the public C ABI (H2D + kernels + D2H inside the timed region) ----
-    L = ctx.L
-    hb = C.c_void_p()
-    capi._check(None, L.corn_hbatch_create(total_bytes + 64, len(lengths), C.byref(hb)), "corn_hbatch_create")
-    capi._check(None, L.corn_hbatch_pin(hb), "corn_hbatch_pin")
-    cur = L.corn_hbatch_cursor(hb)
-    capi._check(ctx.ctx, L.corn_bench_download_all(ctx.ctx, db, cur), "download")
-    for Lr in lengths:                           # same layout rule => same offsets; padding is already zero
-        capi._check(None, L.corn_hbatch_commit(hb, Lr), "commit")
-    view = capi.Batch()
-    L.corn_hbatch_view(hb, C.byref(view))
+    # ---- e2e: FASTA text in page-locked host memory through the public C ABI: ingest (H2D + device parse) +
+    #      telofind + telowin, results copied back.  Every rank does its own shard. ----
+    seqs = []
+    for db, recs in zip(dbs, my_batches):
+        flat = ctx.download_all(db)
+        off = 0
+        for r in recs:
+            Lr = int(lengths[int(r)])
+            seqs.append((names[int(r)], flat[off:off + Lr]))
+            off += (Lr + 1 + 31) // 32 * 32
+    for db in dbs:
+        ctx.free(db)                              # make room: the e2e path builds its own resident copy
+    # text blocks of at most ~3.7 GB (what one corn_gpu_ingest call takes), cut at record boundaries
+    blocks, cur, cur_b = [], [], 0
+    for nm, a in seqs:
+        if cur and cur_b + len(a) > 3_600_000_000:
+            blocks.append(cur); cur, cur_b = [], 0
+        cur.append((nm, a)); cur_b += len(a)
+    if cur:
+        blocks.append(cur)
+    texts = [fasta_text(b) for b in blocks]
+    for t in texts:
+        Lc.corn_gpu_host_register(t.ctypes.data, len(t))
     hits = capi.Hits()
 
     def e2e_step():
-        capi._check(ctx.ctx, L.corn_gpu_telofind(ctx.ctx, C.byref(view), b"TTAGGG", C.byref(hits)), "corn_gpu_telofind")
-        nrun = hits.n_run
-        L.corn_gpu_hits_free(C.byref(hits))
-        w = ctx.telowin(THR)
-        return nrun, len(w)
+        nrun = nwin = 0
+        for t in texts:
+            ing = ctx.ingest(t, final=True, keep_db=True)
+            capi._check(ctx.ctx, Lc.corn_gpu_telofind_dev(ctx.ctx, ing["db"], b"TTAGGG", C.byref(hits)), "corn_gpu_telofind_dev")
+            nrun += hits.n_run
+            Lc.corn_gpu_hits_free(C.byref(hits))
+            nwin += len(ctx.telowin(THR))
+            ctx.free(ing["db"])
+        return nrun, nwin
 
-    ctx.free(db)                                  # make room: the e2e path uploads its own copy
     e2e_step()
     barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.e2e_steps):
         nrun, nwin = e2e_step()
     ev1.record(stream)
     barrier()
-    e2e_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = float(n_bases) * world * args.e2e_steps / (float(t.item()) * 1e-3) / 1e9
-    line["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total_bytes,
-                   "d2h_bytes_per_step": int(nrun) * 16 + int(nwin) * 16, "steps": args.e2e_steps,
-                   "ms_per_step": float(t.item()) / args.e2e_steps,
-                   "bound": "PCIe: the pinned H2D copy of 1 byte per base dominates (the scan kernel itself runs ~100x faster)"}
+    t_wall = time.perf_counter() - t_wall0
+    e2e_ms = allmax(ev0.elapsed_time(ev1))                 # device time, max over ranks (the host wall clock is reported beside it)
+    text_bytes = int(sum(len(t) for t in texts))
+    line["e2e"] = {"value": float(n_bases_total) * args.e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": int(allsum(text_bytes)), "d2h_bytes_per_step": int(allsum(int(nrun) * 16 + int(nwin) * 16)),
+                   "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps, "host_wall_ms_per_step": allmax(t_wall * 1e3) / args.e2e_steps,
+                   "what": "FASTA text (60 columns) in page-locked host memory -> corn_gpu_ingest (PCIe + device parse) -> corn_gpu_telofind_dev -> corn_gpu_telowin -> runs + windows on the host",
+                   "bound": "PCIe: the H2D copy of the text (1.02 bytes per base) dominates; parse + scan run ~30x faster"}
+    for t in texts:
+        Lc.corn_gpu_host_unregister(t.ctypes.data)
 
-    # ---- CPU baseline: the reference binary, one thread (as shipped), bounded sample ----
-    if not args.no_cpu_baseline and rank == 0 and world == 1:
+    # ---- CPU baseline + the drop-in binary from file to text (N = 1) ----
+    if not args.no_cpu_baseline and rank == 0 and not sharded:
         binary, kind = ref_binary()
-        seq = np.frombuffer((C.c_uint8 * total_bytes).from_address(cur), dtype=np.uint8)
-        sample, off, got = [], 0, 0
-        budget = 600_000_000 if args.workload == "c2" else 10**12
-        for i, Lr in enumerate(lengths):
-            if got < budget and (got + Lr <= budget or not sample):
-                sample.append((f"chr{i + 1}", seq[off:off + Lr]))
-                got += Lr
-            off += (Lr + 1 + 31) // 32 * 32
+        sample, got = [], 0
+        budget = 600_000_000 if wl == "c2" else 10**12
+        for nm, a in seqs:
+            if got < budget and (got + len(a) <= budget or not sample):
+                sample.append((nm, a))
+                got += len(a)
         ours = os.path.join(ROOT, "cornetto_b200", "bin", "cornetto")
-        with tempfile.TemporaryDirectory(prefix="corn_cpu_") as td:
-            fa = os.path.join(td, "sample.fa")
-            write_fasta(fa, sample)
-            tf, tw = cpu_pipeline_seconds(binary, fa, td)
-            # the drop-in binary on the same file, same two commands (process start, CUDA start-up, file read,
-            # device-side parsing, scan and text output all inside the wall clock)
-            runs3 = [cpu_pipeline_seconds(ours, fa, td) for _ in range(3)]      # CUDA start-up of a fresh process is noisy: best of 3
-            of, ow = min(r[0] for r in runs3), min(r[1] for r in runs3)
-            cli = {"sample": {"bases": int(got), "telofind_s": of, "telowin_s": ow, "gbases_per_s": got / (of + ow) / 1e9,
-                              "reference_telofind_s": tf, "reference_telowin_s": tw}}
-            if not args.no_cli_full:
-                full = os.path.join(td, "full.fa")
-                allc, off2 = [], 0
-                for i, Lr in enumerate(lengths):
-                    allc.append((f"chr{i + 1}", seq[off2:off2 + Lr]))
-                    off2 += (Lr + 1 + 31) // 32 * 32
-                write_fasta(full, allc)
-                runs2 = [cpu_pipeline_seconds(ours, full, td) for _ in range(2)]
-                ff, fw = min(r[0] for r in runs2), min(r[1] for r in runs2)
-                cli["full"] = {"bases": int(n_bases), "fasta_bytes": os.path.getsize(full), "telofind_s": ff, "telowin_s": fw,
-                               "gbases_per_s": n_bases / (ff + fw) / 1e9}
+        fa = os.path.join(td, "sample.fa")
+        write_fasta(fa, sample)
+        tf, tw = cpu_pipeline_seconds(binary, fa, td)
+        # the drop-in binary on the same file, same two commands (process start, CUDA start-up, file read,
+        # device-side parsing, scan and text output all inside the wall clock)
+        runs3 = [cpu_pipeline_seconds(ours, fa, td) for _ in range(3)]      # CUDA start-up of a fresh process is noisy: best of 3
+        of, ow = min(r[0] for r in runs3), min(r[1] for r in runs3)
+        cli = {"sample": {"bases": int(got), "telofind_s": of, "telowin_s": ow, "gbases_per_s": got / (of + ow) / 1e9,
+                          "reference_telofind_s": tf, "reference_telowin_s": tw}}
         line["cpu_baseline"] = {"value": got / (tf + tw) / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
                                 "sample": f"{len(sample)} contigs ({got / 1e6:.0f} Mb) of the same assembly, FASTA on tmpfs/disk, page-cache warm",
                                 "telofind_s": tf, "telowin_s": tw}
+        if not args.no_cli_full:
+            full = os.path.join(td, "full.fa")
+            write_fasta(full, seqs)
+            runs2 = [cpu_pipeline_seconds(ours, full, td) for _ in range(2)]
+            ff, fw = min(r[0] for r in runs2), min(r[1] for r in runs2)
+            cli["full"] = {"bases": int(n_bases_total), "fasta_bytes": os.path.getsize(full), "telofind_s": ff, "telowin_s": fw,
+                           "gbases_per_s": n_bases_total / (ff + fw) / 1e9}
+            line["e2e_from_file"] = {"value": n_bases_total / (ff + fw) / 1e9, "unit": UNIT,
+                                     "what": "`cornetto telofind full.fa > x.telomere` + `cornetto telowin x.telomere 99.9 0.4`: FASTA file (page cache) to text, "
+                                             "process and CUDA start-up included; best of 2",
+                                     "telofind_s": ff, "telowin_s": fw,
+                                     "reference_same_sample_gbases_per_s": got / (tf + tw) / 1e9,
+                                     "bound": "CUDA start-up of two fresh processes, the read(2) of 3.2 GB, the staged H2D copy and text formatting; kernels are <1 % of it"}
         cli["what"] = ("wall clock of the drop-in `cornetto telofind` + `cornetto telowin` commands on FASTA files (parse included), "
                        "bound by CUDA start-up (0.4-2 s per process on these boxes), the file read and text formatting")
         line["cli"] = cli
-    L.corn_hbatch_destroy(hb)
     if rank == 0:
         print(json.dumps(line), flush=True)
+    td_obj.cleanup()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -68,7 +68,8 @@ SYMBOLS = [
     "sdust", "sdust_buf_init", "sdust_buf_destroy", "sdust_core",
     "corn_gpu_ingest", "corn_gpu_ingest_free", "corn_gpu_host_register", "corn_gpu_host_unregister",
     "corn_gpu_last_timing", "corn_gpu_total_launches",
-    "corn_bench_fill_random", "corn_bench_apply_features", "corn_bench_download_all", "corn_bench_flush_l2",
+    "corn_shard_plan", "corn_shard_local_index", "corn_shard_merge_runs", "corn_shard_merge_intervals",
+    "corn_bench_fill_random", "corn_bench_fill_random_rec", "corn_bench_apply_features", "corn_bench_download_all", "corn_bench_flush_l2",
 ]
 
 _lib = None
@@ -145,7 +146,12 @@ def load() -> C.CDLL:
     L.corn_gpu_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.corn_gpu_total_launches.argtypes = [vp]
     L.corn_gpu_total_launches.restype = u64
+    L.corn_shard_plan.argtypes = [vp, u32, u32, vp]
+    L.corn_shard_local_index.argtypes = [vp, u32, u32, vp, vp]
+    L.corn_shard_merge_runs.argtypes = [vp, vp, vp, u32, u32, vp]
+    L.corn_shard_merge_intervals.argtypes = [vp, vp, vp, u32, u32, vp, vp]
     L.corn_bench_fill_random.argtypes = [vp, vp, u64]
+    L.corn_bench_fill_random_rec.argtypes = [vp, vp, u64, vp]
     L.corn_bench_apply_features.argtypes = [vp, vp, vp, u32]
     L.corn_bench_download_all.argtypes = [vp, vp, vp]
     L.corn_bench_flush_l2.argtypes = [vp]
@@ -155,6 +161,49 @@ def load() -> C.CDLL:
 
 class CornError(RuntimeError):
     pass
+
+
+# ---- record sharding over several GPUs (csrc/shard.cu; pure host arithmetic, no device needed) -----------
+def shard_plan(lengths, n_shards: int) -> np.ndarray:
+    """corn_shard_plan: shard_of[r] for every record (longest first onto the least loaded shard)."""
+    L = load()
+    lens = np.ascontiguousarray(lengths, dtype=np.uint32)
+    out = np.zeros(len(lens), dtype=np.uint32)
+    _check(None, L.corn_shard_plan(lens.ctypes.data if len(lens) else None, len(lens), n_shards, out.ctypes.data if len(lens) else None), "corn_shard_plan")
+    return out
+
+
+def shard_records(shard_of, shard: int) -> np.ndarray:
+    """global record numbers of one shard, in file order (= the order of the records inside its batch)."""
+    return np.flatnonzero(np.asarray(shard_of) == shard).astype(np.uint32)
+
+
+def shard_merge_runs(per_shard_runs, shard_of) -> np.ndarray:
+    """corn_shard_merge_runs: per-shard run lists (rec = index inside the shard) -> one list in file order."""
+    L = load()
+    shard_of = np.ascontiguousarray(shard_of, dtype=np.uint32)
+    parts = [np.ascontiguousarray(r, dtype=RUN_DTYPE) for r in per_shard_runs]
+    n = np.array([len(p) for p in parts], dtype=np.uint64)
+    ptrs = (C.c_void_p * len(parts))(*[p.ctypes.data if len(p) else None for p in parts])
+    out = np.zeros(int(n.sum()), dtype=RUN_DTYPE)
+    _check(None, L.corn_shard_merge_runs(ptrs, n.ctypes.data, shard_of.ctypes.data if len(shard_of) else None, len(shard_of), len(parts),
+                                         out.ctypes.data if len(out) else None), "corn_shard_merge_runs")
+    return out
+
+
+def shard_merge_intervals(per_shard, shard_of):
+    """corn_shard_merge_intervals: per-shard (iv, rec_first) -> (iv, rec_first) in file order."""
+    L = load()
+    shard_of = np.ascontiguousarray(shard_of, dtype=np.uint32)
+    ivs = [np.ascontiguousarray(a, dtype=np.uint64) for a, _ in per_shard]
+    firsts = [np.ascontiguousarray(b, dtype=np.uint64) for _, b in per_shard]
+    p_iv = (C.c_void_p * len(ivs))(*[a.ctypes.data if len(a) else None for a in ivs])
+    p_first = (C.c_void_p * len(firsts))(*[b.ctypes.data for b in firsts])
+    out = np.zeros(sum(len(a) for a in ivs), dtype=np.uint64)
+    first = np.zeros(len(shard_of) + 1, dtype=np.uint64)
+    _check(None, L.corn_shard_merge_intervals(p_iv, p_first, shard_of.ctypes.data if len(shard_of) else None, len(shard_of), len(ivs),
+                                              out.ctypes.data if len(out) else None, first.ctypes.data), "corn_shard_merge_intervals")
+    return out, first
 
 
 def _check(ctx, rc, what):
@@ -343,8 +392,12 @@ class Context:
         return int(self.L.corn_gpu_total_launches(self.ctx))
 
     # ---- bench helpers (include/corn_bench.h) ------------------------------------------------------
-    def fill_random(self, db, seed: int):
-        _check(self.ctx, self.L.corn_bench_fill_random(self.ctx, db, seed), "corn_bench_fill_random")
+    def fill_random(self, db, seed: int, rec_id=None):
+        if rec_id is None:
+            _check(self.ctx, self.L.corn_bench_fill_random(self.ctx, db, seed), "corn_bench_fill_random")
+        else:
+            ids = np.ascontiguousarray(rec_id, dtype=np.uint32)
+            _check(self.ctx, self.L.corn_bench_fill_random_rec(self.ctx, db, seed, ids.ctypes.data), "corn_bench_fill_random_rec")
 
     def apply_features(self, db, feats: np.ndarray):
         feats = np.ascontiguousarray(feats, dtype=FEAT_DTYPE)

@@ -14,15 +14,19 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x)
 }
 
 // one thread per 16-byte block of the batch
+// rec_id == NULL: keyed by (seed, block index in the batch).  rec_id != NULL: keyed by (seed, rec_id[record], block
+// index inside the record), so a record has the same bytes whichever batch -- whichever GPU's shard -- it is in.
 __global__ void __launch_bounds__(256) k_fill_random(uint8_t *seq, uint64_t n_blocks16, const uint32_t *__restrict__ rec_off,
-                                                     const uint32_t *__restrict__ rec_len, uint32_t n_rec, uint64_t seed)
+                                                     const uint32_t *__restrict__ rec_len, uint32_t n_rec, uint64_t seed,
+                                                     const uint32_t *__restrict__ rec_id)
 {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_blocks16) return;
     const uint32_t pos = (uint32_t)(g << 4);
     const uint32_t rec = corn_upper_bound(rec_off, n_rec, pos) - 1;
     const uint32_t r0 = rec_off[rec], r1 = r0 + rec_len[rec];
-    uint64_t h = mix64(seed ^ (g * 0xD1342543DE82EF95ull));
+    uint64_t h = rec_id ? mix64(mix64(seed ^ ((uint64_t)rec_id[rec] << 40)) ^ ((uint64_t)((pos - r0) >> 4) * 0xD1342543DE82EF95ull))
+                        : mix64(seed ^ (g * 0xD1342543DE82EF95ull));
     uint32_t w[4] = { 0, 0, 0, 0 };
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -72,7 +76,22 @@ extern "C" int corn_bench_fill_random(corn_ctx_t *ctx, corn_dbatch_t *db, uint64
     CORN_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t nb = db->total_bytes / 16;
     if (nb == 0 || db->n_rec == 0) return CORN_OK;
-    k_fill_random<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(db->d_seq, nb, db->d_rec_off, db->d_rec_len, db->n_rec, seed);
+    k_fill_random<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(db->d_seq, nb, db->d_rec_off, db->d_rec_len, db->n_rec, seed, NULL);
+    CORN_LAUNCH_CHECK(ctx);
+    CORN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CORN_OK;
+}
+
+extern "C" int corn_bench_fill_random_rec(corn_ctx_t *ctx, corn_dbatch_t *db, uint64_t seed, const uint32_t *rec_id)
+{
+    if (!ctx || !db || !rec_id) return CORN_E_ARG;
+    CORN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nb = db->total_bytes / 16;
+    if (nb == 0 || db->n_rec == 0) return CORN_OK;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->wins, (size_t)db->n_rec * sizeof(uint32_t)));
+    CORN_CUDA(ctx, cudaMemcpyAsync(ctx->wins.p, rec_id, (size_t)db->n_rec * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    k_fill_random<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(db->d_seq, nb, db->d_rec_off, db->d_rec_len, db->n_rec, seed,
+                                                                         (const uint32_t *)ctx->wins.p);
     CORN_LAUNCH_CHECK(ctx);
     CORN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CORN_OK;

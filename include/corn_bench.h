@@ -28,6 +28,9 @@ typedef struct corn_feature {
 /* every base of every record <- uniform A/C/G/T from a counter-based generator keyed by
  * (seed, byte position in the batch); padding stays 0x00. */
 int corn_bench_fill_random(corn_ctx_t *ctx, corn_dbatch_t *db, uint64_t seed);
+/* same, keyed by (seed, rec_id[record], position inside the record): a record gets the same bytes whichever batch
+ * (whichever GPU's shard) holds it.  rec_id: [n_rec] host array of global record numbers. */
+int corn_bench_fill_random_rec(corn_ctx_t *ctx, corn_dbatch_t *db, uint64_t seed, const uint32_t *rec_id);
 /* overlays features; the features of ONE call are applied concurrently (overlapping ones race,
  * any outcome being a valid sequence); successive calls are ordered. */
 int corn_bench_apply_features(corn_ctx_t *ctx, corn_dbatch_t *db, const corn_feature_t *feat, uint32_t n_feat);

@@ -222,6 +222,26 @@ void corn_gpu_ingest_free(corn_ingest_t *ing);
 int  corn_gpu_host_register(void *p, uint64_t bytes);
 void corn_gpu_host_unregister(void *p);
 
+/* ---- several GPUs: record sharding (csrc/shard.cu; host arithmetic only, usable without a device) ----------
+ * The reference is one thread in one address space (records scanned and printed in file order,
+ * src/find_telomere.c:101-105).  Here the unit of distribution is the record: no scan looks across a record
+ * boundary, so shards are independent -- no halo, no collective -- and results only have to be put back into
+ * file order.  Records are never cut (a single-contig input stays on one GPU).
+ *   corn_shard_plan         shard_of[r] for every record: longest first onto the least loaded shard
+ *                           (deterministic: every process of a job derives the same plan from the lengths);
+ *   corn_shard_local_index  local[r] = index of record r inside its shard's batch (file order is kept inside
+ *                           a shard), count[s] = records of shard s;
+ *   corn_shard_merge_runs / corn_shard_merge_intervals
+ *                           per-shard results (rec = index inside the shard) -> one list in file order, i.e.
+ *                           exactly what a single corn_gpu_telofind / corn_gpu_sdust over all records returns.
+ *                           out must hold the sum of the per-shard counts (out_first: n_rec + 1). */
+int corn_shard_plan(const uint32_t *length, uint32_t n_rec, uint32_t n_shards, uint32_t *shard_of);
+int corn_shard_local_index(const uint32_t *shard_of, uint32_t n_rec, uint32_t n_shards, uint32_t *local, uint32_t *count);
+int corn_shard_merge_runs(const corn_run_t *const *runs, const uint64_t *n_run, const uint32_t *shard_of,
+                          uint32_t n_rec, uint32_t n_shards, corn_run_t *out);
+int corn_shard_merge_intervals(const uint64_t *const *iv, const uint64_t *const *rec_first, const uint32_t *shard_of,
+                               uint32_t n_rec, uint32_t n_shards, uint64_t *out_iv, uint64_t *out_first);
+
 /* ---- measurement hooks (CUDA events on the context's stream; bench.py reads them) ---------- */
 typedef struct corn_timing {
     float h2d_ms;       /* host->device copies of the last call */

@@ -18,7 +18,7 @@ db = ctx.alloc(lengths)
 ctx.fill_random(db, 42)
 mode = sys.argv[3] if len(sys.argv) > 3 else "full"     # full | plain (random only) | notelo (no telomeric ends)
 if mode != "plain":
-    tand, lower = bench.make_features(capi, lengths, 7)
+    tand, lower, _ = bench.make_features(capi, lengths, 7)
     if mode == "notelo":
         tand = tand[tand["len"] < 3000]
     ctx.apply_features(db, tand)

@@ -1,9 +1,11 @@
 """Full-size parity on the GPU box (BASELINE.json configs[1] and [3]): the 3.1 Gb synthetic
 T2T-like assembly that bench.py scans, generated in HBM.
 
-The oracle cannot scan 3.1 Gb inside a test budget, so parity at this size is checked by
- - exact comparison against the oracle on whole contigs downloaded from the device
-   (the two shortest, ~96 Mb, plus the ends of the longest one),
+The assembly carries N gaps (three per contig, 1..50 000 bases: BASELINE.md's "N-gap variant for exactness"), so the
+stale-window behaviour of sdust at non-ACGT bytes is exercised at full size.  The oracle cannot scan all 3.1 Gb inside a
+test budget, so parity at this size is checked by
+ - exact comparison against the oracle on WHOLE contigs downloaded from the device: the longest (248 Mb), the
+   shortest and a mid-sized one (~0.4 Gb together), for telofind and for sdust,
  - size-independent properties over ALL results: every run is a tandem repeat of the motif and
    is maximal (checked on the bytes of a random sample of 2000 runs), runs are sorted and disjoint
    per (record, strand), strand-0 runs precede strand-1 runs per record, fused == general telowin,
@@ -31,10 +33,12 @@ def world():
     ctx = capi.Context(0)
     lengths = bench.workload_lengths(os.environ.get("CORN_TEST_WORKLOAD", "c2"))
     db = ctx.alloc(lengths)
-    ctx.fill_random(db, 42)
-    tand, lower = bench.make_features(capi, lengths, 7)
+    ctx.fill_random(db, 42, rec_id=np.arange(len(lengths), dtype=np.uint32))
+    tand, lower, gaps = bench.make_features(capi, lengths, 7, n_gaps=3)
+    assert len(gaps) >= 2 * len(lengths)
     ctx.apply_features(db, tand)
     ctx.apply_features(db, lower)
+    ctx.apply_features(db, gaps)
     yield ctx, capi, db, lengths, bench
     ctx.free(db)
     ctx.close()
@@ -53,9 +57,9 @@ def test_fullsize_telofind_telowin(world):
     assert (start[1:][same] > end[:-1][same]).all() or (start[1:][same] >= end[:-1][same]).all()
     assert ((end - start) % 6 == 0).all() and (end > start).all()
     assert (end <= np.asarray(lengths, dtype=np.int64)[rec]).all()
-    # exact vs the oracle on the two shortest contigs
+    # exact vs the oracle on three whole contigs: the longest, the shortest and a mid-sized one
     order = np.argsort(lengths)
-    for r in order[:2]:
+    for r in (order[-1], order[0], order[len(order) // 2]):
         seq = ctx.download(db, int(r), int(lengths[r]))
         want = oracle_telofind([seq], "TTAGGG")
         got = as_rows(runs[runs["rec"] == r])
@@ -111,8 +115,9 @@ def test_fullsize_sdust(world):
         a, b = int(first[r]), int(first[r + 1])
         assert (s[a + 1:b] > f[a:b - 1]).all()          # sorted, disjoint, not touching
     order = np.argsort(lengths)
-    r = int(order[0])
-    seq = ctx.download(db, r, int(lengths[r]))
-    wiv, _ = oracle_sdust([seq], 20, 64)
-    got = iv[int(first[r]):int(first[r + 1])]
-    assert len(got) == len(wiv) and (got == wiv).all()
+    for r in (int(order[-1]), int(order[0]), int(order[len(order) // 2])):      # whole contigs, N gaps included
+        seq = ctx.download(db, r, int(lengths[r]))
+        assert (seq == ord("N")).sum() > 0 or lengths[r] <= 200_000
+        wiv, _ = oracle_sdust([seq], 20, 64)
+        got = iv[int(first[r]):int(first[r + 1])]
+        assert len(got) == len(wiv) and (got == wiv).all(), f"contig {r}"

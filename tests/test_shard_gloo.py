@@ -2,7 +2,9 @@
 
 The scan itself needs a GPU, so here every rank runs the ORACLE on its shard (checker code used
 as a stand-in for the device call -- test infrastructure only); what is under test is
-cornetto_b200/shard.py: byte-balanced assignment, one gather of sparse results, file-order merge."""
+the library's record sharding (csrc/shard.cu through ctypes: corn_shard_plan, corn_shard_merge_runs,
+corn_shard_merge_intervals -- the code bench.py --gpus N runs on): byte-balanced assignment, one gather of the sparse
+results, file-order merge.""" 
 import os
 import socket
 import sys
@@ -18,13 +20,14 @@ import numpy as np
 import torch.distributed as dist
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
 import synth
-from cornetto_b200 import shard
+from cornetto_b200 import capi
 from cornetto_b200.capi import RUN_DTYPE
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 recs = synth.assembly(77, [90_000, 5_000, 60_000, 0, 33, 20_000, 41_000, 7, 15_000], n_gaps=2, telo=(50, 300), microsat_per_mb=2000.0)
 lengths = [len(s) for _, s in recs]
-plan = shard.plan_shards(lengths, world)
+shard_of = capi.shard_plan(lengths, world)
+plan = [[int(x) for x in capi.shard_records(shard_of, r)] for r in range(world)]
 L = C.CDLL(os.path.join(sys.argv[1], "oracle", "_build", "liboracle.so"))
 class Run(C.Structure):
     _fields_ = [("strand", C.c_uint32), ("start", C.c_uint64), ("end", C.c_uint64)]
@@ -45,8 +48,8 @@ mine = scan(plan[rank])
 gathered = [None] * world
 dist.gather_object(mine, gathered if rank == 0 else None, dst=0)
 if rank == 0:
-    runs = shard.merge_runs([g[0] for g in gathered], plan, len(recs))
-    iv, first = shard.merge_intervals([g[1] for g in gathered], plan, len(recs))
+    runs = capi.shard_merge_runs([g[0] for g in gathered], shard_of)
+    iv, first = capi.shard_merge_intervals([g[1] for g in gathered], shard_of)
     want_runs, (want_iv, want_first) = scan(list(range(len(recs))))
     assert sorted(sum(plan, [])) == list(range(len(recs)))
     loads = [sum(lengths[i] for i in p) for p in plan]
@@ -78,11 +81,23 @@ def test_world2_shard_and_gather(tmp_path, oracle_bin):
 
 
 def test_plan_is_balanced_and_complete():
-    from cornetto_b200 import shard
+    from cornetto_b200 import capi
     sys.path.insert(0, ROOT)
     import bench
-    for world in (1, 2, 4, 8):
-        plan = shard.plan_shards(bench.CHM13, world)
-        assert sorted(sum(plan, [])) == list(range(len(bench.CHM13)))
-        loads = [sum(bench.CHM13[i] for i in p) for p in plan]
-        assert max(loads) / (sum(loads) / world) < 1.08
+    for lengths, bound in ((bench.CHM13, 1.08), (bench.workload_lengths("c3"), 1.03)):
+        for world in (1, 2, 4, 8):
+            shard_of = capi.shard_plan(lengths, world)
+            assert (capi.shard_plan(lengths, world) == shard_of).all()                 # deterministic
+            plan = [list(capi.shard_records(shard_of, r)) for r in range(world)]
+            assert sorted(int(x) for p in plan for x in p) == list(range(len(lengths)))
+            loads = [sum(lengths[i] for i in p) for p in plan]
+            assert max(loads) / (sum(loads) / world) < bound, (world, loads)
+
+
+def test_merge_rejects_unordered_lists():
+    from cornetto_b200 import capi
+    shard_of = capi.shard_plan([10, 20, 30], 2)
+    bad = np.zeros(2, dtype=capi.RUN_DTYPE)
+    bad["rec"] = [1, 0]                                                               # not in record order
+    with pytest.raises(capi.CornError):
+        capi.shard_merge_runs([bad, bad[:0]], shard_of)
