@@ -99,7 +99,7 @@ extern "C" void corn_gpu_destroy(corn_ctx_t *ctx)
     if (ctx->spare_base) cudaFree(ctx->spare_base);
     corn_dbuf *bufs[] = { &ctx->cand, &ctx->tile_tab, &ctx->events, &ctx->runs, &ctx->misc, &ctx->scan_tmp,
                           &ctx->bins, &ctx->bitmap, &ctx->wins, &ctx->sd_slots, &ctx->sd_out, &ctx->sd_tab,
-                          &ctx->ing_text, &ctx->ing_tab, &ctx->ing_lines, &ctx->ing_rec };
+                          &ctx->ing_text, &ctx->ing_tab, &ctx->ing_lines, &ctx->ing_rec, &ctx->ranks, &ctx->hot };
     for (size_t i = 0; i < sizeof bufs / sizeof bufs[0]; ++i) dbuf_free(bufs[i]);
     for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->own_stream);

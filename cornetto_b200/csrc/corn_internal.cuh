@@ -47,6 +47,16 @@ struct corn_dbatch {
 
 // telowin geometry: a record owns ceil(len/200) bins plus four zero bins so that a window can always read five
 static inline __host__ __device__ uint32_t corn_nbins_of(uint32_t len) { return (len + 199u) / 200u + 4u; }
+// A full window (1000 bases = five bins) that holds car marked bases has a bin with at least car / 5 of them.  The run
+// assembly lists the bins that reach CORN_HOT_BIN; whenever the threshold asks for car >= 5 * CORN_HOT_BIN (any
+// threshold_adj >= 0.2: the default is 0.4 * 0.994), every passing full window contains a listed bin, and telowin only
+// has to look at the five windows around each of them (a few thousand per genome) instead of at every window.
+#define CORN_HOT_BIN 40u
+#define CORN_HOT_CAP (1u << 20)
+// layout of the first 64 bytes of ctx->misc (one small readback fetches them all):
+//   [0,16) telofind totals  [16] tile ticket counter  [20] telofind error counter  [24] dense-tile queue length
+//   [32,48) telowin counters ([1] bitmap words, [2] windows written, [3] hot blocks)  [48] hot bins listed
+#define CORN_MISC_HOT_COUNT 48
 
 struct corn_dbuf {         // grow-only device scratch
     void  *p;
@@ -83,6 +93,8 @@ struct corn_ctx {
     corn_dbuf ing_tab;     // ingest: per-tile newline counts / bases
     corn_dbuf ing_lines;   // ingest: line tables
     corn_dbuf ing_rec;     // ingest: record table
+    corn_dbuf ranks;       // telofind: per-record run ranks
+    corn_dbuf hot;         // telofind -> telowin: bins that reached CORN_HOT_BIN marked bases
 
     // one retired sequence buffer kept for the next upload (cudaMalloc/cudaFree of GBs cost milliseconds)
     uint8_t *spare_base;
@@ -104,6 +116,10 @@ struct corn_ctx {
     uint32_t  last_n_win;          // windows returned by the previous telowin: sizes the speculative D2H copy
     int       last_runs_disjoint;  // runs cannot overlap (border-free motif, no fwd/rev overlap)
     int       last_motif_len;
+    // 200-bp bin counts filled by the run assembly of the last telofind (disjoint runs only), with the list of bins
+    // that reached CORN_HOT_BIN: a fused telowin(hits == NULL) then only looks at windows around those
+    const corn_dbatch *bins_for_db;    // NULL: ctx->bins does not hold the counts of last_db's runs
+    int       counters_clean;          // the tile / dense-queue counters in ctx->misc were left zeroed by the last telofind
 
     void     *h_pinned_small;      // 4 KiB pinned scratch for small readbacks
 

@@ -233,6 +233,7 @@ template <int M_CT, uint64_t FC_CT, uint64_t RC_CT>
 __global__ void __launch_bounds__(256, 5) k_telofind_scan(const ScanParams P)
 {
     const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.tile_counter[1] = 0;      // error counter of the run assembly that follows
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(256) k_telofind_scan_generic(const ScanParams 
     const int lane = threadIdx.x & 31;
     const int m = P.m;
     const uint8_t f0 = __ldg(P.pat), r0 = __ldg(P.pat + 256);
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.tile_counter[1] = 0;      // error counter of the run assembly that follows
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
@@ -334,6 +336,7 @@ struct ScatterParams {
     const uint4 *totals;       // device: #start_f, #end_f, #start_r, #end_r
     uint32_t capacity;         // entries available in ev
     int m;
+    uint32_t *counters;        // [0] tile ticket counter, [2] dense-tile queue length (reset here)
 };
 
 __device__ __forceinline__ void emit_bits(uint32_t mask, uint32_t *dst, uint32_t pos0)
@@ -387,6 +390,9 @@ __global__ void __launch_bounds__(256) k_telofind_scatter(const ScatterParams P)
     __shared__ uint4 bat[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint4 tot = *P.totals;
+    // the scan and the dense-tile pass are done with their ticket counter and queue length: leave them zeroed for
+    // the next call (one launch and one dependency less than a reset in front of every scan)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { P.counters[0] = 0; P.counters[2] = 0; }
     if ((uint64_t)tot.x + tot.y + tot.z + tot.w > P.capacity) return;     // host grows the buffer and relaunches
     uint32_t *start_f = P.ev, *end_f = start_f + tot.x, *start_r = end_f + tot.y, *end_r = start_r + tot.z;
     const uint32_t tile0 = blockIdx.x * 32u;
@@ -449,6 +455,12 @@ struct AssembleParams {
     uint32_t *rank_f, *rank_r; // [n_rec+1]: number of fwd / rev runs that start before record r
     corn_run_t *out;
     uint32_t *err;
+    // telowin's 200-bp bin counts, filled here when runs cannot overlap (bins != NULL): replaces the separate pass over
+    // the finished run list, src/telomere_windows.c:75-79 (the paint loop)
+    const uint32_t *bin_base;  // [n_rec+1] first bin of each record
+    uint8_t  *bins;            // zeroed before the launch
+    uint32_t *hot_list;        // bins that reached CORN_HOT_BIN (any order), CORN_HOT_CAP entries
+    uint32_t *hot_count;
 };
 
 // rank_f[r] = #forward run starts before rec_off[r] (r = 0..n_rec), same for reverse.  Records are
@@ -495,6 +507,21 @@ __global__ void __launch_bounds__(256) k_telofind_assemble(const AssembleParams 
         corn_run_t r;
         r.rec = rec; r.strand = rev ? 1u : 0u; r.start = s - r0; r.end = e - r0;
         P.out[slot] = r;
+        if (P.bins) {
+            // marked bases per 200-bp bin: runs are disjoint here, so every run adds its overlap with each bin it
+            // touches (bytes inside a word: a bin never exceeds 200, so the add cannot carry into its neighbour)
+            const uint32_t b0 = P.bin_base[rec];
+            uint32_t a = r.start;
+            while (a < r.end) {
+                const uint32_t bin = a / 200u, lim = min(r.end, (bin + 1u) * 200u), g = b0 + bin, sh = 8u * (g & 3u);
+                const uint32_t before = (atomicAdd((uint32_t *)(P.bins + (g & ~3u)), (lim - a) << sh) >> sh) & 0xFFu;
+                if (before < CORN_HOT_BIN && before + (lim - a) >= CORN_HOT_BIN) {       // crossed once per bin: counts only grow
+                    const uint32_t h = atomicAdd(P.hot_count, 1u);
+                    if (h < CORN_HOT_CAP) P.hot_list[h] = g;
+                }
+                a = lim;
+            }
+        }
     }
 }
 
@@ -616,8 +643,12 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
         CORN_CUDA(ctx, cudaStreamSynchronize(st));
         snprintf(ctx->cached_motif, sizeof ctx->cached_motif, "%s", motif);
     }
-    k_reset_counter<<<1, 32, 0, st>>>(sp.tile_counter, 3);
-    corn_count_launch(ctx);
+    if (!ctx->counters_clean) {                       // first call on this context, or the previous one did not get as far as its scatter pass
+        k_reset_counter<<<1, 32, 0, st>>>(sp.tile_counter, 3);
+        corn_count_launch(ctx);
+    }
+    ctx->counters_clean = 0;
+    ctx->bins_for_db = NULL;                          // ctx->bins is about to be rewritten (or left stale)
 
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     if (n_tiles) {
@@ -659,24 +690,36 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
         ScatterParams sc;
         sc.c_idx = sp.c_idx; sc.c_a = sp.c_a; sc.c_b = sp.c_b; sc.c_c = sp.c_c; sc.c_d = sp.c_d;
         sc.tile_off = tile_off; sc.tile_ncand = sp.tile_ncand; sc.n_tiles = n_tiles;
-        sc.ev = ev; sc.totals = d_totals; sc.capacity = (uint32_t)ev_cap; sc.m = mi.m;
+        sc.ev = ev; sc.totals = d_totals; sc.capacity = (uint32_t)ev_cap; sc.m = mi.m; sc.counters = sp.tile_counter;
         if (n_tiles) {
             k_telofind_scatter<<<(n_tiles + 31) / 32, 256, 0, st>>>(sc);
             corn_count_launch(ctx);
             CORN_LAUNCH_CHECK(ctx);
+            ctx->counters_clean = 1;
         }
         if (!mi.bordered) {
-            CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, 2 * ((size_t)db->n_rec + 2) * sizeof(uint32_t)));   // rank tables (bins is free here)
+            CORN_TRY(corn_dbuf_reserve(ctx, &ctx->ranks, 2 * ((size_t)db->n_rec + 2) * sizeof(uint32_t)));
             AssembleParams ap;
             ap.ev = ev; ap.totals = d_totals; ap.ev_capacity = (uint32_t)ev_cap; ap.run_capacity = (uint32_t)run_cap;
             ap.rec_off = db->d_rec_off; ap.n_rec = db->n_rec;
-            ap.rank_f = (uint32_t *)ctx->bins.p; ap.rank_r = ap.rank_f + db->n_rec + 2;
+            ap.rank_f = (uint32_t *)ctx->ranks.p; ap.rank_r = ap.rank_f + db->n_rec + 2;
             ap.out = (corn_run_t *)ctx->runs.p; ap.err = d_err;
+            ap.bin_base = NULL; ap.bins = NULL; ap.hot_list = NULL; ap.hot_count = NULL;
+            if (!mi.strands_overlap && db->n_rec && db->d_bin_base && db->n_bins_total <= 0xFFFFFF00ull) {
+                // runs cannot overlap: the run assembly also counts telowin's bins (and lists the hot ones)
+                CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (size_t)db->n_bins_total + 128));
+                CORN_TRY(corn_dbuf_reserve(ctx, &ctx->hot, (size_t)CORN_HOT_CAP * sizeof(uint32_t)));
+                ap.bin_base = db->d_bin_base; ap.bins = (uint8_t *)ctx->bins.p;
+                ap.hot_list = (uint32_t *)ctx->hot.p; ap.hot_count = (uint32_t *)(misc + CORN_MISC_HOT_COUNT);
+                CORN_CUDA(ctx, cudaMemsetAsync(ap.bins, 0, (size_t)db->n_bins_total + 64, st));
+                CORN_CUDA(ctx, cudaMemsetAsync(ap.hot_count, 0, sizeof(uint32_t), st));
+            }
             if (db->n_rec) {
                 k_telofind_ranks<<<(unsigned)(((size_t)db->n_rec + 1 + 7) / 8), 256, 0, st>>>(ap, tile_off, sp.tile_ncand, sp.c_idx, sp.c_a, sp.c_b, n_tiles);
                 k_telofind_assemble<<<ctx->sm_count * 8, 256, 0, st>>>(ap);
                 corn_count_launch(ctx, 2);
                 CORN_LAUNCH_CHECK(ctx);
+                ctx->bins_for_db = ap.bins ? db : NULL;       // (a capacity overflow leaves them empty; the repeat below refills them)
             }
             CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
             if (!out && attempt == 0 && allow_async) {
@@ -709,11 +752,11 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
             }
             if (db->n_rec) {
                 const size_t n2 = 2 * (size_t)db->n_rec;
-                CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (2 * n2 + 8) * sizeof(uint32_t)));   // borrowed as a temporary
+                CORN_TRY(corn_dbuf_reserve(ctx, &ctx->ranks, (2 * n2 + 8) * sizeof(uint32_t)));
                 GreedyParams gp;
                 gp.occ_f = ev; gp.occ_r = ev + tot[0]; gp.n_f = tot[0]; gp.n_r = tot[2];
                 gp.rec_off = db->d_rec_off; gp.n_rec = db->n_rec; gp.m = mi.m;
-                gp.cnt = (uint32_t *)ctx->bins.p; uint32_t *goff = gp.cnt + n2; gp.off = goff; gp.out = NULL;
+                gp.cnt = (uint32_t *)ctx->ranks.p; uint32_t *goff = gp.cnt + n2; gp.off = goff; gp.out = NULL;
                 k_telofind_greedy<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>(gp);
                 corn_count_launch(ctx);
                 CORN_LAUNCH_CHECK(ctx);

@@ -13,6 +13,8 @@
 //   general        (runs given by the caller, any order, overlaps allowed -- the text-driven
 //                   `cornetto telowin` path): paint a 1-bit-per-base map with atomicOr (union
 //                   semantics, exactly the reference's byte map), then popcount per bin.
+#include <algorithm>
+
 #include "corn_internal.cuh"
 
 namespace {
@@ -223,6 +225,50 @@ __global__ void __launch_bounds__(256) k_windows_write(const uint8_t *__restrict
     }
 }
 
+// Fused path (bins and the hot-bin list come from telofind's run assembly).  car_min_full >= 5 * CORN_HOT_BIN, so a
+// full window (den = 1000, i + 1000 < len) that passes holds a listed bin: the thread of a listed bin g looks at the
+// five windows that contain it and reports those of which g is the FIRST listed bin.  The last window of every record
+// (den = len - i <= 1000: the only one the reference tests with a shorter denominator, src/telomere_windows.c:33-41)
+// is decided by one thread per record with the exact double-precision test.  Windows are written in any order; the
+// host puts the few thousand of them into (record, start) order.
+__global__ void __launch_bounds__(256) k_windows_hot(const uint8_t *__restrict__ bins, const uint32_t *__restrict__ bin_base,
+                                                     const uint32_t *__restrict__ rec_len, uint32_t n_rec, double thr, uint32_t car_min_full,
+                                                     const uint32_t *__restrict__ hot_list, const uint32_t *__restrict__ hot_count,
+                                                     uint32_t capacity, corn_window_t *out, uint32_t *n_out)
+{
+    const uint32_t n_hot = min(*hot_count, CORN_HOT_CAP);
+    const uint32_t n_items = n_hot + n_rec;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_items; t += gridDim.x * blockDim.x) {
+        if (t < n_hot) {
+            const uint32_t g = hot_list[t];
+            const uint32_t rec = corn_upper_bound(bin_base, n_rec, g) - 1;
+            const uint32_t b0 = bin_base[rec], k0 = g - b0, nwin = nwin_of(rec_len[rec]);
+            if (nwin < 2) continue;                                   // no full window in this record
+            const uint32_t k_hi = min(k0, nwin - 2u), k_lo = k0 >= 4u ? k0 - 4u : 0u;
+            for (uint32_t k = k_lo; k <= k_hi; ++k) {
+                bool first = true;
+                for (uint32_t j = k; j < k0; ++j) first &= bins[b0 + j] < CORN_HOT_BIN;
+                if (!first) continue;
+                const uint8_t *b = bins + b0 + k;
+                const uint32_t car = (uint32_t)b[0] + b[1] + b[2] + b[3] + b[4];
+                if (car >= car_min_full) {
+                    const uint32_t o = atomicAdd(n_out, 1u);
+                    if (o < capacity) { corn_window_t w; w.rec = rec; w.start = k * 200u; w.end = k * 200u + 1000u; w.car = car; out[o] = w; }
+                }
+            }
+        } else {
+            const uint32_t rec = t - n_hot;
+            const uint32_t nwin = nwin_of(rec_len[rec]);
+            if (nwin == 0) continue;
+            corn_window_t w;
+            if (window_at(bins, bin_base, rec_len, n_rec, bin_base[rec] + nwin - 1u, thr, w)) {
+                const uint32_t o = atomicAdd(n_out, 1u);
+                if (o < capacity) out[o] = w;
+            }
+        }
+    }
+}
+
 __global__ void k_bit_bases(const uint32_t *__restrict__ rec_len, uint32_t *__restrict__ words, uint32_t n_rec)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,6 +282,37 @@ __global__ void k_words_to_bits(const uint32_t *__restrict__ word_base, uint64_t
 }
 
 }  // namespace
+
+// common tail of both window paths: hand the host array over, fill the timing, and settle an un-synced telofind
+static int telowin_finish(corn_ctx *ctx, corn_windows_t *out, corn_window_t *h_win, uint32_t n_win, const uint32_t hv[16], int pending,
+                          const corn_timing_t &t_find, const corn_hits_t *hits, const corn_contigs_t *contigs, double thr)
+{
+    ctx->last_n_win = n_win;
+    out->n_win = n_win;
+    out->win = h_win; out->_owner = h_win;
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[8], ctx->ev[9]);
+    cudaEventElapsedTime(&ctx->timing.post_ms, ctx->ev[9], ctx->ev[10]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[10], ctx->ev[11]);
+    ctx->timing.out_bytes = (uint64_t)n_win * sizeof(corn_window_t);
+    if (pending) {
+        // the stream is idle now: look at the telofind totals/flags that were left unchecked
+        const corn_timing_t t_win = ctx->timing;
+        ctx->timing = t_find;
+        const uint64_t before = ctx->total_launches;
+        int r = corn_telofind_resolve_with(ctx, hv);
+        if (r != CORN_OK) { corn_gpu_windows_free(out); return r; }
+        if (ctx->total_launches != before) {       // a buffer had been too small and the runs were rebuilt: redo the windows
+            corn_gpu_windows_free(out);
+            return corn_gpu_telowin(ctx, hits, contigs, thr, out);
+        }
+        // report the fused step as one: scan = the telofind scan kernel, post = every other kernel
+        ctx->timing.post_ms += t_win.post_ms;
+        ctx->timing.d2h_ms += t_win.d2h_ms;
+        ctx->timing.launches += t_win.launches;
+        ctx->timing.out_bytes += t_win.out_bytes;
+    }
+    return CORN_OK;
+}
 
 extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const corn_contigs_t *contigs,
                                 double thr, corn_windows_t *out)
@@ -322,7 +399,65 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (size_t)n_bins_total + 128));
     uint8_t *bins = (uint8_t *)ctx->bins.p;
 
-    if (disjoint) {
+    // integer form of the test for full windows, derived with the reference's own double expression
+    uint32_t car_min_full = 1001;
+    for (uint32_t c = 0; c <= 1000; ++c) if ((double)c / (double)1000 >= thr) { car_min_full = c; break; }
+    const bool bins_ready = !hits && disjoint && ctx->bins_for_db == ctx->last_db;      // counted by telofind's run assembly
+    if (hits) ctx->bins_for_db = NULL;                  // ctx->bins is about to hold the counts of other runs
+
+    if (bins_ready && car_min_full >= 5u * CORN_HOT_BIN && !getenv("CORNETTO_NO_HOT_WINDOWS")) {
+        // ---- fused fast path: only the windows around the listed bins and the last window of every record ----
+        size_t cap_win = ctx->events.cap / sizeof(corn_window_t);
+        if (cap_win < 65536) { CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, 65536 * sizeof(corn_window_t))); cap_win = ctx->events.cap / sizeof(corn_window_t); }
+        corn_window_t *d_out = (corn_window_t *)ctx->events.p;
+        const uint32_t *d_hot_count = (const uint32_t *)((uint8_t *)ctx->misc.p + CORN_MISC_HOT_COUNT);
+        corn_window_t *h_win = NULL;
+        uint32_t hv[16], n_win = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const uint64_t items = (uint64_t)n_rec + 4096u;
+            const unsigned g = (unsigned)((items + 255) / 256 < (uint64_t)ctx->sm_count * 8u ? (items + 255) / 256 : (uint64_t)ctx->sm_count * 8u);
+            k_windows_hot<<<g, 256, 0, st>>>(bins, bin_base, d_len, n_rec, thr, car_min_full, (const uint32_t *)ctx->hot.p, d_hot_count,
+                                             (uint32_t)(cap_win > 0xFFFFFFFFull ? 0xFFFFFFFFull : cap_win), d_out, d_tot + 2);
+            corn_count_launch(ctx);
+            CORN_LAUNCH_CHECK(ctx);
+            CORN_CUDA(ctx, cudaEventRecord(ctx->ev[10], st));
+            size_t spec = (size_t)ctx->last_n_win + ctx->last_n_win / 4 + 4096;
+            if (spec > cap_win) spec = cap_win;
+            h_win = (corn_window_t *)corn_host_alloc(spec * sizeof(corn_window_t));
+            if (!h_win) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc of %zu windows", spec);
+            CORN_CUDA(ctx, cudaMemcpyAsync(h_win, d_out, spec * sizeof(corn_window_t), cudaMemcpyDeviceToHost, st));
+            CORN_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned_small, ctx->misc.p, 64, cudaMemcpyDeviceToHost, st));
+            CORN_CUDA(ctx, cudaEventRecord(ctx->ev[11], st));
+            CORN_CUDA(ctx, cudaStreamSynchronize(st));
+            memcpy(hv, ctx->h_pinned_small, 64);
+            n_win = hv[8 + 2];
+            if (hv[CORN_MISC_HOT_COUNT / 4] > CORN_HOT_CAP) {       // more hot bins than the list holds (a batch made of telomeres): general path
+                corn_host_free(h_win);
+                ctx->bins_for_db = ctx->last_db;
+                h_win = NULL;
+                break;
+            }
+            if (n_win <= spec) break;
+            corn_host_free(h_win);                                  // more windows than expected: make room and write them again
+            h_win = NULL;
+            if (attempt == 1) return corn_set_err(ctx, CORN_E_INTERNAL, "window count changed between two passes");
+            CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, ((size_t)n_win + 1) * sizeof(corn_window_t)));
+            cap_win = ctx->events.cap / sizeof(corn_window_t);
+            d_out = (corn_window_t *)ctx->events.p;
+            ctx->last_n_win = n_win;
+            CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 16, st));
+        }
+        if (h_win) {
+            // (record, start) order = the reference's print order (records in file order, i ascending)
+            std::sort(h_win, h_win + n_win, [](const corn_window_t &a, const corn_window_t &b) { return a.rec != b.rec ? a.rec < b.rec : a.start < b.start; });
+            return telowin_finish(ctx, out, h_win, n_win, hv, pending, t_find, hits, contigs, thr);
+        }
+        CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 16, st));
+    }
+
+    if (bins_ready) {
+        // counted already by telofind's run assembly
+    } else if (disjoint) {
         CORN_CUDA(ctx, cudaMemsetAsync(bins, 0, (size_t)n_bins_total + 64, st));
         if (n_run || pending) {
             const unsigned g = pending ? (unsigned)ctx->sm_count * 8u : (unsigned)((n_run + 255) / 256);
@@ -367,9 +502,6 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
     // exceeds it and the total tells us afterwards whether a second write pass is needed
     size_t cap_win = ctx->events.cap / sizeof(corn_window_t);
     if (cap_win < 65536) { CORN_TRY(corn_dbuf_reserve(ctx, &ctx->events, 65536 * sizeof(corn_window_t))); cap_win = ctx->events.cap / sizeof(corn_window_t); }
-    // integer form of the test for full windows, derived with the reference's own double expression
-    uint32_t car_min_full = 1001;
-    for (uint32_t c = 0; c <= 1000; ++c) if ((double)c / (double)1000 >= thr) { car_min_full = c; break; }
     k_windows_mark<<<n_blk, 256, 0, st>>>(bins, bin_base, d_len, n_rec, n_bins_total, thr, car_min_full, wmask, blk_cnt, hot, n_hot);
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
@@ -407,31 +539,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
         CORN_CUDA(ctx, cudaMemcpyAsync(h_win, d_out, (size_t)n_win * sizeof(corn_window_t), cudaMemcpyDeviceToHost, st));
         CORN_CUDA(ctx, cudaStreamSynchronize(st));
     }
-    ctx->last_n_win = n_win;
-    out->n_win = n_win;
-    out->win = h_win; out->_owner = h_win;
-    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[8], ctx->ev[9]);
-    cudaEventElapsedTime(&ctx->timing.post_ms, ctx->ev[9], ctx->ev[10]);
-    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[10], ctx->ev[11]);
-    ctx->timing.out_bytes = (uint64_t)n_win * sizeof(corn_window_t);
-    if (pending) {
-        // the stream is idle now: look at the telofind totals/flags that were left unchecked
-        const corn_timing_t t_win = ctx->timing;
-        ctx->timing = t_find;
-        const uint64_t before = ctx->total_launches;
-        int r = corn_telofind_resolve_with(ctx, hv);
-        if (r != CORN_OK) { corn_gpu_windows_free(out); return r; }
-        if (ctx->total_launches != before) {       // a buffer had been too small and the runs were rebuilt: redo the windows
-            corn_gpu_windows_free(out);
-            return corn_gpu_telowin(ctx, hits, contigs, thr, out);
-        }
-        // report the fused step as one: scan = the telofind scan kernel, post = every other kernel
-        ctx->timing.post_ms += t_win.post_ms;
-        ctx->timing.d2h_ms += t_win.d2h_ms;
-        ctx->timing.launches += t_win.launches;
-        ctx->timing.out_bytes += t_win.out_bytes;
-    }
-    return CORN_OK;
+    return telowin_finish(ctx, out, h_win, n_win, hv, pending, t_find, hits, contigs, thr);
 }
 
 extern "C" void corn_gpu_windows_free(corn_windows_t *w)
