@@ -14,6 +14,7 @@
 //                   `cornetto telowin` path): paint a 1-bit-per-base map with atomicOr (union
 //                   semantics, exactly the reference's byte map), then popcount per bin.
 #include <algorithm>
+#include <vector>
 
 #include "corn_internal.cuh"
 
@@ -283,6 +284,31 @@ __global__ void k_words_to_bits(const uint32_t *__restrict__ word_base, uint64_t
 
 }  // namespace
 
+// (record, start) order = the reference's print order (records in file order, i ascending).  The key of a window is
+// its global bin number bin_base[rec] + start / 200 -- unique and ascending in that order -- and a few thousand 32-bit
+// keys are put in order by an LSD radix sort (three 11-bit passes, ~10 us; a comparison sort of the structs took ~100).
+static void order_windows(corn_window_t *w, uint32_t n, const uint32_t *bin_base)
+{
+    if (n < 2) return;
+    bool sorted = true;
+    for (uint32_t i = 1; i < n && sorted; ++i) sorted = w[i - 1].rec < w[i].rec || (w[i - 1].rec == w[i].rec && w[i - 1].start < w[i].start);
+    if (sorted) return;
+    std::vector<uint32_t> key(n), idx(n), idx2(n);
+    for (uint32_t i = 0; i < n; ++i) { key[i] = bin_base[w[i].rec] + w[i].start / 200u; idx[i] = i; }
+    uint32_t cnt[2048];
+    for (int pass = 0; pass < 3; ++pass) {
+        const int sh = 11 * pass;
+        memset(cnt, 0, sizeof cnt);
+        for (uint32_t i = 0; i < n; ++i) ++cnt[(key[idx[i]] >> sh) & 2047u];
+        uint32_t acc = 0;
+        for (int b = 0; b < 2048; ++b) { const uint32_t c = cnt[b]; cnt[b] = acc; acc += c; }
+        for (uint32_t i = 0; i < n; ++i) idx2[cnt[(key[idx[i]] >> sh) & 2047u]++] = idx[i];
+        idx.swap(idx2);
+    }
+    std::vector<corn_window_t> tmp(w, w + n);
+    for (uint32_t i = 0; i < n; ++i) w[i] = tmp[idx[i]];
+}
+
 // common tail of both window paths: hand the host array over, fill the timing, and settle an un-synced telofind
 static int telowin_finish(corn_ctx *ctx, corn_windows_t *out, corn_window_t *h_win, uint32_t n_win, const uint32_t hv[16], int pending,
                           const corn_timing_t &t_find, const corn_hits_t *hits, const corn_contigs_t *contigs, double thr)
@@ -448,8 +474,7 @@ extern "C" int corn_gpu_telowin(corn_ctx_t *ctx, const corn_hits_t *hits, const 
             CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 16, st));
         }
         if (h_win) {
-            // (record, start) order = the reference's print order (records in file order, i ascending)
-            std::sort(h_win, h_win + n_win, [](const corn_window_t &a, const corn_window_t &b) { return a.rec != b.rec ? a.rec < b.rec : a.start < b.start; });
+            order_windows(h_win, n_win, ctx->last_db->h_bin_base);
             return telowin_finish(ctx, out, h_win, n_win, hv, pending, t_find, hits, contigs, thr);
         }
         CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 16, st));

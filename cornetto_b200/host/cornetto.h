@@ -33,6 +33,7 @@ int assbed_main(int argc, char *argv[]);
 int nx_main(int argc, char *argv[]);
 int report_main(int argc, char *argv[]);
 int seq_main(int argc, char *argv[]);
+int telostats_main(int argc, char *argv[]);
 
 /* misc.c */
 uint64_t cornetto_batch_capacity(const char *path, int n_parts);
@@ -74,6 +75,7 @@ typedef struct {
     char   **name;        /* [n] strdup'ed (serial reader) or pointers into name_arena (device-parsed) */
     uint32_t n, max_rec;
     int      eof;         /* input exhausted (or stopped at a malformed FASTQ record) */
+    uint64_t seq;         /* 0, 1, 2, ... in input order (set by the pipelines before the callback runs) */
     /* device-parsed batches (ingest.c): the records are already resident */
     corn_dbatch_t  *db;
     const uint32_t *length;      /* [n] */
@@ -117,6 +119,11 @@ void outbuf_format_parallel(outbuf_t *ob, uint64_t n_items, format_range_fn fn, 
  * $CORNETTO_GPUS = number of devices to use (default 1; batches go round-robin over them). */
 typedef void (*batch_fn)(corn_ctx_t *ctx, rec_batch_t *b, outbuf_t *out, void *arg);
 void run_batch_pipeline(fastx_t *fx, const char *path, batch_fn fn, void *arg);
+/* where the pipelines write the batches' text, in batch order (stdout unless set; telostats writes a file) */
+void  cornetto_set_pipeline_out(FILE *fp);
+FILE *cornetto_pipeline_out(void);
+/* next batch number of this process (batches are numbered in input order across both pipelines) */
+uint64_t cornetto_next_batch_seq(void);
 
 /* ---- device-side parsing for plain files (ingest.c) --------------------------------------------
  * Reads the file in large blocks, hands each block to corn_gpu_ingest() and calls fn with a

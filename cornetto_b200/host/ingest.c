@@ -41,6 +41,7 @@ typedef struct {
     uint8_t        *blk;         /* where the current block starts inside it */
     uint64_t        cap, n;
     int             final, teardown;
+    uint64_t        seq;         /* index of the current block in input order */
     uint64_t        consumed;
     int             irregular;
     outbuf_t        out;
@@ -114,7 +115,7 @@ static void *iworker_main(void *p)
         if (!ing.irregular && ing.n_rec) {
             rec_batch_t b;
             memset(&b, 0, sizeof b);
-            b.n = ing.n_rec; b.db = ing.db; b.length = ing.length;
+            b.n = ing.n_rec; b.db = ing.db; b.length = ing.length; b.seq = w->seq;
             t0 = realtime();
             build_names(&b, w->blk, w->n, &ing);
             w->fn(w->ctx, &b, &w->out, w->arg);
@@ -266,7 +267,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
     for (;;) {
         iworker_t *x = &w[dispatched % n_workers];
         wait_idle(x);
-        if (dispatched - n_workers >= written) { outbuf_write(&x->out, stdout); written = dispatched - n_workers + 1; }
+        if (dispatched - n_workers >= written) { outbuf_write(&x->out, cornetto_pipeline_out()); written = dispatched - n_workers + 1; }
         if (!x->text) {
             void *p = NULL;
             if (posix_memalign(&p, 2u << 20, reserve + block + 64) != 0) p = NULL;
@@ -296,6 +297,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
         x->n = carry_len + fresh;
         x->final = (fresh < want || file_pos >= size);
         x->ingested = 0;
+        x->seq = cornetto_next_batch_seq();
         pthread_mutex_lock(&x->mu);
         x->state = 1;
         pthread_cond_broadcast(&x->cv);
@@ -314,7 +316,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
         if (!x->final && reserve) {                      /* read ahead for the next block while this one is shipped and parsed */
             iworker_t *y = &w[(dispatched + 1) % n_workers];
             wait_idle(y);
-            if (dispatched + 1 - n_workers >= written) { outbuf_write(&y->out, stdout); written = dispatched + 1 - n_workers + 1; }
+            if (dispatched + 1 - n_workers >= written) { outbuf_write(&y->out, cornetto_pipeline_out()); written = dispatched + 1 - n_workers + 1; }
             if (!y->text) {
                 void *p = NULL;
                 if (posix_memalign(&p, 2u << 20, reserve + block + 64) != 0) p = NULL;
@@ -343,7 +345,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
         iworker_t *y = &w[written % n_workers];
         wait_idle(y);
         const double t_wr = realtime();
-        outbuf_write(&y->out, stdout);
+        outbuf_write(&y->out, cornetto_pipeline_out());
         TRACE("[ingest] wrote output in %.3f s\n", realtime() - t_wr);
     }
     for (int i = 0; i < n_spawned; ++i) {
@@ -356,7 +358,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
         outbuf_free(&w[i].out);
         if (!complete || !cornetto_fast_exit()) free(w[i].text);
     }
-    fflush(stdout);
+    fflush(cornetto_pipeline_out());
     free(w);
     close(fd);
     TRACE("[ingest] pipeline done (complete %d)\n", complete);

@@ -16,6 +16,7 @@ static int print_usage(FILE *fp)
     fprintf(fp, "       telobreaks      find telomere breaks in a fasta file\n");
     fprintf(fp, "       telofind        find telomere sequences in a fasta file\n");
     fprintf(fp, "       sdust           symmetric DUST (https://github.com/lh3/sdust)\n");
+    fprintf(fp, "       telostats       scripts/telostats.sh in one pass: telofind, telowin, merged windows at contig ends, tally\n");
     fprintf(fp, "   misc:\n");
     fprintf(fp, "       fa2bed          create a bed file with assembly contig lengths\n");
     fprintf(fp, "       nx              nx or ngx plot tables\n");
@@ -37,6 +38,7 @@ int main(int argc, char *argv[])
     else if (strcmp(argv[1], "telobreaks") == 0) ret = telomere_breaks_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "telofind") == 0) ret = find_telomere_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "sdust") == 0) ret = sdust_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "telostats") == 0) ret = telostats_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "fa2bed") == 0) ret = assbed_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "nx") == 0) ret = nx_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "report") == 0) ret = report_main(argc - 1, argv + 1);

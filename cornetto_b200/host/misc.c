@@ -109,6 +109,12 @@ void outbuf_init(outbuf_t *o, FILE *fp)
 }
 void outbuf_flush(outbuf_t *o) { if (o->fp && o->n) { fwrite(o->buf, 1, o->n, o->fp); o->n = 0; } }
 void outbuf_free(outbuf_t *o) { outbuf_flush(o); if (o->fp) fflush(o->fp); free(o->buf); o->buf = NULL; }
+static FILE *g_pipeline_out;
+void  cornetto_set_pipeline_out(FILE *fp) { g_pipeline_out = fp; }
+FILE *cornetto_pipeline_out(void) { return g_pipeline_out ? g_pipeline_out : stdout; }
+static uint64_t g_batch_seq;
+uint64_t cornetto_next_batch_seq(void) { return g_batch_seq++; }      /* called by the one dispatching thread */
+
 void outbuf_write(outbuf_t *o, FILE *fp) { if (o->n) fwrite(o->buf, 1, o->n, fp); o->n = 0; }
 static inline void need(outbuf_t *o, size_t k)
 {

@@ -92,10 +92,11 @@ void run_batch_pipeline(fastx_t *fx, const char *path, batch_fn fn, void *arg)
     for (;;) {
         worker_t *x = &w[dispatched % n_workers];
         wait_idle(x);
-        if (dispatched - n_workers >= written) { outbuf_write(&x->out, stdout); written = dispatched - n_workers + 1; }
+        if (dispatched - n_workers >= written) { outbuf_write(&x->out, cornetto_pipeline_out()); written = dispatched - n_workers + 1; }
         if (!x->batch) x->batch = rec_batch_create(cap, (uint32_t)max_rec);
         if (rec_batch_fill(x->batch, fx) == 0) break;
         const int input_done = x->batch->eof;
+        x->batch->seq = cornetto_next_batch_seq();
         pthread_mutex_lock(&x->mu);
         x->state = 1;
         pthread_cond_broadcast(&x->cv);
@@ -106,7 +107,7 @@ void run_batch_pipeline(fastx_t *fx, const char *path, batch_fn fn, void *arg)
     for (; written < dispatched; ++written) {           /* drain, oldest first */
         worker_t *y = &w[written % n_workers];
         wait_idle(y);
-        outbuf_write(&y->out, stdout);
+        outbuf_write(&y->out, cornetto_pipeline_out());
     }
     for (int i = 0; i < n_workers; ++i) {
         pthread_mutex_lock(&w[i].mu);
@@ -117,6 +118,6 @@ void run_batch_pipeline(fastx_t *fx, const char *path, batch_fn fn, void *arg)
         outbuf_free(&w[i].out);
         if (w[i].batch && !cornetto_fast_exit()) rec_batch_destroy(w[i].batch);
     }
-    fflush(stdout);
+    fflush(cornetto_pipeline_out());
     free(w);
 }

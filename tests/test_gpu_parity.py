@@ -262,6 +262,43 @@ def test_abi_sdust(ctx, capi, tw):
     assert len(iv) == len(wiv) and (iv == wiv).all()
 
 
+def test_cli_telostats_matches_script(tmp_path, oracle_bin):
+    """`cornetto telostats asm.fa` = scripts/telostats.sh in one pass: every file the script leaves behind and its
+    stdout, against the oracle's telofind / fa2bed / telowin and the restated tail (oracle/telostats_tail.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import telostats_tail as tt
+    recs = synth.assembly(91, [260_000, 140_000, 100_001, 90_000, 60_000, 900, 130_000], n_gaps=1, telo=(150, 700), n_its=2)
+    # an interstitial telomere block in the middle of the first contig (must NOT reach the ends bed) and one just inside
+    # the last 50 kb of the second (must)
+    blk = np.frombuffer(b"TTAGGG" * 400, dtype=np.uint8)
+    recs[0][1][120_000:120_000 + len(blk)] = blk
+    recs[1][1][95_000:95_000 + len(blk)] = blk
+    for env in ({}, {"CORNETTO_BATCH_BYTES": "300000"}, {"CORNETTO_INGEST": "0"}):
+        wd = tmp_path / ("w%d" % len(env) + "".join(env))
+        wd.mkdir()
+        fa = write(str(wd / "asm.fa"), synth.fasta_bytes(recs))
+        e = dict(os.environ)
+        e.update(env)
+        p = subprocess.run([BIN, "telostats", "asm.fa"], cwd=str(wd), env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert p.returncode == 0, p.stderr[-2000:]
+        want_t, _, _ = run([oracle_bin, "telofind", fa])
+        want_l = lens_from_fa2bed(run([oracle_bin, "fa2bed", fa])[0])
+        tf = write(str(wd / "want.telomere"), retab_telomere(want_t))
+        want_w, _, _ = run([oracle_bin, "telowin", tf, "99.9", "0.4"])
+        tail = tt.run_tail(want_w.decode(), want_l.decode(), "asm.fa", "asm")
+        t = wd / "tmp_asm_telostats"
+        assert (t / "asm.telomere").read_bytes() == retab_telomere(want_t)
+        assert (t / "asm.lens").read_bytes() == want_l
+        assert (t / "asm.windows.0.4").read_bytes() == want_w and len(want_w) > 200
+        assert (t / "asm.windows.0.4.bed").read_text() == tail["merged_bed"]
+        assert (t / "asm.ends.bed").read_text() == tail["ends_bed"]
+        assert (wd / "asm.windows.0.4.50kb.ends.bed").read_text() == tail["final_bed"]
+        assert p.stdout.decode() == tail["stdout"]
+        assert tail["final_bed"].count("\n") >= 10 and "contig_1\t120" not in tail["final_bed"]
+    _, _, rc = cornetto(["telostats"], check=False)
+    assert rc == 1
+
+
 def test_sdust_library_api(capi):
     """sdust() / sdust_buf_init / sdust_core / sdust_buf_destroy with the reference's signatures and ownership rules
     (src/sdust/sdust.h:16-21): l_seq < 0 means strlen, sdust()'s result is free()d by the caller, sdust_core()'s
@@ -329,7 +366,7 @@ def test_abi_async_fused_matches_sync(ctx, capi):
             assert len(wins) == len(want_wins) and (wins == want_wins).all()
             t = c2.timing()
             if it > 0:                            # (the first pass may have had to grow its buffers and repeat)
-                assert t["scan_ms"] > 0 and t["launches"] >= 8, t
+                assert t["scan_ms"] > 0 and t["launches"] >= 6, t
         runs = c2.telofind_dev(db, "TTAGGG", fetch=True)
         assert len(runs) == len(want_runs) and (runs == want_runs).all()
         c2.free(db)
