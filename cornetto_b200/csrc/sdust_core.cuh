@@ -457,6 +457,127 @@ SD_HD void sd_run_chunk(Fetch &fetch, int l_seq, int c0, int c1, int T, int W, c
     sd_sink_close(k);
 }
 
+// ---- items of the two-phase execution (see below) ---------------------------------------------------
+// warm start of an item whose preceding block is quiet: P is known to be empty at c0, so only the window has to be
+// rebuilt -- W triplet positions back from c0 itself (W-2 plus two for the run cut at p0), window half only
+template <class Fetch>
+SD_HD int sd_warm_quiet(Fetch &fetch, int c0, int W)
+{
+    int p = c0;
+    if (p <= 0) return 0;
+    int need = W, run = 0;
+    while (p > 0 && need > 0) {
+        --p;
+        if (sd_nt4(fetch(p)) < 4) { if (++run >= 3) --need; }
+        else run = 0;
+    }
+    return p;
+}
+
+// the window half of sd_step alone (no save, no find_perfect, no flush: P is empty and stays empty)
+SD_HD void sd_step_window(sd_state &s, const sd_mem &m, int b, int T, int W)
+{
+    if (b < 4) {
+        ++s.l;
+        s.t = (s.t << 2 | (unsigned)b) & 63u;
+        if (s.l >= 3) sd_shift_window(s, m, (int)s.t, T, W);
+    } else { s.l = 0; s.t = 0; }
+}
+
+#define SD_ITEM_QUIET 1u     /* the block before c0 is quiet: window-only warm-up from sd_warm_quiet() */
+#define SD_ITEM_CHAIN 2u     /* the previous item of the record ends exactly at c0 (same run of blocks): fold across the seam */
+
+template <class Fetch>
+SD_HD void sd_run_item(Fetch &fetch, int l_seq, int c0, int c1, uint32_t flags, int T, int W, const sd_mem &m, sd_sink &k)
+{
+    sd_state s;
+    sd_reset(s, m, W);
+    const bool quiet = (flags & SD_ITEM_QUIET) != 0;
+    const int p0 = quiet ? sd_warm_quiet(fetch, c0, W) : sd_warm_start(fetch, c0, W);
+    s.pstart = p0; s.pslot = (int)((uint32_t)p0 % (uint32_t)W);
+    const int stop = c1 < l_seq ? c1 : l_seq;
+    for (int i = p0; i < stop; ++i) {
+        if (i == c0) k.on = 1;
+        if (quiet && i < c0) sd_step_window(s, m, sd_nt4(fetch(i)), T, W);
+        else sd_step(s, m, k, i, sd_nt4(fetch(i)), T, W);
+    }
+    if (c1 >= l_seq) { k.on = 1; sd_step(s, m, k, l_seq, 4, T, W); }
+    sd_sink_close(k);
+}
+
+// --------------------------------------------------------------------------------------------
+// Two-phase execution (W <= 64, floor(2T/10) == 4: the defaults).
+//
+// shift_window() does not depend on the perfect-interval list P at all: the window w, its counts, rw and L evolve from
+// the triplets alone, and find_perfect() is only ever called at steps where  rw*10 > L*T  (:149) -- on ordinary
+// sequence well under 1 % of the steps, in short bursts.  Between two such steps more than a window apart P is empty
+// (an entry lives at most W-2 emitting steps, and a non-ACGT byte empties P at once), so nothing there can be saved.
+//
+// Phase 1, the SCOUT, therefore runs the window half alone over every base, in a form without a single
+// data-dependent loop, and records WHERE the trigger fires.  Instead of the suffix counts cv[] and the shrink loop
+// (:79-85) it keeps, per triplet value, the window count and the ring positions of the last four occurrences in one
+// 32-bit word:  v is the longest suffix in which no triplet occurs more than four times, so pushing t shortens it
+// exactly when t then occurs five times inside it, and the new v starts right after the fourth-previous occurrence:
+//        L <- min(L + 1, wn, distance to the 4th previous occurrence of t  [if t is now >= 5 times in the window]).
+// rv and cv[] are not needed for the trigger.  (sd_scout_* below; the test is bit-identical to :149, checked
+// against the full machine in tests/sim.)
+//
+// Phase 2 runs the full machine only over ITEMS: maximal runs of 64-base blocks that hold a trigger position i or lie
+// within its drain (blocks of i and of i + 64), cut every SD_ITEM_MAX bases.  An item whose preceding block is quiet
+// starts with P empty for certain, so its warm-up only has to rebuild the window (W-2 emitted triplets, window half
+// only); an item cut out of a longer run uses the general exact start of section 2 above.  Items own their save events
+// by time as before, and since starts and finishes of different runs of blocks are more than a window apart, only
+// items of the same run are folded across their seams.
+// --------------------------------------------------------------------------------------------
+#if !defined(SD_WIDE)
+#define SD_BLK 64                 /* activity granularity (bases) */
+#define SD_ITEM_MAX 1024          /* longest item (bases); >= 4W so that a seam fold never looks past one item */
+
+struct sd_scout {
+    uint32_t wn, L, rw, e;        // window size, suffix length, window score, emitted-triplet counter (ring position = e & 63)
+    int l;                        // current ACGT run length
+    unsigned t;
+};
+
+// word of triplet value x: count:8 << 24 | p4:6 << 18 | p3:6 << 12 | p2:6 << 6 | p1:6   (p1 = ring position of the
+// most recent occurrence).  SD_SW(x) / SD_SR(i) are the storage accessors: plain arrays on the host, shared-memory
+// columns on the device.
+template <class Words, class Ring>
+SD_HD void sd_scout_reset(sd_scout &s, Words &words, Ring &ring)
+{
+    s.wn = s.L = s.rw = s.e = 0; s.l = 0; s.t = 0;
+    for (int i = 0; i < 64; ++i) words(i) = 0;
+    (void)ring;
+}
+
+// one emitted triplet; returns whether the reference would call find_perfect with something to examine
+template <class Words, class Ring>
+SD_HD bool sd_scout_push(sd_scout &s, Words &words, Ring &ring, uint32_t t, int T, int W)
+{
+    if (s.wn >= (uint32_t)(W - 2)) {
+        const uint32_t x = ring((s.e - s.wn) & 63u);
+        const uint32_t wx = words(x) - (1u << 24);
+        words(x) = wx;
+        s.rw -= wx >> 24;
+        --s.wn;
+    }
+    if (s.L > s.wn) s.L = s.wn;
+    ring(s.e & 63u) = (uint8_t)t;
+    ++s.wn;
+    const uint32_t w = words(t);
+    const uint32_t c = w >> 24;
+    s.rw += c;
+    const uint32_t d4 = (s.e - (w >> 18)) & 63u;
+    ++s.L;
+    if (c >= 4u && d4 < s.L) s.L = d4;
+    words(t) = ((c + 1u) << 24) | ((w << 6) & 0xFFFFC0u) | (s.e & 63u);
+    ++s.e;
+    return s.rw * 10u > s.L * (uint32_t)T && s.L < s.wn;
+}
+
+SD_HD bool sd_scout_supported(int T, int W) { return W >= 3 && W <= 64 && T > 0 && (T << 1) / 10 == 4; }
+#endif
+
 // --------------------------------------------------------------------------------------------
 // Seam fold.  Chunk j (k-th chunk of its record, covering positions [k*C, ...)) left its list
 // R_j in slots[j*cap .. j*cap+n[j]).  The record's result is the fold of R_0, R_1, ... with the
@@ -520,6 +641,68 @@ SD_HD void sd_gather_write(const uint64_t *slots, const uint32_t *n, uint32_t ca
                 const uint32_t jj = j + (kk - k);
                 for (uint32_t b = 0; b < n[jj]; ++b) {
                     const uint64_t nx = slots[(uint64_t)jj * cap + b];
+                    if (SD_IV_START(nx) <= F) { if (SD_IV_FINISH(nx) > F) F = SD_IV_FINISH(nx); }
+                    else { open = 0; break; }
+                }
+            }
+            iv = (uint64_t)(uint32_t)SD_IV_START(iv) << 32 | (uint32_t)F;
+        }
+        *dst++ = iv;
+    }
+}
+
+// ---- the same fold over ITEMS (two-phase execution): item j covers [c0[j], c1[j]) of its record, its list is
+// slots[off[j] .. off[j] + n[j]), and flags[j] & SD_ITEM_CHAIN says that item j-1 ends exactly where j begins.
+// Items are at most SD_ITEM_MAX >= 4W long but the first one of a run may be short, so the look-back walks the
+// chain until it has covered [c0 - 4W, c0).
+SD_HD int sd_item_incoming_finish(const uint64_t *slots, const uint32_t *off, const uint32_t *n, const uint32_t *c0, const uint32_t *flags,
+                                  uint32_t j, int W)
+{
+    uint32_t jj = j;
+    while ((flags[jj] & SD_ITEM_CHAIN) && (int)c0[jj] > (int)c0[j] - 4 * W) --jj;      // (jj > 0 whenever its CHAIN bit is set)
+    int F = -1;
+    for (; jj < j; ++jj)
+        for (uint32_t a = 0; a < n[jj]; ++a) {
+            const uint64_t iv = slots[(uint64_t)off[jj] + a];
+            if (F >= 0 && SD_IV_START(iv) <= F) { if (SD_IV_FINISH(iv) > F) F = SD_IV_FINISH(iv); }
+            else F = SD_IV_FINISH(iv);
+        }
+    return F;
+}
+
+SD_HD uint32_t sd_item_absorbed(const uint64_t *slots, const uint32_t *off, const uint32_t *n, const uint32_t *c0, const uint32_t *flags,
+                                uint32_t j, int W)
+{
+    if (!(flags[j] & SD_ITEM_CHAIN)) return 0;
+    int F = sd_item_incoming_finish(slots, off, n, c0, flags, j, W);
+    uint32_t a = 0;
+    while (a < n[j] && F >= 0 && SD_IV_START(slots[(uint64_t)off[j] + a]) <= F) {
+        const int f = SD_IV_FINISH(slots[(uint64_t)off[j] + a]);
+        if (f > F) F = f;
+        ++a;
+    }
+    return a;
+}
+
+SD_HD uint32_t sd_item_gather_count(const uint64_t *slots, const uint32_t *off, const uint32_t *n, const uint32_t *c0, const uint32_t *flags,
+                                    uint32_t j, int W)
+{
+    return n[j] - sd_item_absorbed(slots, off, n, c0, flags, j, W);
+}
+
+SD_HD void sd_item_gather_write(const uint64_t *slots, const uint32_t *off, const uint32_t *n, const uint32_t *c0, const uint32_t *flags,
+                                uint32_t j, uint32_t n_items, int W, uint64_t *dst)
+{
+    const uint32_t a0 = sd_item_absorbed(slots, off, n, c0, flags, j, W);
+    for (uint32_t a = a0; a < n[j]; ++a) {
+        uint64_t iv = slots[(uint64_t)off[j] + a];
+        if (a == n[j] - 1) {
+            int F = SD_IV_FINISH(iv);
+            int open = 1;
+            for (uint32_t jj = j + 1; open && jj < n_items && (flags[jj] & SD_ITEM_CHAIN); ++jj) {
+                if (F < (int)c0[jj] - W) break;                 // nothing later can start at or before F
+                for (uint32_t b = 0; b < n[jj]; ++b) {
+                    const uint64_t nx = slots[(uint64_t)off[jj] + b];
                     if (SD_IV_START(nx) <= F) { if (SD_IV_FINISH(nx) > F) F = SD_IV_FINISH(nx); }
                     else { open = 0; break; }
                 }

@@ -181,6 +181,88 @@ static int sim_sdust(const char *path, int T, int W, int C)
     return 0;
 }
 
+#if !defined(SD_WIDE)
+// ---- two-phase sdust simulation: scout (window half only, per chunk) -> active 64-base blocks -> items -> full
+//      machine per item -> fold across item seams.  Mirrors csrc/sdust.cu's fast path step by step.
+struct HostWords { uint32_t w[64]; uint32_t &operator()(uint32_t i) { return w[i]; } };
+struct HostRing { uint8_t r[64]; uint8_t &operator()(uint32_t i) { return r[i]; } };
+
+static unsigned long long st_pos, st_trig, st_active_blk, st_blk, st_items, st_item_pos, st_dense_items;
+
+static int sim_sdust2(const char *path, int T, int W, int C)
+{
+    if (!sd_scout_supported(T, W)) { fprintf(stderr, "two-phase path needs W <= 64 and floor(2T/10) == 4\n"); return 2; }
+    orc_rec_t *recs; size_t n;
+    if (orc_read_fastx(path, &recs, &n) < 0) return 1;
+    for (size_t r = 0; r < n; ++r) {
+        const int len = (int)recs[r].len;
+        const uint8_t *seq = (const uint8_t *)recs[r].seq;
+        struct { const uint8_t *p; uint8_t operator()(int i) const { return p[i]; } } fetch = { seq };
+        const int n_blk = (len + SD_BLK - 1) / SD_BLK;
+        std::vector<uint8_t> active(n_blk + 2, 0);
+        // phase 1: scout per chunk of C bases
+        for (int c0 = 0; c0 < len; c0 += C) {
+            const int c1 = std::min(len, c0 + C);
+            HostWords words; HostRing ring;
+            sd_scout sc;
+            sd_scout_reset(sc, words, ring);
+            const int p0 = sd_warm_quiet(fetch, c0, W);
+            for (int i = p0; i < c1; ++i) {
+                const int b = sd_nt4(seq[i]);
+                if (b < 4) {
+                    ++sc.l; sc.t = (sc.t << 2 | (unsigned)b) & 63u;
+                    if (sc.l >= 3 && sd_scout_push(sc, words, ring, sc.t, T, W) && i >= c0) {
+                        ++st_trig;
+                        active[i / SD_BLK] = 1;
+                        if (i / SD_BLK + 1 < n_blk) active[i / SD_BLK + 1] = 1;
+                    }
+                } else { sc.l = 0; sc.t = 0; }
+            }
+        }
+        st_pos += len; st_blk += n_blk;
+        // items
+        std::vector<uint32_t> ic0, ic1, iflags;
+        for (int j = 0; j < n_blk; ++j) {
+            if (!active[j]) continue;
+            ++st_active_blk;
+            const bool prev = j > 0 && active[j - 1];
+            if (prev && (j * SD_BLK) % SD_ITEM_MAX != 0) { ic1.back() = (uint32_t)std::min(len, (j + 1) * SD_BLK); continue; }
+            ic0.push_back((uint32_t)(j * SD_BLK));
+            ic1.push_back((uint32_t)std::min(len, (j + 1) * SD_BLK));
+            iflags.push_back((prev ? SD_ITEM_CHAIN : 0u) | ((j > 0 && !prev) ? SD_ITEM_QUIET : 0u));
+        }
+        const uint32_t ni = (uint32_t)ic0.size();
+        st_items += ni;
+        // phase 2: full machine per item
+        std::vector<uint32_t> off(ni + 1, 0), cnt(ni + 1, 0);
+        for (uint32_t j = 0; j < ni; ++j) off[j + 1] = off[j] + (ic1[j] - ic0[j] + 2 * W) / 4 + 2;
+        std::vector<uint64_t> slots(off[ni] + 1);
+        for (uint32_t j = 0; j < ni; ++j) {
+            uint8_t ringb[SD_MAX_W]; sd_cnt_t cw[64], cv[64]; sd_slot_t slot[SD_MAX_W];
+            sd_mem m = { ringb, cw, cv, slot, 4 };
+            sd_sink sink;
+            sd_sink_init(sink, slots.data() + off[j], off[j + 1] - off[j]);
+            // an item that reaches the last block of the record also owns the final flush (c1 >= len)
+            sd_run_item(fetch, len, (int)ic0[j], (int)ic1[j] >= len ? len : (int)ic1[j], iflags[j], T, W, m, sink);
+            if (sink.overflow) { fprintf(stderr, "slot overflow\n"); return 1; }
+            cnt[j] = sink.n;
+            st_item_pos += ic1[j] - ic0[j];
+        }
+        for (uint32_t j = 0; j < ni; ++j) {
+            const uint32_t c = sd_item_gather_count(slots.data(), off.data(), cnt.data(), ic0.data(), iflags.data(), j, W);
+            std::vector<uint64_t> out(c + 1);
+            sd_item_gather_write(slots.data(), off.data(), cnt.data(), ic0.data(), iflags.data(), j, ni, W, out.data());
+            for (uint32_t a = 0; a < c; ++a) printf("%s\t%d\t%d\n", recs[r].name, SD_IV_START(out[a]), SD_IV_FINISH(out[a]));
+        }
+    }
+    orc_free_recs(recs, n);
+    fprintf(stderr, "positions %llu triggers %llu (%.3f%%) active blocks %llu of %llu (%.1f%%) items %llu item positions %llu (%.1f%%)\n",
+            st_pos, st_trig, 100.0 * st_trig / (st_pos ? st_pos : 1), st_active_blk, st_blk, 100.0 * st_active_blk / (st_blk ? st_blk : 1),
+            st_items, st_item_pos, 100.0 * st_item_pos / (st_pos ? st_pos : 1));
+    return 0;
+}
+#endif
+
 int main(int argc, char **argv)
 {
     if (argc < 2) return 1;
@@ -197,5 +279,18 @@ int main(int argc, char **argv)
         if (!f) return 1;
         return sim_sdust(f, T, W, C);
     }
+#if !defined(SD_WIDE)
+    if (!strcmp(argv[1], "sdust2")) {
+        int W = 64, T = 20, C = 4096; const char *f = NULL;
+        for (int i = 2; i < argc; ++i) {
+            if (!strcmp(argv[i], "-w") && i + 1 < argc) W = atoi(argv[++i]);
+            else if (!strcmp(argv[i], "-t") && i + 1 < argc) T = atoi(argv[++i]);
+            else if (!strcmp(argv[i], "-c") && i + 1 < argc) C = atoi(argv[++i]);
+            else f = argv[i];
+        }
+        if (!f) return 1;
+        return sim_sdust2(f, T, W, C);
+    }
+#endif
     return 1;
 }

@@ -6,6 +6,7 @@ C ABI + CUDA) or the C ABI itself via ctypes.  The checkers are the committed go
 the bar is bit-exact.
 """
 import os
+import sys
 import subprocess
 
 import numpy as np
