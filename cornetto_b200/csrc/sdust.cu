@@ -90,6 +90,10 @@ struct SdParams {
     uint32_t *err;
     uint32_t *task_counter;
     const uint32_t *task_list;      // ticket -> warp-task, expensive tasks first
+    // two-phase execution: the work units are ITEMS (runs of active 64-base blocks) instead of the chunks of a fixed grid;
+    // n_chunks then counts the entries of it_list, and slots / gslots / cnt are indexed by item number
+    const uint32_t *it_list;        // NULL: chunk mode.  lane's entry -> item number
+    const uint32_t *it_rec, *it_c0, *it_c1, *it_flags;
 };
 
 // ---- shared-memory layout of a block -------------------------------------------------------------
@@ -301,21 +305,31 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
     // l * n_warps + w).  Low-complexity stretches (satellites, telomeres) make their chunks many times
     // more expensive; spread over the tasks they cost each one slow lane instead of leaving one
     // warp with 32 of them as the kernel's tail.
-    const uint32_t j = (uint32_t)lane * n_warps + warp_id;
-    const bool have = j < P.n_chunks;                 // lanes without a chunk still serve the warp's cooperative calls
+    // (item mode: a task is 32 CONSECUTIVE entries of it_list, which is ordered by length class)
+    const uint32_t e = P.it_list ? warp_id * 32u + (uint32_t)lane : (uint32_t)lane * n_warps + warp_id;
+    const bool have = e < P.n_chunks;                 // lanes without a chunk still serve the warp's cooperative calls
+    const uint32_t j = (have && P.it_list) ? P.it_list[e] : e;      // chunk number, or item number in item mode
     const int T = P.T, W = P.W, cv_max = (P.T << 1) / 10;
     uint32_t *my_slots = P.gslots + (size_t)(have ? j : 0) * lay.slot_words;
     const sd_mem m = sd_mem_of(smem, lay, threadIdx.x, my_slots);
 
     uint32_t rec = 0, k = 0;
     int len = 0, c0 = 0, c1 = 0;
-    if (have) {
+    bool quiet = false;                               // item whose preceding block is quiet: window-only warm-up (P is empty at c0)
+    if (have && P.it_list) {
+        rec = P.it_rec[j];
+        len = (int)P.rec_len[rec];
+        c0 = (int)P.it_c0[j];
+        c1 = (int)P.it_c1[j];
+        quiet = (P.it_flags[j] & SD_ITEM_QUIET) != 0;
+    } else if (have) {
         rec = corn_upper_bound(P.chunk_base, P.n_rec, j) - 1;
         k = j - P.chunk_base[rec];
         len = (int)P.rec_len[rec];
         c0 = (int)k * P.C;
         c1 = min(len, c0 + P.C);
     }
+    (void)k;
     sd_sink sink;
     sd_sink_init(sink, P.slots + (size_t)(have ? j : 0) * P.cap, P.cap);
     DevFetch fetch;
@@ -328,7 +342,8 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
     sd_reset_counters(s, m);                          // (the slot rows were zeroed by a memset before the launch)
     int p0 = 0, n_steps = 0;
     if (have) {
-        p0 = sd_warm_start(fetch, c0, W) & ~15;       // (a longer warm-up is always valid) all lanes then refill their
+        p0 = (quiet ? sd_warm_quiet(fetch, c0, W) : sd_warm_start(fetch, c0, W)) & ~15;
+                                                      // (a longer warm-up is always valid) all lanes then refill their
                                                       // 16-byte fetch buffer on the same steps
         s.pstart = p0; s.pslot = (int)((uint32_t)p0 % (uint32_t)W);
         const int stop = c1 < len ? c1 : len;
@@ -384,7 +399,7 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
             pop_coop<NB>(leader, lane, s, (int)s.t, smem, lay, W);
         }
         bool trig = false;
-        if (emit && s.rw * 10 > s.L * T) {
+        if (emit && s.rw * 10 > s.L * T && !(quiet && p0 + step < c0)) {     // (quiet warm-up: the true run calls nothing here)
             if (!COOP) sd_find_perfect(s, m, T, start, W);
             else trig = s.wn - s.L - 1 >= 0 && s.slack < 0;   // no index to examine / provably no candidate otherwise
         }
@@ -464,9 +479,180 @@ __global__ void __launch_bounds__(SD_BLOCK, (NB == 2 && COOP) ? 8 : 5) k_sdust_s
         if (lane == 0) w = atomicAdd(P.task_counter, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= n_warps) break;
-        sdust_warp_task<NB, COOP>(P, P.task_list[w], n_warps, smem, lay, cnt, lane);
+        sdust_warp_task<NB, COOP>(P, P.task_list ? P.task_list[w] : w, n_warps, smem, lay, cnt, lane);
         __syncwarp();
     }
+}
+
+// =====================================================================================================
+// Two-phase execution (sdust_core.cuh, "Two-phase execution"): scout -> items -> full machine on the items only
+// =====================================================================================================
+constexpr int SC_BLOCK = 128;
+
+struct ScoutParams {
+    const uint8_t  *seq;
+    const uint32_t *rec_off, *rec_len;
+    const uint32_t *chunk_base;     // [n_rec+1] scout chunks (C bases each) before every record
+    const uint32_t *blk_base;       // [n_rec+1] 64-base blocks before every record
+    uint32_t n_rec, n_chunks;
+    int T, W, C;
+    uint8_t *active;                // [n_blk_total + 1], zeroed
+};
+
+// shared-memory accessors of the scout: one 32-bit word per triplet value and a 64-entry byte ring per thread, both as
+// columns (word index = row * SC_BLOCK + thread), so whatever a lane indexes stays in its own bank
+struct ScoutWords {
+    uint32_t *col;
+    __device__ __forceinline__ uint32_t &operator()(uint32_t i) { return col[i * SC_BLOCK]; }
+};
+struct ScoutRing {
+    uint8_t *col;
+    __device__ __forceinline__ uint8_t &operator()(uint32_t i) { return col[(i >> 2) * (SC_BLOCK * 4) + (i & 3u)]; }
+};
+
+// Phase 1.  One thread per chunk of C bases: the window half of the state machine in its loop-free form; wherever the
+// reference would call find_perfect, the 64-base block of that position and the next one (the drain) are marked active.
+__global__ void __launch_bounds__(SC_BLOCK) k_sdust_scout(const ScoutParams P)
+{
+    __shared__ uint32_t sm_words[64 * SC_BLOCK];
+    __shared__ uint32_t sm_ring[16 * SC_BLOCK];
+    const uint32_t g = blockIdx.x * SC_BLOCK + threadIdx.x;
+    const bool have = g < P.n_chunks;
+    ScoutWords words = { sm_words + threadIdx.x };
+    ScoutRing ring = { (uint8_t *)(sm_ring + threadIdx.x) };
+    sd_scout sc;
+    sd_scout_reset(sc, words, ring);
+    uint32_t rec = 0;
+    int len = 0, c0 = 0, c1 = 0, p0 = 0;
+    DevFetch fetch;
+    fetch.seq = P.seq; fetch.blk = -1; fetch.cblk = -1;
+    fetch.buf = make_uint4(0, 0, 0, 0); fetch.codes = 0; fetch.valid = 0;
+    if (have) {
+        rec = corn_upper_bound(P.chunk_base, P.n_rec, g) - 1;
+        len = (int)P.rec_len[rec];
+        c0 = (int)(g - P.chunk_base[rec]) * P.C;
+        c1 = min(len, c0 + P.C);
+        fetch.seq = P.seq + P.rec_off[rec];
+        p0 = sd_warm_quiet(fetch, c0, P.W) & ~15;
+    }
+    uint8_t *act = P.active + (have ? P.blk_base[rec] : 0);
+    const int n_blk = (len + SD_BLK - 1) / SD_BLK;
+    const int T = P.T, W = P.W;
+    const int n_steps = have ? c1 - p0 : 0;
+    // every lane runs (nearly) the same number of steps and no step has a data-dependent loop: the warp stays converged
+    for (int step = 0; step < n_steps; ++step) {
+        const int i = p0 + step;
+        const int b = fetch.nt4(i);
+        if (b < 4) {
+            ++sc.l;
+            sc.t = (sc.t << 2 | (unsigned)b) & 63u;
+            if (sc.l >= 3) {
+                const bool trig = sd_scout_push(sc, words, ring, sc.t, T, W);
+                if (trig && i >= c0) {
+                    const int k = i >> 6;
+                    act[k] = 1;
+                    if (k + 1 < n_blk) act[k + 1] = 1;
+                }
+            }
+        } else { sc.l = 0; sc.t = 0; }
+    }
+}
+
+// Items.  Block j starts an item iff it is active and (the block before it in its record is not, or j lies on the
+// SD_ITEM_MAX grid of its record).  start[] -> exclusive scan -> k_sdust_items writes the item table in position order.
+struct ItemParams {
+    const uint8_t  *active;
+    const uint32_t *blk_base, *rec_len;
+    uint32_t n_rec, n_blk;
+    uint32_t *start;                // [n_blk]: 1 where an item starts; scanned in place to the item number
+    const uint32_t *total;          // number of items (device)
+    uint32_t cap_items;
+    uint32_t *it_rec, *it_c0, *it_c1, *it_flags;
+    uint32_t *it_list, *n_lists;    // item numbers by length class: long ones from the front, short ones from the back of
+                                    // it_list[0 .. *total); n_lists[0] / [1] = short / long items placed so far
+};
+
+__device__ __forceinline__ bool item_starts_at(const uint8_t *__restrict__ active, uint32_t j, uint32_t first_blk_of_rec)
+{
+    if (!active[j]) return false;
+    const uint32_t k = j - first_blk_of_rec;
+    return k == 0 || !active[j - 1] || (k % (SD_ITEM_MAX / SD_BLK)) == 0;
+}
+
+__global__ void __launch_bounds__(256) k_sdust_item_starts(const ItemParams P)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n_blk) return;
+    uint32_t v = 0;
+    if (P.active[j]) {
+        const uint32_t rec = corn_upper_bound(P.blk_base, P.n_rec, j) - 1;
+        v = item_starts_at(P.active, j, P.blk_base[rec]) ? 1u : 0u;
+    }
+    P.start[j] = v;
+}
+
+__global__ void __launch_bounds__(256) k_sdust_items(const ItemParams P, const uint32_t *__restrict__ item_no)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n_blk || !P.active[j]) return;
+    const uint32_t rec = corn_upper_bound(P.blk_base, P.n_rec, j) - 1;
+    const uint32_t b0 = P.blk_base[rec];
+    if (!item_starts_at(P.active, j, b0)) return;
+    const uint32_t it = item_no[j];
+    if (it >= P.cap_items) return;                                     // host grows the tables and repeats
+    const uint32_t len = P.rec_len[rec], k = j - b0, nb = (len + SD_BLK - 1) / SD_BLK;
+    uint32_t e = k + 1;                                                // the item runs to the next cut or to the end of the active run
+    while (e < nb && P.active[b0 + e] && (e % (SD_ITEM_MAX / SD_BLK)) != 0) ++e;
+    const bool prev = k > 0 && P.active[j - 1];
+    P.it_rec[it] = rec;
+    P.it_c0[it] = k * SD_BLK;
+    P.it_c1[it] = min(len, e * SD_BLK);
+    P.it_flags[it] = (prev ? SD_ITEM_CHAIN : 0u) | ((k > 0 && !prev) ? SD_ITEM_QUIET : 0u);
+    // short items (isolated bursts) and long ones (inside low-complexity sequence) go to different warp-tasks: in a
+    // warp all lanes step together, so a 1 kb item among 150-base ones would leave 31 lanes idle most of the time
+    const bool is_long = (e - k) * SD_BLK > 320u;
+    if (is_long) P.it_list[atomicAdd(&P.n_lists[1], 1u)] = it;
+    else P.it_list[*P.total - 1u - atomicAdd(&P.n_lists[0], 1u)] = it;
+}
+
+struct ItemGatherParams {
+    const uint64_t *slots;
+    const uint32_t *cnt, *it_c0, *it_flags, *it_rec;
+    const uint32_t *n_items;        // device
+    uint32_t cap;
+    int W;
+    uint32_t *out_cnt;
+    const uint32_t *out_off;
+    uint64_t *out;
+};
+
+// it_off[] of the fold routines: every item owns `cap` consecutive slots
+struct FixedOff { uint32_t cap; };
+
+__global__ void __launch_bounds__(256) k_sdust_item_gather(const ItemGatherParams P, const uint32_t *__restrict__ off, int write)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *P.n_items;
+    if (j >= n) return;
+    if (!write) { P.out_cnt[j] = sd_item_gather_count(P.slots, off, P.cnt, P.it_c0, P.it_flags, j, P.W); return; }
+    sd_item_gather_write(P.slots, off, P.cnt, P.it_c0, P.it_flags, j, n, P.W, P.out + P.out_off[j]);
+}
+
+__global__ void __launch_bounds__(256) k_sdust_item_off(uint32_t *off, uint32_t n, uint32_t cap)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) off[j] = j * cap;
+}
+
+// rec_first[r] = offset of the first interval of the first item of a record >= r
+__global__ void k_sdust_item_rec_first(const uint32_t *__restrict__ it_rec, const uint32_t *__restrict__ out_off, const uint32_t *__restrict__ n_items,
+                                       const uint32_t *__restrict__ total, uint32_t n_rec, uint64_t *rec_first)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rec) return;
+    const uint32_t n = *n_items;
+    const uint32_t it = corn_lower_bound(it_rec, n, r);               // first item whose record is >= r
+    rec_first[r] = it < n ? out_off[it] : *total;
 }
 
 struct GatherParams {
@@ -503,6 +689,171 @@ __global__ void k_sdust_rec_first(const uint32_t *__restrict__ chunk_base, const
 
 }  // namespace
 
+// --------------------------------------------------------------------------------------------
+// two-phase path (W <= 64, floor(2T/10) == 4: the defaults)
+// --------------------------------------------------------------------------------------------
+static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_intervals_t *out)
+{
+    cudaStream_t st = ctx->stream;
+    const uint32_t n_rec = db->n_rec;
+    uint64_t *h_first = (uint64_t *)corn_host_alloc(sizeof(uint64_t) * ((size_t)n_rec + 1));
+    if (!h_first) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc");
+    out->rec_first = h_first;
+    for (uint32_t r = 0; r <= n_rec; ++r) h_first[r] = 0;
+
+    // scout chunk length: every chunk pays ~W + 16 warm-up positions; 2048 keeps that at 4 % and still gives a 3 Gb
+    // batch 1.5 M threads
+    int C = 2048;
+    if (const char *e = getenv("CORNETTO_SDUST_SCOUT_CHUNK")) { int v = atoi(e); if (v >= 64 && v <= (1 << 20)) C = v / 64 * 64; }
+    uint64_t n_chunks64 = 0, n_blk64 = 0;
+    for (uint32_t r = 0; r < n_rec; ++r) {
+        n_chunks64 += ((uint64_t)db->h_rec_len[r] + C - 1) / C;
+        n_blk64 += ((uint64_t)db->h_rec_len[r] + SD_BLK - 1) / SD_BLK;
+    }
+    if (n_chunks64 == 0) return CORN_OK;
+    if (n_blk64 > 0xFFFFFFF0ull) return corn_set_err(ctx, CORN_E_TOOBIG, "too many sdust blocks");
+    const uint32_t n_chunks = (uint32_t)n_chunks64, n_blk = (uint32_t)n_blk64;
+
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->misc, 4096));
+    uint32_t *d_tot = (uint32_t *)((uint8_t *)ctx->misc.p + 2048);   // [0] intervals, [1] items, [4] overflow errors, [8] task counter, [10..11] list counters
+    uint32_t *d_err = d_tot + 4;
+    CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 64, st));
+
+    // tables: nch | chunk_base | nblk | blk_base (n_rec + 1 each), then start / item_no [n_blk + 1], then active bytes
+    const size_t tab_words = 4 * ((size_t)n_rec + 1) + ((size_t)n_blk + 2) + ((size_t)n_blk + 8) / 4 + 64;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_tab, tab_words * sizeof(uint32_t)));
+    uint32_t *nch = (uint32_t *)ctx->sd_tab.p, *chunk_base = nch + n_rec + 1, *nblk = chunk_base + n_rec + 1, *blk_base = nblk + n_rec + 1;
+    uint32_t *item_no = blk_base + n_rec + 1;
+    uint8_t *active = (uint8_t *)(item_no + n_blk + 2);
+
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    k_sdust_nchunks<<<(n_rec + 255) / 256, 256, 0, st>>>(db->d_rec_len, nch, n_rec, (uint32_t)C);
+    k_sdust_nchunks<<<(n_rec + 255) / 256, 256, 0, st>>>(db->d_rec_len, nblk, n_rec, (uint32_t)SD_BLK);
+    corn_count_launch(ctx, 2);
+    CORN_TRY(corn_scan_u32(ctx, nch, chunk_base, n_rec, chunk_base + n_rec));
+    CORN_TRY(corn_scan_u32(ctx, nblk, blk_base, n_rec, blk_base + n_rec));
+    CORN_CUDA(ctx, cudaMemsetAsync(active, 0, (size_t)n_blk + 4, st));
+
+    // ---- phase 1: scout ----
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    ScoutParams sc;
+    sc.seq = db->d_seq; sc.rec_off = db->d_rec_off; sc.rec_len = db->d_rec_len; sc.chunk_base = chunk_base; sc.blk_base = blk_base;
+    sc.n_rec = n_rec; sc.n_chunks = n_chunks; sc.T = T; sc.W = W; sc.C = C; sc.active = active;
+    k_sdust_scout<<<(n_chunks + SC_BLOCK - 1) / SC_BLOCK, SC_BLOCK, 0, st>>>(sc);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+
+    // ---- items ----
+    ItemParams ip;
+    memset(&ip, 0, sizeof ip);
+    ip.active = active; ip.blk_base = blk_base; ip.rec_len = db->d_rec_len; ip.n_rec = n_rec; ip.n_blk = n_blk;
+    ip.start = item_no; ip.total = d_tot + 1;
+    k_sdust_item_starts<<<(n_blk + 255) / 256, 256, 0, st>>>(ip);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    CORN_TRY(corn_scan_u32(ctx, item_no, item_no, n_blk, d_tot + 1));
+    uint32_t hv[16];
+    CORN_TRY(corn_read_small(ctx, hv, d_tot, 64));
+    const uint32_t n_items = hv[1];
+    if (n_items == 0) {                                  // nothing anywhere that could be masked
+        CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+        CORN_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+        CORN_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+        CORN_CUDA(ctx, cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&ctx->timing.scan_ms, ctx->ev[3], ctx->ev[4]);
+        return CORN_OK;
+    }
+    const uint32_t cap = (uint32_t)(SD_ITEM_MAX + 2 * W) / 4 + 2;
+    if ((uint64_t)n_items * cap > 0xFFFFFFF0ull) {       // (tens of millions of tiny items: slot offsets are 32-bit) the chunk grid takes over
+        corn_host_free(h_first);
+        out->rec_first = NULL;
+        return CORN_E_STATE;
+    }
+    const SdLayout lay(W);
+    const size_t slot_words = (size_t)lay.slot_words;
+    // item tables: rec | c0 | c1 | flags | list | off | cnt | out_cnt | out_off  (n_items + 1 each)
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_out, 9 * ((size_t)n_items + 1) * sizeof(uint32_t)));
+    uint32_t *it_rec = (uint32_t *)ctx->sd_out.p, *it_c0 = it_rec + n_items + 1, *it_c1 = it_c0 + n_items + 1, *it_flags = it_c1 + n_items + 1;
+    uint32_t *it_list = it_flags + n_items + 1, *it_off = it_list + n_items + 1, *cnt = it_off + n_items + 1;
+    uint32_t *out_cnt = cnt + n_items + 1, *out_off = out_cnt + n_items + 1;
+    const size_t iv_bytes = ((size_t)n_items * cap * sizeof(uint64_t) + 255) & ~(size_t)255;
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_slots, iv_bytes + (size_t)n_items * slot_words * sizeof(uint32_t)));
+    uint64_t *slots = (uint64_t *)ctx->sd_slots.p;
+    uint32_t *gslots = (uint32_t *)((uint8_t *)ctx->sd_slots.p + iv_bytes);
+    CORN_CUDA(ctx, cudaMemsetAsync(gslots, 0, (size_t)n_items * slot_words * sizeof(uint32_t), st));
+    ip.cap_items = n_items;
+    ip.it_rec = it_rec; ip.it_c0 = it_c0; ip.it_c1 = it_c1; ip.it_flags = it_flags; ip.it_list = it_list; ip.n_lists = d_tot + 10;
+    k_sdust_items<<<(n_blk + 255) / 256, 256, 0, st>>>(ip, item_no);
+    k_sdust_item_off<<<(n_items + 255) / 256, 256, 0, st>>>(it_off, n_items, cap);
+    corn_count_launch(ctx, 2);
+    CORN_LAUNCH_CHECK(ctx);
+
+    // ---- phase 2: the full machine on the items ----
+    const size_t smem = lay.bytes();
+    typedef void (*sd_kernel_t)(const SdParams);
+    const sd_kernel_t kern = k_sdust_scan<2, true>;       // (sd_scout_supported: W <= 64, T >= 20)
+    CORN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
+    SdParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.seq = db->d_seq; sp.rec_off = db->d_rec_off; sp.rec_len = db->d_rec_len; sp.chunk_base = chunk_base;
+    sp.n_rec = n_rec; sp.n_chunks = n_items; sp.T = T; sp.W = W; sp.C = SD_ITEM_MAX; sp.cap = cap;
+    sp.slots = slots; sp.gslots = gslots; sp.cnt = cnt; sp.err = d_err; sp.task_counter = d_tot + 8; sp.task_list = NULL;
+    sp.it_list = it_list; sp.it_rec = it_rec; sp.it_c0 = it_c0; sp.it_c1 = it_c1; sp.it_flags = it_flags;
+    {
+        const unsigned want = (n_items + SD_BLOCK - 1) / SD_BLOCK, resident = (unsigned)(ctx->sm_count * blocks_per_sm);
+        kern<<<want < resident ? want : resident, SD_BLOCK, smem, st>>>(sp);
+    }
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+
+    // ---- fold across item seams, compact ----
+    ItemGatherParams gp;
+    gp.slots = slots; gp.cnt = cnt; gp.it_c0 = it_c0; gp.it_flags = it_flags; gp.it_rec = it_rec; gp.n_items = d_tot + 1;
+    gp.cap = cap; gp.W = W; gp.out_cnt = out_cnt; gp.out_off = out_off; gp.out = NULL;
+    k_sdust_item_gather<<<(n_items + 255) / 256, 256, 0, st>>>(gp, it_off, 0);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    CORN_TRY(corn_scan_u32(ctx, out_cnt, out_off, n_items, d_tot));
+    CORN_TRY(corn_read_small(ctx, hv, d_tot, 64));
+    const uint32_t n_iv = hv[0];
+    if (hv[4]) return corn_set_err(ctx, CORN_E_INTERNAL, "sdust: %u items overflowed their interval slot", hv[4]);
+    // (the item tables live in sd_out: the compacted intervals and rec_first go to a buffer of their own)
+    const size_t need_out = ((size_t)n_iv + 1) * sizeof(uint64_t) + ((size_t)n_rec + 1) * sizeof(uint64_t);
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bitmap, need_out));
+    gp.out = (uint64_t *)ctx->bitmap.p;
+    uint64_t *d_first = gp.out + n_iv + 1;
+    if (n_iv) {
+        k_sdust_item_gather<<<(n_items + 255) / 256, 256, 0, st>>>(gp, it_off, 1);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+    }
+    k_sdust_item_rec_first<<<(n_rec + 1 + 255) / 256, 256, 0, st>>>(it_rec, out_off, d_tot + 1, d_tot, n_rec, d_first);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+
+    out->n_iv = n_iv;
+    if (n_iv) {
+        out->iv = (uint64_t *)corn_host_alloc((size_t)n_iv * sizeof(uint64_t));
+        if (!out->iv) return corn_set_err(ctx, CORN_E_NOMEM, "pinned alloc of %u intervals", n_iv);
+        CORN_CUDA(ctx, cudaMemcpyAsync(out->iv, gp.out, (size_t)n_iv * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    }
+    CORN_CUDA(ctx, cudaMemcpyAsync(h_first, d_first, ((size_t)n_rec + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+    CORN_CUDA(ctx, cudaStreamSynchronize(st));
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&ctx->timing.scan_ms, ctx->ev[3], ctx->ev[4]);      // scout + item table + item phase
+    cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&b, ctx->ev[4], ctx->ev[5]);
+    ctx->timing.post_ms = a + b;
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[5], ctx->ev[6]);
+    ctx->timing.out_bytes = (uint64_t)n_iv * 8;
+    return CORN_OK;
+}
+
 static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_intervals_t *out)
 {
     // Window range.  The reference accepts whatever atoi() returns (src/sdust/sdust.c:186-189):
@@ -520,6 +871,13 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     memset(&ctx->timing, 0, sizeof ctx->timing);
     ctx->timing.h2d_ms = keep_h2d;
     out->iv = NULL; out->rec_first = NULL; out->n_iv = 0; out->n_rec = db->n_rec; out->_owner = NULL;
+    // the defaults (and anything with W <= 64, 20 <= T <= 24) take the two-phase path; $CORNETTO_SDUST_CLASSIC=1 forces
+    // the chunk-grid kernels, which serve every other (T, W)
+    if (sd_scout_supported(T, W) && !(getenv("CORNETTO_SDUST_CLASSIC") && atoi(getenv("CORNETTO_SDUST_CLASSIC")) > 0))
+    {
+        const int r = sdust_run_fast(ctx, db, T, W, out);
+        if (r != CORN_E_STATE) return r;
+    }
 
     // chunk length: 4096 bases for large batches (5 % warm-up overhead).  A chunk is a serial chain, and
     // the chain of a chunk inside a tandem repeat is ~4x slower than the rest, so on a small batch the
