@@ -742,6 +742,7 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     k_sdust_scout<<<(n_chunks + SC_BLOCK - 1) / SC_BLOCK, SC_BLOCK, 0, st>>>(sc);
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[12], st));
 
     // ---- items ----
     ItemParams ip;
@@ -789,6 +790,7 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     CORN_LAUNCH_CHECK(ctx);
 
     // ---- phase 2: the full machine on the items ----
+    CORN_CUDA(ctx, cudaEventRecord(ctx->ev[13], st));
     const size_t smem = lay.bytes();
     typedef void (*sd_kernel_t)(const SdParams);
     const sd_kernel_t kern = k_sdust_scan<2, true>;       // (sd_scout_supported: W <= 64, T >= 20)
@@ -846,6 +848,14 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     CORN_CUDA(ctx, cudaStreamSynchronize(st));
     float a = 0, b = 0;
     cudaEventElapsedTime(&ctx->timing.scan_ms, ctx->ev[3], ctx->ev[4]);      // scout + item table + item phase
+    if (getenv("CORNETTO_TRACE")) {
+        float t_scout = 0, t_items = 0, t_run = 0;
+        cudaEventElapsedTime(&t_scout, ctx->ev[3], ctx->ev[12]);
+        cudaEventElapsedTime(&t_items, ctx->ev[12], ctx->ev[13]);
+        cudaEventElapsedTime(&t_run, ctx->ev[13], ctx->ev[4]);
+        fprintf(stderr, "[sdust] scout %.3f ms (%u chunks), item table %.3f ms (%u items of %u blocks), item phase %.3f ms, %u intervals\n",
+                t_scout, n_chunks, t_items, n_items, n_blk, t_run, n_iv);
+    }
     cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&b, ctx->ev[4], ctx->ev[5]);
     ctx->timing.post_ms = a + b;
@@ -942,6 +952,7 @@ static int sdust_run(corn_ctx *ctx, const corn_dbatch *db, int T, int W, corn_in
     CORN_TRY(corn_scan_u32(ctx, nch, chunk_base, n_rec, chunk_base + n_rec));
 
     SdParams sp;
+    memset(&sp, 0, sizeof sp);                        // (chunk mode: no item tables)
     sp.seq = db->d_seq; sp.rec_off = db->d_rec_off; sp.rec_len = db->d_rec_len; sp.chunk_base = chunk_base;
     sp.n_rec = n_rec; sp.n_chunks = n_chunks; sp.T = T; sp.W = W; sp.C = C; sp.cap = cap;
     sp.slots = (uint64_t *)ctx->sd_slots.p; sp.cnt = cnt; sp.err = d_err; sp.task_counter = d_tot + 8;

@@ -463,30 +463,114 @@ struct AssembleParams {
     uint32_t *hot_count;
 };
 
-// rank_f[r] = #forward run starts before rec_off[r] (r = 0..n_rec), same for reverse.  Records are
-// chunk aligned, so this is the tile prefix plus the starts of the tile's candidate chunks that lie
-// before the record: three dependent loads instead of a binary search over the event lists.
-__global__ void __launch_bounds__(256) k_telofind_ranks(const AssembleParams P, const uint4 *__restrict__ tile_off,
-                                                        const uint32_t *__restrict__ tile_ncand, const uint32_t *__restrict__ c_idx,
-                                                        const uint32_t *__restrict__ c_sf, const uint32_t *__restrict__ c_sr, uint32_t n_tiles)
+// -------------------------------------------------------------------------------------------
+// tile prefix + record ranks in ONE launch (replaces a three-launch scan and k_telofind_ranks).
+// Exclusive prefix of the per-tile (start_f, end_f, start_r, end_r) counts by a single-pass scan with decoupled
+// look-back: a block owns TP_TILES consecutive tiles, publishes its aggregate, then adds up the aggregates (or the
+// first inclusive prefix it meets) of the blocks before it.  A 4 GiB batch has 131 072 tiles = 128 blocks, all
+// resident at once, so waiting on a predecessor cannot deadlock.  The block then ranks the records that start inside
+// its tiles: rank_f[r] / rank_r[r] = forward / reverse run starts before rec_off[r] = the tile's prefix plus the starts
+// of the tile's candidate chunks that lie before the record (records are chunk aligned).
+// -------------------------------------------------------------------------------------------
+constexpr int TP_THREADS = 256, TP_ITEMS = 4, TP_TILES = TP_THREADS * TP_ITEMS;
+
+struct TilePrefixParams {
+    const uint4 *tile_cnt;
+    uint4 *tile_off;
+    uint32_t n_tiles;
+    uint4 *totals;
+    uint4 *blk_val;            // [n_blocks][2]: aggregate, inclusive prefix
+    uint32_t *blk_flag;        // [n_blocks]: 0 nothing, 1 aggregate published, 2 inclusive prefix published (zeroed before the launch)
+    // ranks
+    const uint32_t *rec_off; uint32_t n_rec;
+    uint32_t *rank_f, *rank_r;
+    const uint32_t *tile_ncand, *c_idx, *c_sf, *c_sr;
+};
+
+__device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__global__ void __launch_bounds__(TP_THREADS) k_telofind_tile_prefix(const TilePrefixParams P)
 {
-    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per record
-    const int lane = threadIdx.x & 31;
-    if (r > P.n_rec) return;
-    const uint4 tot = *P.totals;
-    const uint32_t pos = P.rec_off[r];
-    const uint32_t tile = pos / CORN_TILE_BYTES;
-    uint32_t f = 0, v = 0, f0 = tot.x, v0 = tot.z;
-    if (tile < n_tiles) {
-        const uint4 off = tile_off[tile];
-        f0 = off.x; v0 = off.z;
-        const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
-        const uint32_t n = tile_ncand[tile], chunk = pos / CORN_CHUNK_BYTES;
-        for (uint32_t e = lane; e < n; e += 32)
-            if (c_idx[base + e] < chunk) { f += __popc(c_sf[base + e]); v += __popc(c_sr[base + e]); }
+    __shared__ uint4 warp_tot[TP_THREADS / 32];
+    __shared__ uint4 blk_excl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t t0 = blockIdx.x * TP_TILES + threadIdx.x * TP_ITEMS;
+    uint4 v[TP_ITEMS], sum = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < TP_ITEMS; ++i) {
+        v[i] = t0 + i < P.n_tiles ? P.tile_cnt[t0 + i] : make_uint4(0, 0, 0, 0);
+        sum = add4(sum, v[i]);
     }
-    f = corn_warp_sum(f); v = corn_warp_sum(v);
-    if (lane == 0) { P.rank_f[r] = f0 + f; P.rank_r[r] = v0 + v; }
+    // block-level exclusive scan of the per-thread sums
+    uint4 inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, inc.x, o), b = __shfl_up_sync(0xffffffffu, inc.y, o);
+        const uint32_t c = __shfl_up_sync(0xffffffffu, inc.z, o), d = __shfl_up_sync(0xffffffffu, inc.w, o);
+        if (lane >= o) { inc.x += a; inc.y += b; inc.z += c; inc.w += d; }
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint4 wbase = make_uint4(0, 0, 0, 0), agg = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int w = 0; w < TP_THREADS / 32; ++w) { if (w < warp) wbase = add4(wbase, warp_tot[w]); agg = add4(agg, warp_tot[w]); }
+    // publish the aggregate, look back
+    if (threadIdx.x == 0) {
+        uint4 excl = make_uint4(0, 0, 0, 0);
+        if (blockIdx.x == 0) {
+            P.blk_val[1] = agg;
+            __threadfence();
+            atomicExch(&P.blk_flag[0], 2u);
+        } else {
+            P.blk_val[2 * blockIdx.x] = agg;
+            __threadfence();
+            atomicExch(&P.blk_flag[blockIdx.x], 1u);
+            for (int b = (int)blockIdx.x - 1; b >= 0; --b) {
+                uint32_t f;
+                while ((f = atomicAdd(&P.blk_flag[b], 0u)) == 0u) { }
+                __threadfence();
+                const volatile uint4 *pv = (const volatile uint4 *)&P.blk_val[2 * b + (f == 2u ? 1 : 0)];
+                excl = add4(excl, make_uint4(pv->x, pv->y, pv->z, pv->w));
+                if (f == 2u) break;
+            }
+            P.blk_val[2 * blockIdx.x + 1] = add4(excl, agg);
+            __threadfence();
+            atomicExch(&P.blk_flag[blockIdx.x], 2u);
+        }
+        blk_excl = excl;
+        if (blockIdx.x == gridDim.x - 1) *P.totals = add4(excl, agg);
+    }
+    __syncthreads();
+    uint4 run = add4(blk_excl, add4(wbase, make_uint4(inc.x - sum.x, inc.y - sum.y, inc.z - sum.z, inc.w - sum.w)));
+#pragma unroll
+    for (int i = 0; i < TP_ITEMS; ++i) {
+        if (t0 + i < P.n_tiles) P.tile_off[t0 + i] = run;
+        run = add4(run, v[i]);
+    }
+    __syncthreads();                                    // this block's tile_off entries are visible to the whole block below
+
+    // ---- ranks of the records that start inside this block's tiles (the last block also takes the sentinel n_rec) ----
+    const uint32_t tile_lo = blockIdx.x * TP_TILES, tile_hi = min(P.n_tiles, tile_lo + TP_TILES);
+    const uint32_t r_lo = corn_lower_bound(P.rec_off, P.n_rec, tile_lo * CORN_TILE_BYTES);
+    uint32_t r_hi = tile_hi >= P.n_tiles ? P.n_rec + 1 : corn_lower_bound(P.rec_off, P.n_rec, tile_hi * CORN_TILE_BYTES);
+    for (uint32_t r = r_lo + warp; r < r_hi; r += TP_THREADS / 32) {     // one warp per record
+        const uint32_t pos = P.rec_off[r];                // (rec_off[n_rec] = total bytes)
+        const uint32_t tile = pos / CORN_TILE_BYTES;
+        uint32_t f = 0, q = 0, f0, q0;
+        if (tile < P.n_tiles) {
+            const uint4 off = P.tile_off[tile];
+            f0 = off.x; q0 = off.z;
+            const size_t base = (size_t)tile * CORN_TILE_CHUNKS;
+            const uint32_t n = P.tile_ncand[tile], chunk = pos / CORN_CHUNK_BYTES;
+            for (uint32_t e = lane; e < n; e += 32)
+                if (P.c_idx[base + e] < chunk) { f += __popc(P.c_sf[base + e]); q += __popc(P.c_sr[base + e]); }
+        } else {                                          // behind the last tile: everything
+            const uint4 tot = add4(blk_excl, agg);
+            f0 = tot.x; q0 = tot.z;
+        }
+        f = corn_warp_sum(f); q = corn_warp_sum(q);
+        if (lane == 0) { P.rank_f[r] = f0 + f; P.rank_r[r] = q0 + q; }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_telofind_assemble(const AssembleParams P)
@@ -672,7 +756,25 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
         CORN_LAUNCH_CHECK(ctx);
     }
 
-    CORN_TRY(corn_scan_u32x4(ctx, sp.tile_cnt, tile_off, n_tiles, d_totals));
+    // tile prefix + record ranks, one launch
+    CORN_TRY(corn_dbuf_reserve(ctx, &ctx->ranks, 2 * ((size_t)db->n_rec + 2) * sizeof(uint32_t) + 64));
+    uint32_t *rank_f = (uint32_t *)ctx->ranks.p, *rank_r = rank_f + db->n_rec + 2;
+    if (n_tiles) {
+        const uint32_t n_tp = (n_tiles + TP_TILES - 1) / TP_TILES;
+        CORN_TRY(corn_dbuf_reserve(ctx, &ctx->scan_tmp, (size_t)n_tp * (2 * sizeof(uint4) + sizeof(uint32_t)) + 64));
+        TilePrefixParams tp;
+        tp.tile_cnt = sp.tile_cnt; tp.tile_off = tile_off; tp.n_tiles = n_tiles; tp.totals = d_totals;
+        tp.blk_val = (uint4 *)ctx->scan_tmp.p; tp.blk_flag = (uint32_t *)(tp.blk_val + 2 * (size_t)n_tp);
+        tp.rec_off = db->d_rec_off; tp.n_rec = db->n_rec; tp.rank_f = rank_f; tp.rank_r = rank_r;
+        tp.tile_ncand = sp.tile_ncand; tp.c_idx = sp.c_idx; tp.c_sf = sp.c_a; tp.c_sr = sp.c_b;
+        CORN_CUDA(ctx, cudaMemsetAsync(tp.blk_flag, 0, (size_t)n_tp * sizeof(uint32_t), st));
+        k_telofind_tile_prefix<<<n_tp, TP_THREADS, 0, st>>>(tp);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+    } else {
+        CORN_CUDA(ctx, cudaMemsetAsync(d_totals, 0, sizeof(uint4), st));
+        CORN_CUDA(ctx, cudaMemsetAsync(rank_f, 0, 2 * ((size_t)db->n_rec + 2) * sizeof(uint32_t), st));
+    }
 
     // Everything below is launched against SPECULATIVE buffer capacities (grow-only, remembered across
     // calls) with the exact totals read by the kernels from device memory; the host looks at the
@@ -698,11 +800,10 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
             ctx->counters_clean = 1;
         }
         if (!mi.bordered) {
-            CORN_TRY(corn_dbuf_reserve(ctx, &ctx->ranks, 2 * ((size_t)db->n_rec + 2) * sizeof(uint32_t)));
             AssembleParams ap;
             ap.ev = ev; ap.totals = d_totals; ap.ev_capacity = (uint32_t)ev_cap; ap.run_capacity = (uint32_t)run_cap;
             ap.rec_off = db->d_rec_off; ap.n_rec = db->n_rec;
-            ap.rank_f = (uint32_t *)ctx->ranks.p; ap.rank_r = ap.rank_f + db->n_rec + 2;
+            ap.rank_f = rank_f; ap.rank_r = rank_r;
             ap.out = (corn_run_t *)ctx->runs.p; ap.err = d_err;
             ap.bin_base = NULL; ap.bins = NULL; ap.hot_list = NULL; ap.hot_count = NULL;
             if (!mi.strands_overlap && db->n_rec && db->d_bin_base && db->n_bins_total <= 0xFFFFFF00ull) {
@@ -715,9 +816,8 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
                 CORN_CUDA(ctx, cudaMemsetAsync(ap.hot_count, 0, sizeof(uint32_t), st));
             }
             if (db->n_rec) {
-                k_telofind_ranks<<<(unsigned)(((size_t)db->n_rec + 1 + 7) / 8), 256, 0, st>>>(ap, tile_off, sp.tile_ncand, sp.c_idx, sp.c_a, sp.c_b, n_tiles);
                 k_telofind_assemble<<<ctx->sm_count * 8, 256, 0, st>>>(ap);
-                corn_count_launch(ctx, 2);
+                corn_count_launch(ctx);
                 CORN_LAUNCH_CHECK(ctx);
                 ctx->bins_for_db = ap.bins ? db : NULL;       // (a capacity overflow leaves them empty; the repeat below refills them)
             }
@@ -752,11 +852,11 @@ static int telofind_run(corn_ctx *ctx, const corn_dbatch *db, const char *motif,
             }
             if (db->n_rec) {
                 const size_t n2 = 2 * (size_t)db->n_rec;
-                CORN_TRY(corn_dbuf_reserve(ctx, &ctx->ranks, (2 * n2 + 8) * sizeof(uint32_t)));
+                CORN_TRY(corn_dbuf_reserve(ctx, &ctx->bins, (2 * n2 + 8) * sizeof(uint32_t)));   // (bins is free here: bordered motifs never fuse them)
                 GreedyParams gp;
                 gp.occ_f = ev; gp.occ_r = ev + tot[0]; gp.n_f = tot[0]; gp.n_r = tot[2];
                 gp.rec_off = db->d_rec_off; gp.n_rec = db->n_rec; gp.m = mi.m;
-                gp.cnt = (uint32_t *)ctx->ranks.p; uint32_t *goff = gp.cnt + n2; gp.off = goff; gp.out = NULL;
+                gp.cnt = (uint32_t *)ctx->bins.p; uint32_t *goff = gp.cnt + n2; gp.off = goff; gp.out = NULL;
                 k_telofind_greedy<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>(gp);
                 corn_count_launch(ctx);
                 CORN_LAUNCH_CHECK(ctx);
