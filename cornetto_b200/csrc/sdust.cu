@@ -94,6 +94,7 @@ struct SdParams {
     // n_chunks then counts the entries of it_list, and slots / gslots / cnt are indexed by item number
     const uint32_t *it_list;        // NULL: chunk mode.  lane's entry -> item number
     const uint32_t *it_rec, *it_c0, *it_c1, *it_flags;
+    const uint32_t *list_lo, *list_hi;   // device: this launch serves the entries [*list_lo, *list_hi) of it_list
 };
 
 // ---- shared-memory layout of a block -------------------------------------------------------------
@@ -296,21 +297,28 @@ __device__ __forceinline__ void fp_coop(int leader, int lane, sd_state &s, int m
 // find_perfect (T >= 5; below that a candidate can have new_l == 0 and the serial form is used).
 // Template parameters rather than run-time switches: the register allocation of the default
 // W = 64 kernel is then not sized by the four-block arrays of the W = 128 one.
-template <int NB, bool COOP>
-__device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp_id, uint32_t n_warps, uint32_t *smem, const SdLayout &lay,
-                                                uint8_t *cnt, int lane)
+template <int NB, bool COOP, bool SSM>   // SSM: the perfect-interval slot rows live in shared memory (dense items), else in global memory
+__device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp_id, uint32_t n_warps, uint32_t first_entry, uint32_t n_entries,
+                                                uint32_t *smem, const SdLayout &lay, uint8_t *cnt, int lane)
 {
     const uint32_t FULL = 0xffffffffu;
     // chunk of this lane: consecutive chunks go to DIFFERENT warp-tasks (lane l of task w takes chunk
     // l * n_warps + w).  Low-complexity stretches (satellites, telomeres) make their chunks many times
     // more expensive; spread over the tasks they cost each one slow lane instead of leaving one
     // warp with 32 of them as the kernel's tail.
-    // (item mode: a task is 32 CONSECUTIVE entries of it_list, which is ordered by length class)
+    // (item mode: a task is 32 CONSECUTIVE entries of this launch's part of it_list)
     const uint32_t e = P.it_list ? warp_id * 32u + (uint32_t)lane : (uint32_t)lane * n_warps + warp_id;
-    const bool have = e < P.n_chunks;                 // lanes without a chunk still serve the warp's cooperative calls
-    const uint32_t j = (have && P.it_list) ? P.it_list[e] : e;      // chunk number, or item number in item mode
+    const bool have = e < n_entries;                  // lanes without a chunk still serve the warp's cooperative calls
+    const uint32_t j = (have && P.it_list) ? P.it_list[first_entry + e] : e;      // chunk number, or item number in item mode
     const int T = P.T, W = P.W, cv_max = (P.T << 1) / 10;
     uint32_t *my_slots = P.gslots + (size_t)(have ? j : 0) * lay.slot_words;
+    if (SSM) {
+        // inside low-complexity sequence the slots are read and written at every step: ~60 dependent accesses per
+        // find_perfect call, which from L2 made a step take ~20 k cycles.  One odd-strided row per thread, zeroed here
+        // (the global rows were zeroed by a memset before the launch).
+        my_slots = smem + (size_t)SD_BLOCK * (32 + lay.ring_words) + 16 * (SD_BLOCK / 32) + (size_t)threadIdx.x * lay.slot_words;
+        for (int q = 0; q < lay.slot_words; ++q) my_slots[q] = 0;
+    }
     const sd_mem m = sd_mem_of(smem, lay, threadIdx.x, my_slots);
 
     uint32_t rec = 0, k = 0;
@@ -466,20 +474,22 @@ __global__ void __launch_bounds__(256) k_sdust_order(const uint8_t *__restrict__
 
 // Persistent grid: warps claim warp-tasks from a counter, so the kernel ends one task -- not one wave
 // of blocks -- after the last claim.
-template <int NB, bool COOP>
-__global__ void __launch_bounds__(SD_BLOCK, (NB == 2 && COOP) ? 8 : 5) k_sdust_scan(const SdParams P)
+template <int NB, bool COOP, bool SSM = false>
+__global__ void __launch_bounds__(SD_BLOCK, (NB == 2 && COOP) ? 8 : (SSM ? 3 : 5)) k_sdust_scan(const SdParams P)
 {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31;
     const SdLayout lay(P.W);
     uint8_t *cnt = (uint8_t *)(smem + (size_t)SD_BLOCK * (32 + lay.ring_words)) + 64 * (threadIdx.x >> 5);
-    const uint32_t n_warps = (P.n_chunks + 31u) / 32u;
+    uint32_t first_entry = 0, n_entries = P.n_chunks;
+    if (P.it_list) { first_entry = *P.list_lo; n_entries = *P.list_hi - first_entry; }
+    const uint32_t n_warps = (n_entries + 31u) / 32u;
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(P.task_counter, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= n_warps) break;
-        sdust_warp_task<NB, COOP>(P, P.task_list ? P.task_list[w] : w, n_warps, smem, lay, cnt, lane);
+        sdust_warp_task<NB, COOP, SSM>(P, P.task_list ? P.task_list[w] : w, n_warps, first_entry, n_entries, smem, lay, cnt, lane);
         __syncwarp();
     }
 }
@@ -497,6 +507,7 @@ struct ScoutParams {
     uint32_t n_rec, n_chunks;
     int T, W, C;
     uint8_t *active;                // [n_blk_total + 1], zeroed
+    uint8_t *tcnt;                  // [n_blk_total + 1], zeroed: trigger positions per block (written by the block's own chunk only)
 };
 
 // shared-memory accessors of the scout: one 32-bit word per triplet value and a 64-entry byte ring per thread, both as
@@ -536,6 +547,7 @@ __global__ void __launch_bounds__(SC_BLOCK) k_sdust_scout(const ScoutParams P)
         p0 = sd_warm_quiet(fetch, c0, P.W) & ~15;
     }
     uint8_t *act = P.active + (have ? P.blk_base[rec] : 0);
+    uint8_t *tcn = P.tcnt + (have ? P.blk_base[rec] : 0);
     const int n_blk = (len + SD_BLK - 1) / SD_BLK;
     const int T = P.T, W = P.W;
     const int n_steps = have ? c1 - p0 : 0;
@@ -552,6 +564,7 @@ __global__ void __launch_bounds__(SC_BLOCK) k_sdust_scout(const ScoutParams P)
                     const int k = i >> 6;
                     act[k] = 1;
                     if (k + 1 < n_blk) act[k + 1] = 1;
+                    tcn[k] = (uint8_t)(tcn[k] + 1);          // (chunks are multiples of 64 bases: block k is this thread's alone)
                 }
             }
         } else { sc.l = 0; sc.t = 0; }
@@ -561,15 +574,15 @@ __global__ void __launch_bounds__(SC_BLOCK) k_sdust_scout(const ScoutParams P)
 // Items.  Block j starts an item iff it is active and (the block before it in its record is not, or j lies on the
 // SD_ITEM_MAX grid of its record).  start[] -> exclusive scan -> k_sdust_items writes the item table in position order.
 struct ItemParams {
-    const uint8_t  *active;
+    const uint8_t  *active, *tcnt;
     const uint32_t *blk_base, *rec_len;
     uint32_t n_rec, n_blk;
     uint32_t *start;                // [n_blk]: 1 where an item starts; scanned in place to the item number
     const uint32_t *total;          // number of items (device)
     uint32_t cap_items;
     uint32_t *it_rec, *it_c0, *it_c1, *it_flags;
-    uint32_t *it_list, *n_lists;    // item numbers by length class: long ones from the front, short ones from the back of
-                                    // it_list[0 .. *total); n_lists[0] / [1] = short / long items placed so far
+    uint32_t *it_list, *n_lists;    // item numbers by class: dense ones from the front, sparse ones from the back of
+                                    // it_list[0 .. *total); n_lists[0] / [1] = sparse / dense items placed so far
 };
 
 __device__ __forceinline__ bool item_starts_at(const uint8_t *__restrict__ active, uint32_t j, uint32_t first_blk_of_rec)
@@ -608,10 +621,15 @@ __global__ void __launch_bounds__(256) k_sdust_items(const ItemParams P, const u
     P.it_c0[it] = k * SD_BLK;
     P.it_c1[it] = min(len, e * SD_BLK);
     P.it_flags[it] = (prev ? SD_ITEM_CHAIN : 0u) | ((k > 0 && !prev) ? SD_ITEM_QUIET : 0u);
-    // short items (isolated bursts) and long ones (inside low-complexity sequence) go to different warp-tasks: in a
-    // warp all lanes step together, so a 1 kb item among 150-base ones would leave 31 lanes idle most of the time
-    const bool is_long = (e - k) * SD_BLK > 320u;
-    if (is_long) P.it_list[atomicAdd(&P.n_lists[1], 1u)] = it;
+    // Two classes.  DENSE items lie inside low-complexity sequence (a microsatellite, a telomere): find_perfect runs at
+    // (nearly) every step there, and a warp whose 32 lanes are all in that state does best with the serial per-lane
+    // routine -- the cooperative one serves one lane at a time.  SPARSE items are isolated bursts on ordinary sequence:
+    // a call every few dozen steps per lane, which the cooperative routine serves without stalling 31 lanes for ~60
+    // iterations.  The two classes are run by two launches (k_sdust_scan<2, false> / <2, true>).
+    uint32_t trig = 0;
+    for (uint32_t b = k; b < e; ++b) trig += P.tcnt[b0 + b];
+    const bool dense = trig * 4u >= (e - k) * SD_BLK;
+    if (dense) P.it_list[atomicAdd(&P.n_lists[1], 1u)] = it;
     else P.it_list[*P.total - 1u - atomicAdd(&P.n_lists[0], 1u)] = it;
 }
 
@@ -720,11 +738,13 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 64, st));
 
     // tables: nch | chunk_base | nblk | blk_base (n_rec + 1 each), then start / item_no [n_blk + 1], then active bytes
-    const size_t tab_words = 4 * ((size_t)n_rec + 1) + ((size_t)n_blk + 2) + ((size_t)n_blk + 8) / 4 + 64;
+    const size_t tab_words = 4 * ((size_t)n_rec + 1) + ((size_t)n_blk + 2) + 2 * (((size_t)n_blk + 8) / 4 + 2) + 64;
     CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_tab, tab_words * sizeof(uint32_t)));
     uint32_t *nch = (uint32_t *)ctx->sd_tab.p, *chunk_base = nch + n_rec + 1, *nblk = chunk_base + n_rec + 1, *blk_base = nblk + n_rec + 1;
     uint32_t *item_no = blk_base + n_rec + 1;
     uint8_t *active = (uint8_t *)(item_no + n_blk + 2);
+    const size_t act_bytes = (((size_t)n_blk + 8) / 4 + 2) * 4;
+    uint8_t *tcnt = active + act_bytes;
 
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     k_sdust_nchunks<<<(n_rec + 255) / 256, 256, 0, st>>>(db->d_rec_len, nch, n_rec, (uint32_t)C);
@@ -732,13 +752,13 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     corn_count_launch(ctx, 2);
     CORN_TRY(corn_scan_u32(ctx, nch, chunk_base, n_rec, chunk_base + n_rec));
     CORN_TRY(corn_scan_u32(ctx, nblk, blk_base, n_rec, blk_base + n_rec));
-    CORN_CUDA(ctx, cudaMemsetAsync(active, 0, (size_t)n_blk + 4, st));
+    CORN_CUDA(ctx, cudaMemsetAsync(active, 0, 2 * act_bytes, st));
 
     // ---- phase 1: scout ----
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     ScoutParams sc;
     sc.seq = db->d_seq; sc.rec_off = db->d_rec_off; sc.rec_len = db->d_rec_len; sc.chunk_base = chunk_base; sc.blk_base = blk_base;
-    sc.n_rec = n_rec; sc.n_chunks = n_chunks; sc.T = T; sc.W = W; sc.C = C; sc.active = active;
+    sc.n_rec = n_rec; sc.n_chunks = n_chunks; sc.T = T; sc.W = W; sc.C = C; sc.active = active; sc.tcnt = tcnt;
     k_sdust_scout<<<(n_chunks + SC_BLOCK - 1) / SC_BLOCK, SC_BLOCK, 0, st>>>(sc);
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
@@ -747,7 +767,7 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     // ---- items ----
     ItemParams ip;
     memset(&ip, 0, sizeof ip);
-    ip.active = active; ip.blk_base = blk_base; ip.rec_len = db->d_rec_len; ip.n_rec = n_rec; ip.n_blk = n_blk;
+    ip.active = active; ip.tcnt = tcnt; ip.blk_base = blk_base; ip.rec_len = db->d_rec_len; ip.n_rec = n_rec; ip.n_blk = n_blk;
     ip.start = item_no; ip.total = d_tot + 1;
     k_sdust_item_starts<<<(n_blk + 255) / 256, 256, 0, st>>>(ip);
     corn_count_launch(ctx);
@@ -793,22 +813,28 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[13], st));
     const size_t smem = lay.bytes();
     typedef void (*sd_kernel_t)(const SdParams);
-    const sd_kernel_t kern = k_sdust_scan<2, true>;       // (sd_scout_supported: W <= 64, T >= 20)
-    CORN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int blocks_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
     SdParams sp;
     memset(&sp, 0, sizeof sp);
     sp.seq = db->d_seq; sp.rec_off = db->d_rec_off; sp.rec_len = db->d_rec_len; sp.chunk_base = chunk_base;
     sp.n_rec = n_rec; sp.n_chunks = n_items; sp.T = T; sp.W = W; sp.C = SD_ITEM_MAX; sp.cap = cap;
-    sp.slots = slots; sp.gslots = gslots; sp.cnt = cnt; sp.err = d_err; sp.task_counter = d_tot + 8; sp.task_list = NULL;
+    sp.slots = slots; sp.gslots = gslots; sp.cnt = cnt; sp.err = d_err; sp.task_list = NULL;
     sp.it_list = it_list; sp.it_rec = it_rec; sp.it_c0 = it_c0; sp.it_c1 = it_c1; sp.it_flags = it_flags;
-    {
+    // d_tot: [1] items, [11] dense items (they fill it_list from the front), [13] = 0
+    for (int dense = 1; dense >= 0; --dense) {            // the dense items first: fewer, longer tasks
+        const sd_kernel_t kern = dense ? k_sdust_scan<2, false, true> : k_sdust_scan<2, true, false>;
+        const size_t smem_k = smem + (dense ? (size_t)SD_BLOCK * lay.slot_words * sizeof(uint32_t) : 0);
+        CORN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
+        int blocks_per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SD_BLOCK, smem_k) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
+        sp.list_lo = dense ? d_tot + 13 : d_tot + 11;
+        sp.list_hi = dense ? d_tot + 11 : d_tot + 1;
+        sp.task_counter = dense ? d_tot + 12 : d_tot + 8;
         const unsigned want = (n_items + SD_BLOCK - 1) / SD_BLOCK, resident = (unsigned)(ctx->sm_count * blocks_per_sm);
-        kern<<<want < resident ? want : resident, SD_BLOCK, smem, st>>>(sp);
+        kern<<<want < resident ? want : resident, SD_BLOCK, smem_k, st>>>(sp);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
+        if (dense) CORN_CUDA(ctx, cudaEventRecord(ctx->ev[14], st));
     }
-    corn_count_launch(ctx);
-    CORN_LAUNCH_CHECK(ctx);
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
 
     // ---- fold across item seams, compact ----
@@ -849,12 +875,13 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     float a = 0, b = 0;
     cudaEventElapsedTime(&ctx->timing.scan_ms, ctx->ev[3], ctx->ev[4]);      // scout + item table + item phase
     if (getenv("CORNETTO_TRACE")) {
-        float t_scout = 0, t_items = 0, t_run = 0;
+        float t_scout = 0, t_items = 0, t_dense = 0, t_sparse = 0;
         cudaEventElapsedTime(&t_scout, ctx->ev[3], ctx->ev[12]);
         cudaEventElapsedTime(&t_items, ctx->ev[12], ctx->ev[13]);
-        cudaEventElapsedTime(&t_run, ctx->ev[13], ctx->ev[4]);
-        fprintf(stderr, "[sdust] scout %.3f ms (%u chunks), item table %.3f ms (%u items of %u blocks), item phase %.3f ms, %u intervals\n",
-                t_scout, n_chunks, t_items, n_items, n_blk, t_run, n_iv);
+        cudaEventElapsedTime(&t_dense, ctx->ev[13], ctx->ev[14]);
+        cudaEventElapsedTime(&t_sparse, ctx->ev[14], ctx->ev[4]);
+        fprintf(stderr, "[sdust] scout %.3f ms (%u chunks), item table %.3f ms (%u items of %u blocks), dense items %.3f ms, sparse items %.3f ms, %u intervals\n",
+                t_scout, n_chunks, t_items, n_items, n_blk, t_dense, t_sparse, n_iv);
     }
     cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&b, ctx->ev[4], ctx->ev[5]);

@@ -531,7 +531,8 @@ SD_HD void sd_run_item(Fetch &fetch, int l_seq, int c0, int c1, uint32_t flags, 
 // --------------------------------------------------------------------------------------------
 #if !defined(SD_WIDE)
 #define SD_BLK 64                 /* activity granularity (bases) */
-#define SD_ITEM_MAX 1024          /* longest item (bases); >= 4W so that a seam fold never looks past one item */
+#define SD_ITEM_MAX 512           /* longest item (bases); >= 4W so that a seam fold never looks past one item.  Short items keep
+                                     the serial chain of a task inside a long low-complexity run short (it bounds the kernel's tail) */
 
 struct sd_scout {
     uint32_t wn, L, rw, e;        // window size, suffix length, window score, emitted-triplet counter (ring position = e & 63)
