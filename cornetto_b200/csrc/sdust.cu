@@ -508,17 +508,20 @@ struct ScoutParams {
     int T, W, C;
     uint8_t *active;                // [n_blk_total + 1], zeroed
     uint8_t *tcnt;                  // [n_blk_total + 1], zeroed: trigger positions per block (written by the block's own chunk only)
+    uint8_t *nflag;                 // [n_blk_total + 1], zeroed: the block holds a non-ACGT byte
 };
 
-// shared-memory accessors of the scout: one 32-bit word per triplet value and a 64-entry byte ring per thread, both as
-// columns (word index = row * SC_BLOCK + thread), so whatever a lane indexes stays in its own bank
+// shared-memory accessors of the scout: one 32-bit word per triplet value as a column (word index = row * SC_BLOCK +
+// thread: whatever a lane indexes stays in its own bank) and a 64-entry byte ring per thread as a plain row with an odd
+// word stride (one add per access; lanes that index the same entry -- the usual case -- hit 32 different banks)
+constexpr int SC_RING_STRIDE = 68;
 struct ScoutWords {
     uint32_t *col;
     __device__ __forceinline__ uint32_t &operator()(uint32_t i) { return col[i * SC_BLOCK]; }
 };
 struct ScoutRing {
-    uint8_t *col;
-    __device__ __forceinline__ uint8_t &operator()(uint32_t i) { return col[(i >> 2) * (SC_BLOCK * 4) + (i & 3u)]; }
+    uint8_t *row;
+    __device__ __forceinline__ uint8_t &operator()(uint32_t i) { return row[i]; }
 };
 
 // Phase 1.  One thread per chunk of C bases: the window half of the state machine in its loop-free form; wherever the
@@ -526,55 +529,67 @@ struct ScoutRing {
 __global__ void __launch_bounds__(SC_BLOCK) k_sdust_scout(const ScoutParams P)
 {
     __shared__ uint32_t sm_words[64 * SC_BLOCK];
-    __shared__ uint32_t sm_ring[16 * SC_BLOCK];
+    __shared__ uint32_t sm_ring[SC_RING_STRIDE / 4 * SC_BLOCK];
     const uint32_t g = blockIdx.x * SC_BLOCK + threadIdx.x;
     const bool have = g < P.n_chunks;
     ScoutWords words = { sm_words + threadIdx.x };
-    ScoutRing ring = { (uint8_t *)(sm_ring + threadIdx.x) };
+    ScoutRing ring = { (uint8_t *)sm_ring + threadIdx.x * SC_RING_STRIDE };
     sd_scout sc;
     sd_scout_reset(sc, words, ring);
     uint32_t rec = 0;
     int len = 0, c0 = 0, c1 = 0, p0 = 0;
-    DevFetch fetch;
-    fetch.seq = P.seq; fetch.blk = -1; fetch.cblk = -1;
-    fetch.buf = make_uint4(0, 0, 0, 0); fetch.codes = 0; fetch.valid = 0;
+    const uint8_t *seq = P.seq;
     if (have) {
         rec = corn_upper_bound(P.chunk_base, P.n_rec, g) - 1;
         len = (int)P.rec_len[rec];
         c0 = (int)(g - P.chunk_base[rec]) * P.C;
         c1 = min(len, c0 + P.C);
-        fetch.seq = P.seq + P.rec_off[rec];
+        seq = P.seq + P.rec_off[rec];
+        DevFetch fetch;
+        fetch.seq = seq; fetch.blk = -1; fetch.cblk = -1;
+        fetch.buf = make_uint4(0, 0, 0, 0); fetch.codes = 0; fetch.valid = 0;
         p0 = sd_warm_quiet(fetch, c0, P.W) & ~15;
     }
     uint8_t *act = P.active + (have ? P.blk_base[rec] : 0);
     uint8_t *tcn = P.tcnt + (have ? P.blk_base[rec] : 0);
+    uint8_t *nfl = P.nflag + (have ? P.blk_base[rec] : 0);
     const int n_blk = (len + SD_BLK - 1) / SD_BLK;
     const int T = P.T, W = P.W;
-    const int n_steps = have ? c1 - p0 : 0;
-    // every lane runs (nearly) the same number of steps and no step has a data-dependent loop: the warp stays converged
-    for (int step = 0; step < n_steps; ++step) {
-        const int i = p0 + step;
-        const int b = fetch.nt4(i);
-        if (b < 4) {
-            ++sc.l;
-            sc.t = (sc.t << 2 | (unsigned)b) & 63u;
-            if (sc.l >= 3) {
-                const bool trig = sd_scout_push(sc, words, ring, sc.t, T, W);
-                if (trig && i >= c0) {
-                    const int k = i >> 6;
-                    act[k] = 1;
-                    if (k + 1 < n_blk) act[k + 1] = 1;
-                    tcn[k] = (uint8_t)(tcn[k] + 1);          // (chunks are multiples of 64 bases: block k is this thread's alone)
-                }
+    // sixteen positions per 16-byte load, decoded at once (nt4x4) and stepped through with compile-time shifts.  Every
+    // lane runs (nearly) the same number of steps and no step has a data-dependent loop: the warp stays converged.
+    for (int ib = p0; have && ib < c1; ib += 16) {
+        const uint4 v = __ldg((const uint4 *)(seq + ib));
+        uint32_t v0, v1, v2, v3;
+        const uint32_t codes = nt4x4(v.x, &v0) | (nt4x4(v.y, &v1) << 8) | (nt4x4(v.z, &v2) << 16) | (nt4x4(v.w, &v3) << 24);
+        const uint32_t valid = v0 | (v1 << 4) | (v2 << 8) | (v3 << 12);
+        const int rem = c1 - ib;                              // positions of this group inside the chunk
+        const bool own = ib >= c0;                            // (c0 is a multiple of 64, p0 of 16)
+        const int k = ib >> 6;
+        const uint32_t real = rem < 16 ? (1u << rem) - 1u : 0xFFFFu;
+        if ((valid & real) != real) nfl[k] = 1;               // a non-ACGT byte in this block (any thread may say so)
+        uint32_t ntrig = 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if (q < rem) {
+                if ((valid >> q) & 1u) {
+                    ++sc.l;
+                    sc.t = (sc.t << 2 | ((codes >> (2 * q)) & 3u)) & 63u;
+                    if (sc.l >= 3 && sd_scout_push(sc, words, ring, sc.t, T, W)) ++ntrig;
+                } else { sc.l = 0; sc.t = 0; }
             }
-        } else { sc.l = 0; sc.t = 0; }
+        }
+        if (ntrig && own) {                                   // (a 16-base group lies inside one 64-base block)
+            act[k] = 1;
+            if (k + 1 < n_blk) act[k + 1] = 1;
+            tcn[k] = (uint8_t)(tcn[k] + ntrig);               // (chunks are multiples of 64 bases: block k is this thread's alone)
+        }
     }
 }
 
 // Items.  Block j starts an item iff it is active and (the block before it in its record is not, or j lies on the
 // SD_ITEM_MAX grid of its record).  start[] -> exclusive scan -> k_sdust_items writes the item table in position order.
 struct ItemParams {
-    const uint8_t  *active, *tcnt;
+    const uint8_t  *active, *tcnt, *nflag;
     const uint32_t *blk_base, *rec_len;
     uint32_t n_rec, n_blk;
     uint32_t *start;                // [n_blk]: 1 where an item starts; scanned in place to the item number
@@ -622,13 +637,15 @@ __global__ void __launch_bounds__(256) k_sdust_items(const ItemParams P, const u
     P.it_c1[it] = min(len, e * SD_BLK);
     P.it_flags[it] = (prev ? SD_ITEM_CHAIN : 0u) | ((k > 0 && !prev) ? SD_ITEM_QUIET : 0u);
     // Two classes.  DENSE items lie inside low-complexity sequence (a microsatellite, a telomere): find_perfect runs at
-    // (nearly) every step there, and a warp whose 32 lanes are all in that state does best with the serial per-lane
-    // routine -- the cooperative one serves one lane at a time.  SPARSE items are isolated bursts on ordinary sequence:
-    // a call every few dozen steps per lane, which the cooperative routine serves without stalling 31 lanes for ~60
-    // iterations.  The two classes are run by two launches (k_sdust_scan<2, false> / <2, true>).
+    // (nearly) every step there; one warp runs one such item with the window spread over its lanes (k_sdust_dense).
+    // SPARSE items are isolated bursts on ordinary sequence -- a call every few dozen steps -- and 32 of them share a
+    // warp, one per lane, with the cooperative routines serving whichever lane needs them (k_sdust_scan<2, true>).
     uint32_t trig = 0;
     for (uint32_t b = k; b < e; ++b) trig += P.tcnt[b0 + b];
-    const bool dense = trig * 4u >= (e - k) * SD_BLK;
+    bool dense = trig * 4u >= (e - k) * SD_BLK;
+    // the dense kernel only takes items without a non-ACGT byte from their warm start (at most 3W + 2 = 194 bases, i.e.
+    // four blocks, before c0) to their end
+    for (uint32_t b = k >= 4u ? k - 4u : 0u; dense && b < e; ++b) dense = P.nflag[b0 + b] == 0;
     if (dense) P.it_list[atomicAdd(&P.n_lists[1], 1u)] = it;
     else P.it_list[*P.total - 1u - atomicAdd(&P.n_lists[0], 1u)] = it;
 }
@@ -671,6 +688,148 @@ __global__ void k_sdust_item_rec_first(const uint32_t *__restrict__ it_rec, cons
     const uint32_t n = *n_items;
     const uint32_t it = corn_lower_bound(it_rec, n, r);               // first item whose record is >= r
     rec_first[r] = it < n ? out_off[it] : *total;
+}
+
+// -------------------------------------------------------------------------------------------------------
+// DENSE items: one warp per item, the window spread over the lanes in AGE order (lane = age, two ages per lane).
+// This is sd_run_item_dense() of sdust_core.cuh (the plain-array statement, checked against the oracle in tests/sim)
+// with the loops over ages turned into ballots, shuffles and warp scans.  Only items without a non-ACGT byte in
+// [p0, c1) come here (k_sdust_items checks the scout's per-block flags).
+// -------------------------------------------------------------------------------------------------------
+struct DenseParams {
+    const uint8_t  *seq;
+    const uint32_t *rec_off, *rec_len;
+    const uint32_t *it_list, *it_rec, *it_c0, *it_c1, *it_flags;
+    const uint32_t *n_dense;        // device: the dense items are it_list[0 .. *n_dense)
+    int T, W;
+    uint32_t cap;
+    uint64_t *slots;                // item number * cap
+    uint32_t *cnt, *err, *task_counter;
+};
+
+__device__ __forceinline__ void frac_scan_step(int &r, int &l, int o, int lane)
+{
+    const int yr = __shfl_up_sync(0xffffffffu, r, o), yl = __shfl_up_sync(0xffffffffu, l, o);
+    if (lane >= o) sd_fracmax(r, l, yr, yl);
+}
+
+__global__ void __launch_bounds__(128) k_sdust_dense(const DenseParams P)
+{
+    const uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_dense = *P.n_dense;
+    const int T = P.T, W = P.W;
+    const uint32_t le = (2u << lane) - 1u;            // ages 0..lane of a block
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(P.task_counter, 1u);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= n_dense) break;
+        const uint32_t it = P.it_list[w];
+        const uint32_t rec = P.it_rec[it];
+        const int len = (int)P.rec_len[rec], c0 = (int)P.it_c0[it], c1 = (int)P.it_c1[it];
+        const bool quiet = (P.it_flags[it] & SD_ITEM_QUIET) != 0;
+        int p0 = quiet ? c0 - (W + 2) : c0 - 2 * W - (W + 2);
+        if (p0 < 0 || (!quiet && c0 - 2 * W <= 0)) p0 = 0;
+        const uint8_t *seq = P.seq + P.rec_off[rec];
+        sd_sink sink;
+        sd_sink_init(sink, P.slots + (size_t)it * P.cap, P.cap);
+
+        int x0 = 0xFF, x1 = 0xFF, R0 = 0, R1 = 0;    // per lane: ages lane and 32 + lane
+        uint32_t s0 = 0, s1 = 0;
+        int wn = 0, L = 0, rw = 0;
+        unsigned t = 0;
+        const int stop = c1 < len ? c1 : len;
+        for (int ib = p0; ib < stop; ib += 32) {
+            const int mine = ib + lane < stop ? sd_nt4(__ldg(seq + ib + lane)) : 0;
+            const int n_here = min(32, stop - ib);
+            for (int q = 0; q < n_here; ++q) {
+                const int i = ib + q;
+                if (i == c0) sink.on = 1;
+                t = (t << 2 | (unsigned)__shfl_sync(FULL, mine, q)) & 63u;
+                const int l = i - p0 + 1;
+                if (l < 3) continue;
+                const int start = p0 + (l - W > 0 ? l - W : 0);
+                if (wn >= W - 2) {                    // the oldest element leaves; its interval, if any, is saved
+                    const int o = wn - 1;
+                    const uint32_t so = __shfl_sync(FULL, o < 32 ? s0 : s1, o & 31);
+                    const int xo = __shfl_sync(FULL, o < 32 ? x0 : x1, o & 31);
+                    if (so & SD_SLOT_VALID) sd_sink_put(sink, start - 1, start - 1 + sd_slot_flen(so));
+                    rw -= __popc(__ballot_sync(FULL, x0 == xo)) + __popc(__ballot_sync(FULL, x1 == xo)) - 1;
+                    if (lane == (o & 31)) { if (o < 32) { x0 = 0xFF; s0 = 0; } else { x1 = 0xFF; s1 = 0; } }
+                    --wn;
+                }
+                if (L > wn) L = wn;
+                // every element is one step older
+                {
+                    const int cx = __shfl_sync(FULL, x0, 31), cR = __shfl_sync(FULL, R0, 31);
+                    const uint32_t cs = __shfl_sync(FULL, s0, 31);
+                    x1 = __shfl_up_sync(FULL, x1, 1); R1 = __shfl_up_sync(FULL, R1, 1); s1 = __shfl_up_sync(FULL, s1, 1);
+                    x0 = __shfl_up_sync(FULL, x0, 1); R0 = __shfl_up_sync(FULL, R0, 1); s0 = __shfl_up_sync(FULL, s0, 1);
+                    if (lane == 0) { x1 = cx; R1 = cR; s1 = cs; x0 = 0xFF; }
+                }
+                const uint32_t m0 = __ballot_sync(FULL, x0 == (int)t), m1 = __ballot_sync(FULL, x1 == (int)t);
+                const int c0t = __popc(m0), cnt = c0t + __popc(m1);
+                R0 += __popc(m0 & le);
+                R1 += c0t + __popc(m1 & le);
+                if (lane == 0) { x0 = (int)t; R0 = 0; s0 = 0; }
+                rw += cnt;
+                ++wn;
+                ++L;
+                if (cnt >= 4) {
+                    const int d4 = c0t >= 4 ? (int)__fns(m0, 0, 4) : 32 + (int)__fns(m1, 0, 4 - c0t);
+                    if (d4 < L) L = d4;
+                }
+                if (rw * 10 > L * T && L < wn && !(quiet && i < c0)) {
+                    // find_perfect in age order: exclusive running maximum of (slot, candidate) ratios over younger ages
+                    const int j0 = lane, j1 = 32 + lane;
+                    const bool v0 = (s0 & SD_SLOT_VALID) != 0, v1 = (s1 & SD_SLOT_VALID) != 0;
+                    const int pr0 = v0 ? sd_slot_r(s0) : 0, pl0 = v0 ? sd_slot_l(s0) : 1;
+                    const int pr1 = v1 ? sd_slot_r(s1) : 0, pl1 = v1 ? sd_slot_l(s1) : 1;
+                    const bool cand0 = j0 < wn && j0 >= L && R0 * 10 > T * j0;
+                    const bool cand1 = j1 < wn && j1 >= L && R1 * 10 > T * j1;
+                    int er0 = pr0, el0 = pl0, er1 = pr1, el1 = pl1;
+                    if (cand0) sd_fracmax(er0, el0, R0, j0);
+                    if (cand1) sd_fracmax(er1, el1, R1, j1);
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { frac_scan_step(er0, el0, o, lane); frac_scan_step(er1, el1, o, lane); }
+                    const int t0r = __shfl_sync(FULL, er0, 31), t0l = __shfl_sync(FULL, el0, 31);     // all of block 0
+                    int xr0 = __shfl_up_sync(FULL, er0, 1), xl0 = __shfl_up_sync(FULL, el0, 1);
+                    int xr1 = __shfl_up_sync(FULL, er1, 1), xl1 = __shfl_up_sync(FULL, el1, 1);
+                    if (lane == 0) { xr0 = 0; xl0 = 1; xr1 = 0; xl1 = 1; }
+                    sd_fracmax(xr1, xl1, t0r, t0l);
+                    if (cand0) { sd_fracmax(xr0, xl0, pr0, pl0); if (R0 * xl0 >= xr0 * j0) s0 = sd_slot_pack(R0, j0, j0 + 3); }
+                    if (cand1) { sd_fracmax(xr1, xl1, pr1, pl1); if (R1 * xl1 >= xr1 * j1) s1 = sd_slot_pack(R1, j1, j1 + 3); }
+                }
+            }
+        }
+        if (c1 >= len) {                              // the record ends here: flush (:152-154)
+            sink.on = 1;
+            const int l = len - p0;
+            if (l >= 3) {
+                int start = (l - W + 1 > 0 ? l - W + 1 : 0) + (len + 1 - l);
+                const int a0 = len - 3;
+                for (;;) {
+                    const uint32_t vm0 = __ballot_sync(FULL, (s0 & SD_SLOT_VALID) != 0), vm1 = __ballot_sync(FULL, (s1 & SD_SLOT_VALID) != 0);
+                    if (!(vm0 | vm1)) break;
+                    const int oldest = vm1 ? 63 - __clz(vm1) : 31 - __clz(vm0);
+                    const int a = a0 - oldest;
+                    if (a >= start) start = a + 1;    // (the rounds in between find nothing below their start)
+                    const uint32_t so = __shfl_sync(FULL, oldest < 32 ? s0 : s1, oldest & 31);
+                    sd_sink_put(sink, a, a + sd_slot_flen(so));
+                    if (a0 - lane < start) s0 = 0;
+                    if (a0 - 32 - lane < start) s1 = 0;
+                    ++start;
+                }
+            }
+        }
+        sd_sink_close(sink);
+        if (lane == 0) {
+            P.cnt[it] = sink.n;
+            if (sink.overflow) atomicAdd(P.err, 1u);
+        }
+        __syncwarp();
+    }
 }
 
 struct GatherParams {
@@ -738,13 +897,13 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 64, st));
 
     // tables: nch | chunk_base | nblk | blk_base (n_rec + 1 each), then start / item_no [n_blk + 1], then active bytes
-    const size_t tab_words = 4 * ((size_t)n_rec + 1) + ((size_t)n_blk + 2) + 2 * (((size_t)n_blk + 8) / 4 + 2) + 64;
+    const size_t tab_words = 4 * ((size_t)n_rec + 1) + ((size_t)n_blk + 2) + 3 * (((size_t)n_blk + 8) / 4 + 2) + 64;
     CORN_TRY(corn_dbuf_reserve(ctx, &ctx->sd_tab, tab_words * sizeof(uint32_t)));
     uint32_t *nch = (uint32_t *)ctx->sd_tab.p, *chunk_base = nch + n_rec + 1, *nblk = chunk_base + n_rec + 1, *blk_base = nblk + n_rec + 1;
     uint32_t *item_no = blk_base + n_rec + 1;
     uint8_t *active = (uint8_t *)(item_no + n_blk + 2);
     const size_t act_bytes = (((size_t)n_blk + 8) / 4 + 2) * 4;
-    uint8_t *tcnt = active + act_bytes;
+    uint8_t *tcnt = active + act_bytes, *nflag = tcnt + act_bytes;
 
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     k_sdust_nchunks<<<(n_rec + 255) / 256, 256, 0, st>>>(db->d_rec_len, nch, n_rec, (uint32_t)C);
@@ -752,13 +911,13 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     corn_count_launch(ctx, 2);
     CORN_TRY(corn_scan_u32(ctx, nch, chunk_base, n_rec, chunk_base + n_rec));
     CORN_TRY(corn_scan_u32(ctx, nblk, blk_base, n_rec, blk_base + n_rec));
-    CORN_CUDA(ctx, cudaMemsetAsync(active, 0, 2 * act_bytes, st));
+    CORN_CUDA(ctx, cudaMemsetAsync(active, 0, 3 * act_bytes, st));
 
     // ---- phase 1: scout ----
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     ScoutParams sc;
     sc.seq = db->d_seq; sc.rec_off = db->d_rec_off; sc.rec_len = db->d_rec_len; sc.chunk_base = chunk_base; sc.blk_base = blk_base;
-    sc.n_rec = n_rec; sc.n_chunks = n_chunks; sc.T = T; sc.W = W; sc.C = C; sc.active = active; sc.tcnt = tcnt;
+    sc.n_rec = n_rec; sc.n_chunks = n_chunks; sc.T = T; sc.W = W; sc.C = C; sc.active = active; sc.tcnt = tcnt; sc.nflag = nflag;
     k_sdust_scout<<<(n_chunks + SC_BLOCK - 1) / SC_BLOCK, SC_BLOCK, 0, st>>>(sc);
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
@@ -767,7 +926,7 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     // ---- items ----
     ItemParams ip;
     memset(&ip, 0, sizeof ip);
-    ip.active = active; ip.tcnt = tcnt; ip.blk_base = blk_base; ip.rec_len = db->d_rec_len; ip.n_rec = n_rec; ip.n_blk = n_blk;
+    ip.active = active; ip.tcnt = tcnt; ip.nflag = nflag; ip.blk_base = blk_base; ip.rec_len = db->d_rec_len; ip.n_rec = n_rec; ip.n_blk = n_blk;
     ip.start = item_no; ip.total = d_tot + 1;
     k_sdust_item_starts<<<(n_blk + 255) / 256, 256, 0, st>>>(ip);
     corn_count_launch(ctx);
@@ -819,21 +978,29 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     sp.n_rec = n_rec; sp.n_chunks = n_items; sp.T = T; sp.W = W; sp.C = SD_ITEM_MAX; sp.cap = cap;
     sp.slots = slots; sp.gslots = gslots; sp.cnt = cnt; sp.err = d_err; sp.task_list = NULL;
     sp.it_list = it_list; sp.it_rec = it_rec; sp.it_c0 = it_c0; sp.it_c1 = it_c1; sp.it_flags = it_flags;
-    // d_tot: [1] items, [11] dense items (they fill it_list from the front), [13] = 0
-    for (int dense = 1; dense >= 0; --dense) {            // the dense items first: fewer, longer tasks
-        const sd_kernel_t kern = dense ? k_sdust_scan<2, false, true> : k_sdust_scan<2, true, false>;
-        const size_t smem_k = smem + (dense ? (size_t)SD_BLOCK * lay.slot_words * sizeof(uint32_t) : 0);
-        CORN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
-        int blocks_per_sm = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SD_BLOCK, smem_k) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
-        sp.list_lo = dense ? d_tot + 13 : d_tot + 11;
-        sp.list_hi = dense ? d_tot + 11 : d_tot + 1;
-        sp.task_counter = dense ? d_tot + 12 : d_tot + 8;
-        const unsigned want = (n_items + SD_BLOCK - 1) / SD_BLOCK, resident = (unsigned)(ctx->sm_count * blocks_per_sm);
-        kern<<<want < resident ? want : resident, SD_BLOCK, smem_k, st>>>(sp);
+    // d_tot: [1] items, [11] dense items (they fill it_list from the front)
+    {
+        DenseParams dp;
+        dp.seq = db->d_seq; dp.rec_off = db->d_rec_off; dp.rec_len = db->d_rec_len;
+        dp.it_list = it_list; dp.it_rec = it_rec; dp.it_c0 = it_c0; dp.it_c1 = it_c1; dp.it_flags = it_flags;
+        dp.n_dense = d_tot + 11; dp.T = T; dp.W = W; dp.cap = cap; dp.slots = slots; dp.cnt = cnt; dp.err = d_err; dp.task_counter = d_tot + 12;
+        k_sdust_dense<<<ctx->sm_count * 8, 128, 0, st>>>(dp);
         corn_count_launch(ctx);
         CORN_LAUNCH_CHECK(ctx);
-        if (dense) CORN_CUDA(ctx, cudaEventRecord(ctx->ev[14], st));
+        CORN_CUDA(ctx, cudaEventRecord(ctx->ev[14], st));
+    }
+    {
+        const sd_kernel_t kern = k_sdust_scan<2, true, false>;
+        CORN_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int blocks_per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SD_BLOCK, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = 1; }
+        sp.list_lo = d_tot + 11;
+        sp.list_hi = d_tot + 1;
+        sp.task_counter = d_tot + 8;
+        const unsigned want = (n_items + SD_BLOCK - 1) / SD_BLOCK, resident = (unsigned)(ctx->sm_count * blocks_per_sm);
+        kern<<<want < resident ? want : resident, SD_BLOCK, smem, st>>>(sp);
+        corn_count_launch(ctx);
+        CORN_LAUNCH_CHECK(ctx);
     }
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
 

@@ -505,6 +505,114 @@ SD_HD void sd_run_item(Fetch &fetch, int l_seq, int c0, int c1, uint32_t flags, 
     sd_sink_close(k);
 }
 
+// ---- the machine in AGE ORDER, for items without a non-ACGT byte ------------------------------------------
+// Inside low-complexity sequence find_perfect runs at every step and costs O(W) dependent iterations: served per lane
+// it is latency bound, served cooperatively it occupies a whole warp for one lane.  For such DENSE items one warp
+// runs ONE item, with the window spread over its lanes.  This is the plain-array statement of what that kernel
+// (csrc/sdust.cu: sdust_dense_item) computes with shuffles; tests/sim runs it against the oracle.
+//
+// On a stretch [p0, c1) without non-ACGT bytes the fresh run is regular: every position from p0 + 2 on emits a triplet,
+// the element pushed at position i has the interval start i - 2 for as long as it is in the window, and the window
+// start advances by exactly one per step once it is full.  So the perfect-interval slot of a start position can live
+// WITH the window element of that start, and everything is indexed by AGE j (0 = newest element):
+//   x[j]     triplet;   slot[j]  the perfect interval that starts at this element (sd_slot_pack, 0 = none);
+//   R[j]     score of the suffix that starts at this element = pairs of equal triplets among ages j..0.  Pushing t
+//            adds to R[j] the number of t among ages j..1 -- so the scores find_perfect recomputes with its c[t]++ loop
+//            (:108-112) are simply there, and the suffix counts cv[] / rv are never needed;
+//   L        as in the scout: min(L + 1, wn, age of the 4th previous occurrence of t when t is then >= 5 times in the window).
+// find_perfect in age order (cf. sd_find_perfect_vec): candidate ages j >= L with R[j]*10 > T*j; with
+//   X[j] = best ratio among {slots and candidates of ages < j}  and  M[j] = max(X[j], slot[j]),
+// age j is (re)inserted iff it is a candidate and R[j] / j >= M[j]; the interval is (r = R[j], l = j, flen = j + 3).
+// save_masked_regions(): the only slot that can fall left of the window start is the one of the element that leaves.
+struct sd_dense {
+    int wn, L, rw;
+    uint8_t  x[64];
+    uint16_t R[64];
+    uint32_t slot[64];
+};
+
+SD_HD void sd_dense_find_perfect(sd_dense &d, int T)
+{
+    int xr = 0, xl = 1;                               // X[j]: running maximum over ages < j
+    for (int j = 0; j < d.wn; ++j) {
+        const uint32_t v = d.slot[j];
+        const bool sv = (v & SD_SLOT_VALID) != 0;
+        const int pr = sv ? sd_slot_r(v) : 0, pl = sv ? sd_slot_l(v) : 1;
+        const bool cand = j >= d.L && (int)d.R[j] * 10 > T * j;
+        int er = pr, el = pl;                         // this age's contribution to the running maximum
+        if (cand) {
+            int mr = xr, ml = xl;
+            sd_fracmax(mr, ml, pr, pl);               // M[j]
+            if ((int)d.R[j] * ml >= mr * j) d.slot[j] = sd_slot_pack(d.R[j], j, j + 3);
+            sd_fracmax(er, el, d.R[j], j);
+        }
+        sd_fracmax(xr, xl, er, el);
+    }
+}
+
+// one emitting step: `start` = window start of this step, t = the new triplet
+SD_HD void sd_dense_step(sd_dense &d, sd_sink &k, int start, int t, int T, int W, bool fp_enabled)
+{
+    if (d.wn >= W - 2) {                              // the oldest element leaves; its interval, if any, is saved (:88-102)
+        const int o = d.wn - 1;
+        if (d.slot[o] & SD_SLOT_VALID) sd_sink_put(k, start - 1, start - 1 + sd_slot_flen(d.slot[o]));
+        int c = 0;
+        for (int j = 0; j < o; ++j) c += d.x[j] == d.x[o];
+        d.rw -= c;
+        --d.wn;
+    }
+    if (d.L > d.wn) d.L = d.wn;
+    for (int j = d.wn; j > 0; --j) { d.x[j] = d.x[j - 1]; d.R[j] = d.R[j - 1]; d.slot[j] = d.slot[j - 1]; }
+    int cnt = 0, d4 = 64;
+    for (int j = 1; j <= d.wn; ++j)
+        if (d.x[j] == t) { ++cnt; if (cnt == 4) d4 = j; d.R[j] = (uint16_t)(d.R[j] + cnt); }
+        else d.R[j] = (uint16_t)(d.R[j] + cnt);
+    d.x[0] = (uint8_t)t; d.R[0] = 0; d.slot[0] = 0;
+    d.rw += cnt;
+    ++d.wn;
+    ++d.L;
+    if (cnt >= 4 && d4 < d.L) d.L = d4;
+    if (fp_enabled && d.rw * 10 > d.L * T && d.L < d.wn) sd_dense_find_perfect(d, T);
+}
+
+// flush at the end of the record (:152-154): start counts up from start0; every round saves the valid slot with the
+// smallest start if that is below `start`, and drops every slot below `start`.  a0 = interval start of the newest element.
+SD_HD void sd_dense_flush(sd_dense &d, sd_sink &k, int start0, int a0)
+{
+    for (int start = start0;; ++start) {
+        int oldest = -1;
+        for (int j = d.wn - 1; j >= 0; --j) if (d.slot[j] & SD_SLOT_VALID) { oldest = j; break; }
+        if (oldest < 0) break;
+        if (a0 - oldest >= start) continue;
+        sd_sink_put(k, a0 - oldest, a0 - oldest + sd_slot_flen(d.slot[oldest]));
+        for (int j = 0; j < d.wn; ++j) if (a0 - j < start) d.slot[j] = 0;
+    }
+}
+
+// an item whose bytes [p0, c1) are all A/C/G/T (the caller checks): same events as sd_run_item
+template <class Fetch>
+SD_HD void sd_run_item_dense(Fetch &fetch, int l_seq, int c0, int c1, uint32_t flags, int T, int W, sd_dense &d, sd_sink &k)
+{
+    const bool quiet = (flags & SD_ITEM_QUIET) != 0;
+    int p0 = quiet ? c0 - (W + 2) : c0 - 2 * W - (W + 2);       // = sd_warm_quiet / sd_warm_start on ACGT-only sequence
+    if (p0 < 0 || (!quiet && c0 - 2 * W <= 0)) p0 = 0;
+    d.wn = d.L = d.rw = 0;
+    unsigned t = 0;
+    const int stop = c1 < l_seq ? c1 : l_seq;
+    for (int i = p0; i < stop; ++i) {
+        if (i == c0) k.on = 1;
+        t = (t << 2 | (unsigned)sd_nt4(fetch(i))) & 63u;
+        const int l = i - p0 + 1;
+        if (l >= 3) sd_dense_step(d, k, p0 + (l - W > 0 ? l - W : 0), (int)t, T, W, !(quiet && i < c0));
+    }
+    if (c1 >= l_seq) {
+        k.on = 1;
+        const int l = l_seq - p0;
+        if (l >= 3) sd_dense_flush(d, k, (l - W + 1 > 0 ? l - W + 1 : 0) + (l_seq + 1 - l), l_seq - 3);
+    }
+    sd_sink_close(k);
+}
+
 // --------------------------------------------------------------------------------------------
 // Two-phase execution (W <= 64, floor(2T/10) == 4: the defaults).
 //

@@ -243,7 +243,19 @@ static int sim_sdust2(const char *path, int T, int W, int C)
             sd_sink sink;
             sd_sink_init(sink, slots.data() + off[j], off[j + 1] - off[j]);
             // an item that reaches the last block of the record also owns the final flush (c1 >= len)
-            sd_run_item(fetch, len, (int)ic0[j], (int)ic1[j] >= len ? len : (int)ic1[j], iflags[j], T, W, m, sink);
+            // items without a non-ACGT byte in [p0, c1) may take the age-ordered machine (what the dense kernel runs);
+            // SIM_DENSE=1 sends every such item there, so that the whole corpus checks it
+            const int ic1j = (int)ic1[j] >= len ? len : (int)ic1[j];
+            int lo = (iflags[j] & SD_ITEM_QUIET) ? (int)ic0[j] - (W + 2) : (int)ic0[j] - 2 * W - (W + 2);
+            if (lo < 0) lo = 0;
+            bool acgt = getenv("SIM_DENSE") != NULL;
+            for (int q = lo; acgt && q < std::min(ic1j, len); ++q) acgt = sd_nt4(seq[q]) < 4;
+            if (acgt) {
+                sd_dense dm;
+                sd_run_item_dense(fetch, len, (int)ic0[j], ic1j, iflags[j], T, W, dm, sink);
+                ++st_dense_items;
+            } else
+            sd_run_item(fetch, len, (int)ic0[j], ic1j, iflags[j], T, W, m, sink);
             if (sink.overflow) { fprintf(stderr, "slot overflow\n"); return 1; }
             cnt[j] = sink.n;
             st_item_pos += ic1[j] - ic0[j];
@@ -259,6 +271,7 @@ static int sim_sdust2(const char *path, int T, int W, int C)
     fprintf(stderr, "positions %llu triggers %llu (%.3f%%) active blocks %llu of %llu (%.1f%%) items %llu item positions %llu (%.1f%%)\n",
             st_pos, st_trig, 100.0 * st_trig / (st_pos ? st_pos : 1), st_active_blk, st_blk, 100.0 * st_active_blk / (st_blk ? st_blk : 1),
             st_items, st_item_pos, 100.0 * st_item_pos / (st_pos ? st_pos : 1));
+    if (st_dense_items) fprintf(stderr, "items run by the age-ordered machine: %llu\n", st_dense_items);
     return 0;
 }
 #endif
