@@ -102,6 +102,7 @@ extern "C" void corn_gpu_destroy(corn_ctx_t *ctx)
                           &ctx->ing_text, &ctx->ing_tab, &ctx->ing_lines, &ctx->ing_rec, &ctx->ranks, &ctx->hot };
     for (size_t i = 0; i < sizeof bufs / sizeof bufs[0]; ++i) dbuf_free(bufs[i]);
     for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->aux_ev[0]); cudaEventDestroy(ctx->aux_ev[1]); }
     cudaStreamDestroy(ctx->own_stream);
     cudaFreeHost(ctx->h_pinned_small);
     if (ctx->stage) {

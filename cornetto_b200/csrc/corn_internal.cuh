@@ -71,6 +71,8 @@ struct corn_ctx {
     int          device;
     int          sm_count;
     cudaStream_t own_stream, stream;
+    cudaStream_t aux_stream;   // second stream for kernels that may share the GPU with the main one (sdust: dense and sparse items), created on first use
+    cudaEvent_t  aux_ev[2];
     cudaEvent_t  ev[16];  // 0-1 upload, 2-5 telofind, 8-11 telowin, 2-6 sdust
     char         err[512];
     corn_timing_t timing;

@@ -367,6 +367,40 @@ def test_sim_sdust_vector_form_and_slack_skip(sim_vec_bin, oracle_bin, tmp_path)
     assert skipped > 1000
 
 
+def test_sim_sdust_two_phase(sim_vec_bin, sim_bin, oracle_bin, tmp_path):
+    """The two-phase execution of csrc/sdust.cu's default path, step by step on the CPU: scout (window half without
+    loops) -> active 64-base blocks -> items -> full machine per item -> item seam fold; once with every item on the
+    lane-per-item machine and once with every N-free item on the age-ordered machine the dense kernel runs (SIM_DENSE)."""
+    files = {}
+    for seed in range(3):
+        rng = np.random.default_rng(7100 + seed)
+        recs = []
+        for k in range(5):
+            L = int(rng.integers(100, 20000))
+            recs.append((f"v{k}", synth.make_contig(rng, L, telo=None if k % 2 else (20, 200), n_its=1, microsat_per_mb=float(rng.choice([50, 3000, 20000])),
+                                                     n_gaps=int(rng.integers(0, 25)), gap_len=(1, int(rng.choice([3, 60, 400]))),
+                                                     p_lower=0.1, iupac_per_mb=float(rng.choice([0, 2000])))))
+        files[f"tp{seed}.fa"] = synth.fasta_bytes(recs)
+    ends = [("e1", np.frombuffer(b"ACGTTGCA" * 40 + b"A" * 300, dtype=np.uint8)), ("e2", np.frombuffer(b"AC" * 500, dtype=np.uint8)),
+            ("e3", np.frombuffer(b"A" * 70, dtype=np.uint8)), ("e4", np.frombuffer(b"TTAGGG" * 1500, dtype=np.uint8)),
+            ("e5", np.frombuffer(b"A" * 7, dtype=np.uint8)), ("e6", np.frombuffer(b"AAAAAAAC" * 100, dtype=np.uint8))]
+    files["ends.fa"] = synth.fasta_bytes(ends)
+    n = 0
+    for name, data in files.items():
+        p = write(str(tmp_path / name), data)
+        for opts in ([], ["-w", "32", "-t", "20"], ["-t", "24"], ["-w", "7"]):
+            b, _, _ = run([oracle_bin, "sdust"] + opts + [p])
+            for chunk in ("64", "193", "2048"):
+                for env in (None, dict(os.environ, SIM_DENSE="1")):
+                    a, _, _ = run([sim_bin, "sdust2"] + opts + ["-c", chunk, p], env=env)
+                    assert a == b, (name, opts, chunk, env is not None)
+                    n += 1
+    assert n >= 90
+    # outside W <= 64, floor(2T/10) == 4 the scout's four-occurrence history does not apply: the simulator says so
+    _, _, rc = run([sim_bin, "sdust2", "-t", "15", str(tmp_path / "ends.fa")], check=False)
+    assert rc == 2
+
+
 @pytest.fixture(scope="module")
 def sim_wide_bin(tmp_path_factory, oracle_bin):
     """The simulator built on the WIDE instance of sdust_core.cuh (16-bit counters, 64-bit slots: what csrc/sdust_wide.cu runs)."""
