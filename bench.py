@@ -312,6 +312,63 @@ def bind_to_gpu_numa_node(torch, local):
         return None
 
 
+# ------------------------------------------------------------------------------------------------
+# the GPU generator (csrc/synth.cu), restated in numpy: the reference arm scans the SAME bytes
+# ------------------------------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return x ^ (x >> np.uint64(31))
+
+
+def host_contig(length, rec_id, seed, feats):
+    """Bytes of global record `rec_id` exactly as corn_bench_fill_random_rec + corn_bench_apply_features leave them
+    (k_fill_random / k_apply_features): counter-based A/C/G/T keyed by (seed, record, 16-byte block), then the tandem,
+    lower-case and N features of that record."""
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    out = np.empty(length, dtype=np.uint8)
+    with np.errstate(over="ignore"):
+        key = _mix64(np.uint64(seed) ^ (np.uint64(rec_id) << np.uint64(40)))
+        shifts = (np.arange(16, dtype=np.uint64) * np.uint64(2))[None, :]
+        step = 1 << 20                                           # blocks per slice (16 MB of bases)
+        n_blk = (length + 15) // 16
+        for b0 in range(0, n_blk, step):
+            blk = np.arange(b0, min(n_blk, b0 + step), dtype=np.uint64)
+            h = _mix64(key ^ (blk * np.uint64(0xD1342543DE82EF95)))
+            codes = ((h[:, None] >> shifts) & np.uint64(3)).astype(np.uint8).reshape(-1)
+            lo = b0 * 16
+            hi = min(length, lo + len(codes))
+            out[lo:hi] = acgt[codes[:hi - lo]]
+        for f in feats:                                          # tandem, then lower case, then N gaps
+            for row in f[f["rec"] == rec_id]:
+                st, n = int(row["start"]), int(row["len"])
+                if st >= length:
+                    continue
+                n = min(n, length - st)
+                kind = int(row["kind"])
+                if kind == 1:
+                    out[st:st + n] = ord("N")
+                elif kind == 2:
+                    seg = out[st:st + n]
+                    up = (seg >= ord("A")) & (seg <= ord("Z"))
+                    seg[up] += 32
+                else:
+                    period = int(row["period"])
+                    i = np.arange(n, dtype=np.uint64)
+                    copy, k = i // np.uint64(period), (i % np.uint64(period)).astype(np.int64)
+                    b = row["unit"][k].copy()
+                    h = _mix64((np.uint64(int(row["seed"])) << np.uint64(32)) ^ copy)
+                    frac = (h & np.uint64(0xFFFFFF)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+                    var = (frac < np.float32(row["p_variant"])) & (((h >> np.uint64(24)) % np.uint64(period)).astype(np.int64) == k)
+                    b[var] = acgt[((h[var] >> np.uint64(40)) & np.uint64(3)).astype(np.int64)]
+                    out[st:st + n] = b
+    return out
+
+
 def host_random_contig(rng, L):
     """numpy stand-in of the GPU generator for the reference arm (same composition, other bytes)."""
     s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=L, dtype=np.uint8)]
@@ -322,31 +379,57 @@ def host_random_contig(rng, L):
     return s
 
 
+def workload_text(wl, world):
+    return {"c2": "c2: telofind(TTAGGG)+telowin(0.4, 99.9) on a synthetic 3.12 Gb T2T-like haploid assembly (24 contigs)",
+            "c3": "c3: telofind(TTAGGG)+telowin(0.4, 99.9) on ONE synthetic 6.2 Gb diploid assembly (48 contigs, N gaps)"}.get(wl, wl)
+
+
+def _write_part(job):
+    """worker of the reference arm: one contig-split FASTA with the same bytes the GPU arm generates in HBM"""
+    path, idxs, lengths, names, seed_bytes, feats = job
+    write_fasta(path, [(names[j], host_contig(lengths[j], j, seed_bytes, feats)) for j in idxs])
+    return path
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from cornetto_b200 import capi          # (dtype of the feature table only: the CUDA library is not loaded on this arm)
     binary, kind = ref_binary()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    scale = 4                                    # bounded sample: the c2 contig set at 1/4 length (779 Mb), ~0.4 s per step
-    est = 0.4 * (args.steps + args.warmup)       # keep the whole run within a few minutes whatever K and W are
-    if est > 150:
-        scale = int(min(64, -(-4 * est // 150)))
-    lengths = [L // scale for L in workload_lengths("c2")]
-    P = max(1, min(cores, len(lengths)))
-    rng = np.random.default_rng(1234)
+    wl = args.workload or ("c2" if args.gpus == 1 else "c3")
+    lengths_all = workload_lengths(wl)
+    names = workload_names(wl)
+    feats = make_features(capi, lengths_all, 7, n_gaps=3 if wl in ("c3", "small3") else 0)
+    # Same bytes as the GPU arm (host_contig restates its generator).  The whole assembly per step when the run stays
+    # within a few minutes (~0.55 s per Gb on 16+ cores), else the longest contigs up to a budget -- a bounded sample.
+    per_gb = 0.6
+    budget_s = 150.0
+    n_steps = args.steps + args.warmup
+    total_all = float(sum(lengths_all))
+    keep = list(range(len(lengths_all)))
+    if total_all / 1e9 * per_gb * n_steps > budget_s:
+        want = budget_s / n_steps / per_gb * 1e9
+        order = sorted(keep, key=lambda j: -lengths_all[j])
+        keep, acc = [], 0.0
+        for j in order:
+            if acc + lengths_all[j] <= want or not keep:
+                keep.append(j); acc += lengths_all[j]
+        keep.sort()
+    lengths = {j: lengths_all[j] for j in keep}
+    P = max(1, min(cores, len(keep)))
     with tempfile.TemporaryDirectory(prefix="corn_ref_") as td:
         # contig-split FASTAs, longest-first round robin over P processes
-        order = np.argsort(lengths)[::-1]
+        order = sorted(keep, key=lambda j: -lengths_all[j])
         groups = [[] for _ in range(P)]
         for i, idx in enumerate(order):
             groups[i % P].append(int(idx))
-        files = []
-        for g, idxs in enumerate(groups):
-            path = os.path.join(td, f"part{g}.fa")
-            write_fasta(path, [(f"chr{j + 1}", host_random_contig(rng, lengths[j])) for j in idxs])
-            files.append(path)
-        total = float(sum(lengths))
+        jobs = [(os.path.join(td, f"part{g}.fa"), idxs, lengths_all, names, 42, feats) for g, idxs in enumerate(groups)]
+        import multiprocessing as mp
+        with mp.Pool(P) as pool:
+            files = pool.map(_write_part, jobs)
+        total = float(sum(lengths.values()))
 
         def one_step():
             t0 = time.perf_counter()
@@ -364,13 +447,14 @@ def run_reference_arm(args):
         times = [one_step() for _ in range(args.steps)]
     t = sum(times)
     value = total * args.steps / t / 1e9
+    sample = ("the whole assembly" if len(keep) == len(lengths_all) else f"its {len(keep)} longest contigs ({total / 1e6:.0f} Mb)") + \
+             f", same bytes as the GPU arm, {P} processes over contig-split FASTAs (files in, text out)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "c2_t2t_haploid_3.1Gb telofind+telowin(0.4, 99.9)", "sample": f"24 contigs at 1/{scale} length ({total / 1e6:.0f} Mb) per step",
-                       "processes": P},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": kind,
-                             "sample": f"c2 contig set at 1/{scale} length, {P} processes over contig-split FASTAs"},
+            "config": {"workload": workload_text(wl, args.gpus), "contigs": len(lengths_all), "bases": int(total_all)},
+            "sample": sample, "processes": P,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -649,12 +733,10 @@ def main():
         roofline["kernel_ms_max_over_ranks"] = allmax(scan_avg_ms)
         roofline["post_kernels_ms_max_over_ranks"] = allmax(solo["post_ms"])
 
-    what = {"c2": "telofind(TTAGGG)+telowin(0.4, 99.9) on a synthetic 3.12 Gb T2T-like haploid assembly, 1 GPU",
-            "c3": f"telofind(TTAGGG)+telowin(0.4, 99.9) on ONE synthetic 6.2 Gb diploid assembly (48 contigs, N gaps) sharded over {world} GPU(s) by corn_shard_plan"}.get(wl, wl)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{wl}: {what}", "contigs": len(lengths), "bases": n_bases_total,
+            "config": {"workload": workload_text(wl, world), "contigs": len(lengths), "bases": n_bases_total,
                        "bases_this_rank": my_bases, "hbm_bytes_this_rank": total_bytes, "resident_batches_this_rank": len(dbs),
                        "l2_policy": "every shard (>= 0.78 GB) is far larger than the 126 MB L2: every step streams it from HBM",
                        "windows_found_this_rank": res["n_win"],
@@ -767,14 +849,19 @@ def main():
 
     # ---- e2e: FASTA text in page-locked host memory through the public C ABI: ingest (H2D + device parse) +
     #      telofind + telowin, results copied back.  Every rank does its own shard. ----
-    seqs = []
+    seqs, seq_ids = [], []
     for db, recs in zip(dbs, my_batches):
         flat = ctx.download_all(db)
         off = 0
         for r in recs:
             Lr = int(lengths[int(r)])
             seqs.append((names[int(r)], flat[off:off + Lr]))
+            seq_ids.append(int(r))
             off += (Lr + 1 + 31) // 32 * 32
+    # the reference arm (bench.py --impl reference) builds its FASTA files with host_contig(): same bytes?  (shortest contig of this rank)
+    j = int(np.argmin([len(a) for _, a in seqs]))
+    same_bytes = bool(np.array_equal(seqs[j][1], host_contig(len(seqs[j][1]), seq_ids[j], seed_bytes, feats)))
+    line["config"]["same_bytes_as_reference_arm"] = {"contig": seqs[j][0], "identical": same_bytes}
     for db in dbs:
         ctx.free(db)                              # make room: the e2e path builds its own resident copy
     # text blocks of at most ~3.7 GB (what one corn_gpu_ingest call takes), cut at record boundaries
@@ -850,12 +937,25 @@ def main():
             ff, fw = min(r[0] for r in runs2), min(r[1] for r in runs2)
             cli["full"] = {"bases": int(n_bases_total), "fasta_bytes": os.path.getsize(full), "telofind_s": ff, "telowin_s": fw,
                            "gbases_per_s": n_bases_total / (ff + fw) / 1e9}
-            line["e2e_from_file"] = {"value": n_bases_total / (ff + fw) / 1e9, "unit": UNIT,
-                                     "what": "`cornetto telofind full.fa > x.telomere` + `cornetto telowin x.telomere 99.9 0.4`: FASTA file (page cache) to text, "
-                                             "process and CUDA start-up included; best of 2",
-                                     "telofind_s": ff, "telowin_s": fw,
+            # the same product from ONE process: `cornetto telostats full.fa` (scripts/telostats.sh fused: device parse,
+            # telofind, telowin on the resident runs, merged windows at the contig ends, tally) -- and its files must be
+            # the two commands' files
+            def telostats_once():
+                t0 = time.perf_counter()
+                subprocess.run([ours, "telostats", "full.fa"], cwd=td, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+                return time.perf_counter() - t0
+            ts = min(telostats_once() for _ in range(2))
+            subprocess.run(f"{ours} telowin {td}/full.fa.telomere 99.9 0.4 > {td}/two.windows 2>/dev/null", shell=True, check=True)
+            same = (open(os.path.join(td, "tmp_full_telostats", "full.telomere"), "rb").read() == open(os.path.join(td, "full.fa.telomere"), "rb").read()
+                    and open(os.path.join(td, "tmp_full_telostats", "full.windows.0.4"), "rb").read() == open(os.path.join(td, "two.windows"), "rb").read())
+            line["e2e_from_file"] = {"value": n_bases_total / ts / 1e9, "unit": UNIT,
+                                     "what": "`cornetto telostats full.fa`: FASTA file (page cache) -> .telomere, .lens, .windows.0.4, merged BED, contig-end BED and tally "
+                                             "(everything scripts/telostats.sh leaves behind) from one process, process and CUDA start-up included; best of 2",
+                                     "telostats_s": ts, "files_identical_to_the_two_commands": bool(same),
+                                     "two_commands": {"what": "`cornetto telofind full.fa > x.telomere` + `cornetto telowin x.telomere 99.9 0.4`, best of 2",
+                                                      "telofind_s": ff, "telowin_s": fw, "value": n_bases_total / (ff + fw) / 1e9},
                                      "reference_same_sample_gbases_per_s": got / (tf + tw) / 1e9,
-                                     "bound": "CUDA start-up of two fresh processes, the read(2) of 3.2 GB, the staged H2D copy and text formatting; kernels are <1 % of it"}
+                                     "bound": "CUDA start-up of a fresh process, the read(2) of 3.2 GB, the staged H2D copy and text formatting; kernels are <1 % of it"}
         cli["what"] = ("wall clock of the drop-in `cornetto telofind` + `cornetto telowin` commands on FASTA files (parse included), "
                        "bound by CUDA start-up (0.4-2 s per process on these boxes), the file read and text formatting")
         line["cli"] = cli
