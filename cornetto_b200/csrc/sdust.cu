@@ -568,19 +568,21 @@ __global__ void __launch_bounds__(SC_BLOCK) k_sdust_scout(const ScoutParams P)
         const uint32_t real = rem < 16 ? (1u << rem) - 1u : 0xFFFFu;
         if ((valid & real) != real) nfl[k] = 1;               // a non-ACGT byte in this block (any thread may say so)
         uint32_t ntrig = 0;
+        bool stale = false;                                   // a trigger less than W bases after a non-ACGT byte
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             if (q < rem) {
                 if ((valid >> q) & 1u) {
                     ++sc.l;
                     sc.t = (sc.t << 2 | ((codes >> (2 * q)) & 3u)) & 63u;
-                    if (sc.l >= 3 && sd_scout_push(sc, words, ring, sc.t, T, W)) ++ntrig;
+                    if (sc.l >= 3 && sd_scout_push(sc, words, ring, sc.t, T, W)) { ++ntrig; stale |= sc.l < W; }
                 } else { sc.l = 0; sc.t = 0; }
             }
         }
         if (ntrig && own) {                                   // (a 16-base group lies inside one 64-base block)
             act[k] = 1;
             if (k + 1 < n_blk) act[k + 1] = 1;
+            if (stale && k + 2 < n_blk) act[k + 2] = 1;       // the longer drain of the stale phase (sdust_core.cuh)
             tcn[k] = (uint8_t)(tcn[k] + ntrig);               // (chunks are multiples of 64 bases: block k is this thread's alone)
         }
     }

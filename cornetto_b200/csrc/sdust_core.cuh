@@ -630,8 +630,15 @@ SD_HD void sd_run_item_dense(Fetch &fetch, int l_seq, int c0, int c1, uint32_t f
 // rv and cv[] are not needed for the trigger.  (sd_scout_* below; the test is bit-identical to :149, checked
 // against the full machine in tests/sim.)
 //
+// How long an entry lives: inserted at step j it has a start in [ws(j), ws(j) + W-3] and leaves when the window start
+// passes it.  In the normal phase (run length l >= W) the window start advances with every step: gone by j + W-2.  In the
+// STALE phase -- fewer than W bases after a non-ACGT byte, where ws is still pinned to the first base after it while the
+// (stale) window already holds W-2 triplets (:146) -- the start can lie up to W-3 right of ws and ws only starts moving
+// when l reaches W: gone by j + (W - l) + W-2 < j + 2W.  (This is the quirk that lets intervals cover bases that are not
+// low complexity at all.)  So a trigger at i keeps the blocks of i and i + 64 busy, and of i + 128 too in the stale phase.
+//
 // Phase 2 runs the full machine only over ITEMS: maximal runs of 64-base blocks that hold a trigger position i or lie
-// within its drain (blocks of i and of i + 64), cut every SD_ITEM_MAX bases.  An item whose preceding block is quiet
+// within its drain, cut every SD_ITEM_MAX bases.  An item whose preceding block is quiet
 // starts with P empty for certain, so its warm-up only has to rebuild the window (W-2 emitted triplets, window half
 // only); an item cut out of a longer run uses the general exact start of section 2 above.  Items own their save events
 // by time as before, and since starts and finishes of different runs of blocks are more than a window apart, only

@@ -16,13 +16,15 @@ lengths = [mb * 1_000_000 // 4] * 4
 ctx = capi.Context(0)
 db = ctx.alloc(lengths)
 ctx.fill_random(db, 42)
-mode = sys.argv[3] if len(sys.argv) > 3 else "full"     # full | plain (random only) | notelo (no telomeric ends)
+mode = sys.argv[3] if len(sys.argv) > 3 else "full"     # full | plain (random only) | notelo (no telomeric ends) | gaps (full + N gaps)
 if mode != "plain":
-    tand, lower, _ = bench.make_features(capi, lengths, 7)
+    tand, lower, gaps = bench.make_features(capi, lengths, 7, n_gaps=3 if mode == "gaps" else 0)
     if mode == "notelo":
         tand = tand[tand["len"] < 3000]
     ctx.apply_features(db, tand)
     ctx.apply_features(db, lower)
+    if len(gaps):
+        ctx.apply_features(db, gaps)
 for _ in range(reps):
     iv, first = ctx.sdust_dev(db)
     t = ctx.timing()

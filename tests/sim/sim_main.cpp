@@ -215,6 +215,7 @@ static int sim_sdust2(const char *path, int T, int W, int C)
                         ++st_trig;
                         active[i / SD_BLK] = 1;
                         if (i / SD_BLK + 1 < n_blk) active[i / SD_BLK + 1] = 1;
+                        if (sc.l < W && i / SD_BLK + 2 < n_blk) active[i / SD_BLK + 2] = 1;    // stale phase: longer drain (sdust_core.cuh)
                     }
                 } else { sc.l = 0; sc.t = 0; }
             }

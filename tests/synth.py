@@ -113,6 +113,39 @@ def fastq_bytes(records, width: int = 0) -> bytes:
     return bytes(out)
 
 
+def _low_complexity(rng):
+    kind = rng.integers(0, 3)
+    if kind == 0:
+        return np.full(int(rng.integers(5, 14)), ACGT[rng.integers(0, 4)], dtype=np.uint8)
+    per = int(rng.integers(1, 7))
+    return np.tile(ACGT[rng.integers(0, 4, size=per)], int(rng.integers(2, 40)))[:int(rng.integers(6, 120))]
+
+
+def stale_window_record(rng, n_events: int):
+    """sdust's stale-window quirk at full strength: runs of N (1..5000) with low-complexity sequence shortly BEFORE them
+    (what the stale window holds) and 0..140 bases AFTER them (where the window start is still pinned, src/sdust/sdust.c:146,
+    and perfect intervals live up to 2W steps instead of W).  A two-phase sdust that drains only W positions after a
+    trigger loses intervals on this input."""
+    parts = []
+    for _ in range(n_events):
+        parts.append(ACGT[rng.integers(0, 4, size=int(rng.integers(0, 300)))])
+        if rng.random() < 0.5:
+            parts.append(_low_complexity(rng))
+        parts.append(ACGT[rng.integers(0, 4, size=int(rng.integers(0, 70)))])
+        parts.append(np.full(int(rng.choice([1, 2, 3, 10, 64, 200, 1600, 5000])), ord("N"), dtype=np.uint8))
+        parts.append(ACGT[rng.integers(0, 4, size=int(rng.integers(0, 140)))])
+        parts.append(_low_complexity(rng))
+        if rng.random() < 0.3:
+            parts.append(ACGT[rng.integers(0, 4, size=int(rng.integers(0, 70)))])
+            parts.append(_low_complexity(rng))
+    return np.concatenate(parts)
+
+
+def stale_window_records(seed: int, n_rec: int = 5):
+    rng = np.random.default_rng(seed)
+    return [(f"stale_{k}", stale_window_record(rng, int(rng.integers(3, 60)))) for k in range(n_rec)]
+
+
 def assembly(seed: int, lengths, **kw):
     rng = np.random.default_rng(seed)
     return [(f"contig_{i + 1}", make_contig(rng, int(L), **kw)) for i, L in enumerate(lengths)]

@@ -328,6 +328,19 @@ def test_sdust_library_api(capi):
     L.sdust_buf_destroy(None)
 
 
+def test_abi_sdust_stale_window_after_gaps(ctx, capi):
+    """Low-complexity sequence right after runs of N: perfect intervals inserted while the window start is still pinned
+    to the first base after the gap live up to 2W steps (src/sdust/sdust.c:146); the two-phase path must keep those
+    positions in its items.  (bench.py's in-run check found a lost 7-base interval 57 bases after a 1.6 kb gap.)"""
+    for seed in (9100, 9103, 9107):
+        recs = [s for _, s in synth.stale_window_records(seed, n_rec=8)]
+        hb = capi.HostBatch(recs)
+        for T, W in ((20, 64), (22, 50), (20, 32)):
+            iv, first = ctx.sdust(hb, T, W)
+            wiv, wfirst = oracle_sdust(recs, T, W)
+            assert (first == wfirst).all() and len(iv) == len(wiv) and (iv == wiv).all(), (seed, T, W)
+
+
 def test_abi_errors(ctx, capi):
     hb = capi.HostBatch([b"ACGT"])
     with pytest.raises(capi.CornError):

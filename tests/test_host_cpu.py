@@ -385,6 +385,8 @@ def test_sim_sdust_two_phase(sim_vec_bin, sim_bin, oracle_bin, tmp_path):
             ("e3", np.frombuffer(b"A" * 70, dtype=np.uint8)), ("e4", np.frombuffer(b"TTAGGG" * 1500, dtype=np.uint8)),
             ("e5", np.frombuffer(b"A" * 7, dtype=np.uint8)), ("e6", np.frombuffer(b"AAAAAAAC" * 100, dtype=np.uint8))]
     files["ends.fa"] = synth.fasta_bytes(ends)
+    for seed in (9100, 9101):                      # low complexity right after runs of N: the long drain of the stale phase
+        files[f"stale{seed}.fa"] = synth.fasta_bytes(synth.stale_window_records(seed))
     n = 0
     for name, data in files.items():
         p = write(str(tmp_path / name), data)
