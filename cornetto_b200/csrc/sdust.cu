@@ -45,20 +45,8 @@ __device__ __forceinline__ uint32_t nt4x4(uint32_t w, uint32_t *valid4)
 // byte stream over one record, 16 bytes per global load
 struct DevFetch {
     const uint8_t *seq;
-    uint4 buf;
-    int blk;
     uint32_t codes, valid;          // the 16 bytes of block cblk, decoded (nt4)
     int cblk;
-    __device__ __forceinline__ uint8_t operator()(int i)
-    {
-        const int b = i >> 4;
-        if (b != blk) { buf = __ldg((const uint4 *)(seq + ((size_t)b << 4))); blk = b; }
-        // branch-free byte select (a chain of ?: here made the compiler clone the whole step body four
-        // times, one per source register, and run each clone with a quarter of the lanes)
-        const uint32_t k = (uint32_t)i & 15u;
-        const uint32_t lo = __byte_perm(buf.x, buf.y, k & 7u), hi = __byte_perm(buf.z, buf.w, k & 7u);
-        return (uint8_t)((k & 8u) ? hi : lo);
-    }
     // sd_nt4(byte i), sixteen positions decoded per load
     __device__ __forceinline__ int nt4(int i)
     {
@@ -74,6 +62,25 @@ struct DevFetch {
         return ((valid >> k) & 1u) ? (int)((codes >> (2u * k)) & 3u) : 4;
     }
 };
+
+// sd_warm_start / sd_warm_quiet (sdust_core.cuh) on the device: the same walk to the left until W triplet positions have
+// been passed, but a 16-byte block without a single A/C/G/T is stepped over at once (a chunk or item that starts behind a
+// 50 kb gap walks across all of it, and the other 31 lanes wait for that one)
+__device__ __forceinline__ int dev_warm_walk(DevFetch &fetch, int p, int W)
+{
+    if (p <= 0) return 0;
+    int need = W, run = 0;
+    while (p > 0 && need > 0) {
+        if ((p & 15) == 0 && p >= 16) {
+            (void)fetch.nt4(p - 1);                       // decodes block [p - 16, p)
+            if (fetch.valid == 0u) { p -= 16; run = 0; continue; }
+        }
+        --p;
+        if (fetch.nt4(p) < 4) { if (++run >= 3) --need; }
+        else run = 0;
+    }
+    return p;
+}
 
 #define SD_QUICK_POPS 4
 
@@ -342,15 +349,14 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
     sd_sink_init(sink, P.slots + (size_t)(have ? j : 0) * P.cap, P.cap);
     DevFetch fetch;
     fetch.seq = P.seq + (have ? P.rec_off[rec] : 0);
-    fetch.blk = -1; fetch.cblk = -1;
-    fetch.buf = make_uint4(0, 0, 0, 0);
+    fetch.cblk = -1;
     fetch.codes = 0; fetch.valid = 0;
 
     sd_state s;
     sd_reset_counters(s, m);                          // (the slot rows were zeroed by a memset before the launch)
     int p0 = 0, n_steps = 0;
     if (have) {
-        p0 = (quiet ? sd_warm_quiet(fetch, c0, W) : sd_warm_start(fetch, c0, W)) & ~15;
+        p0 = dev_warm_walk(fetch, quiet ? c0 : c0 - 2 * W, W) & ~15;     // = sd_warm_quiet / sd_warm_start
                                                       // (a longer warm-up is always valid) all lanes then refill their
                                                       // 16-byte fetch buffer on the same steps
         s.pstart = p0; s.pslot = (int)((uint32_t)p0 % (uint32_t)W);
@@ -358,15 +364,25 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
         n_steps = (stop - p0) + (c1 >= len ? 1 : 0);  // + the reference's i == l_seq iteration for the record's last chunk
     }
 
+    // `skipped` = positions of the warm-up that were jumped over: after the first byte of a run of non-ACGT bytes (which
+    // flushes P and resets l, t) the following ones change nothing (:152-156), and a warm-up that starts in front of a
+    // 50 kb gap would otherwise step through all of it with 31 lanes waiting
+    int skipped = 0, cur_i = 0;
     for (int step = 0;; ++step) {
-        const bool live = step < n_steps;
+        const bool live = step + skipped < n_steps;
         if (!__any_sync(FULL, live)) break;
         bool emit = false, need_pop = false;
         int start = 0;
         if (live) {
-            const int i = p0 + step;
+            const int i = p0 + step + skipped;
+            cur_i = i;
             if (i >= c0) sink.on = 1;
             const int b = i < len ? fetch.nt4(i) : 4;
+            if (b >= 4) {
+                int nx = i + 1;
+                while (nx < c0 && fetch.nt4(nx) >= 4) ++nx;
+                skipped += nx - (i + 1);
+            }
             if (b < 4) {
                 ++s.l;
                 s.t = (s.t << 2 | (unsigned)b) & 63u;
@@ -407,7 +423,7 @@ __device__ __forceinline__ void sdust_warp_task(const SdParams &P, uint32_t warp
             pop_coop<NB>(leader, lane, s, (int)s.t, smem, lay, W);
         }
         bool trig = false;
-        if (emit && s.rw * 10 > s.L * T && !(quiet && p0 + step < c0)) {     // (quiet warm-up: the true run calls nothing here)
+        if (emit && s.rw * 10 > s.L * T && !(quiet && cur_i < c0)) {         // (quiet warm-up: the true run calls nothing here)
             if (!COOP) sd_find_perfect(s, m, T, start, W);
             else trig = s.wn - s.L - 1 >= 0 && s.slack < 0;   // no index to examine / provably no candidate otherwise
         }
@@ -546,9 +562,8 @@ __global__ void __launch_bounds__(SC_BLOCK) k_sdust_scout(const ScoutParams P)
         c1 = min(len, c0 + P.C);
         seq = P.seq + P.rec_off[rec];
         DevFetch fetch;
-        fetch.seq = seq; fetch.blk = -1; fetch.cblk = -1;
-        fetch.buf = make_uint4(0, 0, 0, 0); fetch.codes = 0; fetch.valid = 0;
-        p0 = sd_warm_quiet(fetch, c0, P.W) & ~15;
+        fetch.seq = seq; fetch.cblk = -1; fetch.codes = 0; fetch.valid = 0;
+        p0 = dev_warm_walk(fetch, c0, P.W) & ~15;            // = sd_warm_quiet
     }
     uint8_t *act = P.active + (have ? P.blk_base[rec] : 0);
     uint8_t *tcn = P.tcnt + (have ? P.blk_base[rec] : 0);
@@ -567,6 +582,7 @@ __global__ void __launch_bounds__(SC_BLOCK) k_sdust_scout(const ScoutParams P)
         const int k = ib >> 6;
         const uint32_t real = rem < 16 ? (1u << rem) - 1u : 0xFFFFu;
         if ((valid & real) != real) nfl[k] = 1;               // a non-ACGT byte in this block (any thread may say so)
+        if ((valid & real) == 0u) { sc.l = 0; sc.t = 0; continue; }      // sixteen non-ACGT bytes (inside a gap): nothing else to do
         uint32_t ntrig = 0;
         bool stale = false;                                   // a trigger less than W bases after a non-ACGT byte
 #pragma unroll
