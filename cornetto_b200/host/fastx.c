@@ -31,7 +31,15 @@ struct fastx {
     int      at_line_start, pending_cr, seq_done, term;
     size_t   line_len;
     uint64_t seq_len;
+    /* kseq only learns that the input has ended from a read that returns fewer than its 16384 buffer bytes
+     * (src/kseq.h:72-73,107-108): when the input length is a multiple of 16384 it finds out one read later, and two
+     * decisions fall the other way at that moment (fastx_next, fastx_seq).  total = bytes delivered so far;
+     * zero_read = kseq would already have made the read that returned nothing. */
+    uint64_t total;
+    int      zero_read;
 };
+
+static int kseq_knows_eof(const fastx_t *fx) { return fx->zero_read || (fx->total % 16384u) != 0; }
 
 fastx_t *fastx_open(const char *path)
 {
@@ -66,6 +74,7 @@ fastx_t *fastx_open_at(const char *path, uint64_t offset)
     fastx_t *fx = fastx_open(path);
     if (fx && offset) {
         if (fx->fd < 0 || lseek(fx->fd, (off_t)offset, SEEK_SET) < 0) { fastx_close(fx); return NULL; }
+        fx->total = offset;                          /* (kseq_knows_eof: position in the file, not in this reader) */
     }
     return fx;
 }
@@ -88,6 +97,7 @@ static int fill(fastx_t *fx)
     fx->beg = 0;
     fx->end = n > 0 ? (size_t)n : 0;
     if (n <= 0) { fx->eof = 1; return 0; }
+    fx->total += (uint64_t)n;
     return 1;
 }
 
@@ -97,14 +107,25 @@ int fastx_next(fastx_t *fx)
 {
     if (fx->last_char == 0) {                       /* jump to the next header character */
         for (;;) {
-            if (!fill(fx)) return 0;
+            if (!fill(fx)) { fx->zero_read = 1; return 0; }
             const uint8_t *p = fx->buf + fx->beg, *e = fx->buf + fx->end;
             while (p < e && *p != '>' && *p != '@') ++p;
             if (p < e) { fx->beg = (size_t)(p - fx->buf) + 1; break; }
             fx->beg = fx->end;
         }
     }
-    if (!fill(fx)) return 0;                        /* header char was the last byte: EOF */
+    if (!fill(fx)) {
+        /* the header character was the last byte of the input.  If kseq already knows that (ks_getuntil returns -1,
+         * :194) there is no record; if the input length is a multiple of its buffer it reads an empty name instead
+         * and delivers one more record: name "", length 0 */
+        if (kseq_knows_eof(fx)) return 0;
+        fx->zero_read = 1;
+        fx->name[0] = 0;
+        fx->last_char = 0;
+        fx->at_line_start = 1; fx->pending_cr = 0; fx->seq_done = 0; fx->term = 0;
+        fx->line_len = 0; fx->seq_len = 0;
+        return 1;
+    }
     size_t nl = 0;
     int c = 0;
     for (;;) {
@@ -136,10 +157,15 @@ size_t fastx_seq(fastx_t *fx, uint8_t *dst, size_t cap, int *done)
     if (fx->seq_done) { *done = 1; return 0; }
     for (;;) {
         if (!fill(fx)) {                             /* end of input */
-            if (fx->pending_cr && fx->line_len == 1) {   /* lone '\r' read right at EOF is kept */
+            /* a line that is a lone '\r', read right at the end of the input: kseq has stored it and calls
+             * ks_getuntil2 for the rest of the line.  Knowing the input has ended, that call returns at once and the
+             * byte stays; not knowing it yet (length a multiple of 16384), it runs into the CR rule (:138) and drops
+             * the byte unless it is the whole sequence so far */
+            if (fx->pending_cr && fx->line_len == 1 && (kseq_knows_eof(fx) || fx->seq_len == 0)) {
                 if (w == cap) return w;
                 dst[w++] = '\r'; fx->seq_len++;
             }
+            fx->zero_read = 1;
             fx->pending_cr = 0;
             fx->term = -1; fx->seq_done = 1; *done = 1;
             return w;

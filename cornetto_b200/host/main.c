@@ -28,10 +28,49 @@ static int print_usage(FILE *fp)
     return fp == stdout ? EXIT_SUCCESS : EXIT_FAILURE;
 }
 
+/* CUDA start-up is the longest phase of every scan command (0.5-3 s, and it grows with the number of devices the
+ * driver has to bring up).  A run uses $CORNETTO_GPUS devices (default 1) starting at $CORNETTO_GPU (default 0):
+ * hide the others from the runtime before its first call, so that only those are initialised.  An existing
+ * CUDA_VISIBLE_DEVICES is honoured (the selection is made among its entries); $CORNETTO_KEEP_VISIBLE=1 leaves it alone. */
+static void restrict_visible_devices(void)
+{
+    const char *keep = getenv("CORNETTO_KEEP_VISIBLE");
+    if (keep && atoi(keep) > 0) return;
+    const char *eg = getenv("CORNETTO_GPUS"), *e0 = getenv("CORNETTO_GPU");
+    int n = eg && atoi(eg) > 0 ? atoi(eg) : 1;
+    const int first = (n == 1 && e0 && atoi(e0) > 0) ? atoi(e0) : 0;
+    const char *vis = getenv("CUDA_VISIBLE_DEVICES");
+    char out[1024];
+    size_t o = 0;
+    out[0] = 0;
+    if (vis && *vis) {                                   /* entries first .. first + n - 1 of the existing list */
+        int idx = 0;
+        const char *p = vis;
+        while (*p && n > 0) {
+            const char *q = strchr(p, ',');
+            const size_t len = q ? (size_t)(q - p) : strlen(p);
+            if (idx >= first && len > 0 && o + len + 2 < sizeof out) {
+                if (o) out[o++] = ',';
+                memcpy(out + o, p, len); o += len; out[o] = 0;
+                --n;
+            }
+            ++idx;
+            if (!q) break;
+            p = q + 1;
+        }
+        if (o == 0) return;                              /* selection outside the list: let the runtime report it */
+    } else {
+        for (int i = 0; i < n && o + 16 < sizeof out; ++i) o += (size_t)snprintf(out + o, sizeof out - o, "%s%d", i ? "," : "", first + i);
+    }
+    setenv("CUDA_VISIBLE_DEVICES", out, 1);
+    if (first) setenv("CORNETTO_GPU", "0", 1);           /* the chosen device is now number 0 */
+}
+
 int main(int argc, char *argv[])
 {
     double realtime0 = realtime();
     int ret = 1;
+    restrict_visible_devices();
 
     if (argc < 2) return print_usage(stderr);
     else if (strcmp(argv[1], "telowin") == 0) ret = telomere_windows_main(argc - 1, argv + 1);

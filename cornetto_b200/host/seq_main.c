@@ -20,6 +20,8 @@ typedef struct {
     gzFile fp;
     unsigned char *buf;
     int beg, end, eof;
+    uint64_t total;          /* bytes delivered so far; zero_read: kseq would already have made the read that returned */
+    int zero_read;           /* nothing -- it learns of the end of the input only from a short read (src/kseq.h:107-108) */
     int last_char;
     str_t name, comment, seq, qual;
 } rd_t;
@@ -43,10 +45,18 @@ static int rd_fill(rd_t *r)
     r->beg = 0;
     r->end = gzread(r->fp, r->buf, RD_BUF);
     if (r->end <= 0) { r->end = 0; r->eof = 1; return 0; }
+    r->total += (uint64_t)r->end;
     return 1;
 }
 
-static int rd_getc(rd_t *r) { return rd_fill(r) ? r->buf[r->beg++] : -1; }
+static int rd_knows_eof(const rd_t *r) { return r->zero_read || (r->total % 16384u) != 0; }
+
+static int rd_getc(rd_t *r)
+{
+    if (rd_fill(r)) return r->buf[r->beg++];
+    r->zero_read = 1;
+    return -1;
+}
 
 /* reads up to (and consumes) the next delimiter; returns the string length or -1 when no byte was left */
 static long rd_until(rd_t *r, int sep, str_t *s, int *dret, int append)
@@ -65,7 +75,13 @@ static long rd_until(rd_t *r, int sep, str_t *s, int *dret, int append)
         r->beg = i + 1;
         if (i < r->end) { if (dret) *dret = r->buf[i]; break; }
     }
-    if (!got) return -1;
+    if (!got) {
+        /* no byte left.  kseq returns -1 only if it already KNOWS the input has ended (:100); when the length is a
+         * multiple of its 16384-byte buffer it reads nothing, falls through and finishes the string (empty name;
+         * CR rule applied to what is there) */
+        if (rd_knows_eof(r)) return -1;
+        r->zero_read = 1;
+    }
     str_reserve(s, s->l + 1);
     if (sep == SEP_LINE && s->l > 1 && s->s[s->l - 1] == '\r') --s->l;      /* (on the whole string, :138) */
     s->s[s->l] = 0;

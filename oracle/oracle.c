@@ -14,9 +14,21 @@
  * src/kseq.h:91-141, restated over an in-memory copy of the (decompressed) file.
  * ====================================================================================== */
 
-typedef struct { const uint8_t *b; size_t n, p; } cur_t;
+/* zero_read: kseq learns that the input has ended only from a read that returns fewer than its 16384 buffer bytes
+ * (src/kseq.h:72-73,107-108); when the input length is a multiple of 16384 it finds out one read later.  Until then
+ * ks_getuntil2 at the end of the data does not return -1 (:100) but reads nothing, falls through and finishes the
+ * string -- which gives one more record with an empty name after a final '>' / '@', and strips a final lone '\r'.
+ * [checked against the compiled reference on files of 16384, 32768 and 49152 bytes] */
+typedef struct { const uint8_t *b; size_t n, p; int zero_read; } cur_t;
 
-static int cur_getc(cur_t *c) { return c->p < c->n ? (int)c->b[c->p++] : -1; }
+static int cur_knows_eof(const cur_t *c) { return c->zero_read || (c->n % 16384u) != 0; }
+
+static int cur_getc(cur_t *c)
+{
+    if (c->p < c->n) return (int)c->b[c->p++];
+    c->zero_read = 1;
+    return -1;
+}
 
 typedef struct { char *s; size_t l, m; } str_t;
 
@@ -33,7 +45,14 @@ static void str_need(str_t *s, size_t extra)
  * Returns -1 when called at end of data (src/kseq.h:95), else the string length. */
 static long getline_append(cur_t *c, str_t *s)
 {
-    if (c->p >= c->n) return -1;
+    if (c->p >= c->n) {
+        if (cur_knows_eof(c)) return -1;
+        c->zero_read = 1;                           /* reads nothing, then the CR rule and the terminator as usual */
+        str_need(s, 0);
+        if (s->l > 1 && s->s[s->l - 1] == '\r') --s->l;
+        s->s[s->l] = 0;
+        return (long)s->l;
+    }
     const uint8_t *nl = (const uint8_t *)memchr(c->b + c->p, '\n', c->n - c->p);
     size_t k = nl ? (size_t)(nl - (c->b + c->p)) : c->n - c->p;
     str_need(s, k);
@@ -47,7 +66,7 @@ static long getline_append(cur_t *c, str_t *s)
 
 int orc_parse_fastx_mem(const uint8_t *buf, size_t n, orc_rec_t **recs_out, size_t *n_out)
 {
-    cur_t c = { buf, n, 0 };
+    cur_t c = { buf, n, 0, 0 };
     orc_rec_t *recs = NULL;
     size_t nr = 0, mr = 0;
     int last_char = 0, ch;
@@ -60,7 +79,10 @@ int orc_parse_fastx_mem(const uint8_t *buf, size_t n, orc_rec_t **recs_out, size
             last_char = ch;
         }
         /* name: up to the first isspace() (src/kseq.h:195) */
-        if (c.p >= c.n) break;                      /* ks_getuntil() < 0 -> EOF */
+        if (c.p >= c.n) {                           /* ks_getuntil() < 0 -> EOF, if kseq knows; else an empty name */
+            if (cur_knows_eof(&c)) break;
+            c.zero_read = 1;
+        }
         str_need(&name, 0);
         ch = 0;
         while (c.p < c.n) {

@@ -239,4 +239,20 @@ def quirk_corpus(seed: int = 7):
         ("micro", R(64) + b"CAG" * 40 + R(64) + b"AT" * 50 + R(64)),
         ("bytes0123", b"\x01\x02\x03" * 20 + R(10)),
     ])
+    # 7. kseq learns of the end of the input only from a read shorter than its 16384-byte buffer (src/kseq.h:107-108):
+    #    files whose size is a multiple of 16384 and that end in a header character or a lone '\r' behave differently
+    #    from the same endings at any other size (one more record with an empty name; the '\r' is dropped)
+    def sized(total, head, tail):
+        line = b"ACGT" * 15 + b"\n"
+        body_len = total - len(head) - len(tail)
+        body = line * (body_len // len(line))
+        rest = body_len - len(body)
+        if rest > 0:
+            body += (b"A" * (rest - 1) + b"\n") if rest > 1 else b"\n"
+        out = head + body + tail
+        assert len(out) == total
+        return out
+    files["q7_eof16k_gt.fa"] = sized(16384, b">r1 c\n" + b"TTAGGG" * 8 + b"\n", b"\n>")
+    files["q7_eof32k_cr.fa"] = sized(32768, b">r1\n", b"\n\r")
+    files["q7_eof16k_off.fa"] = sized(16383, b">r1\n", b"\n>")
     return files
