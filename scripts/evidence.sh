@@ -1,18 +1,25 @@
 # Collects the per-round evidence under gpurun_out/ (copy what should be judged into profiles/).
-# usage: bash scripts/evidence.sh <tag>      e.g. r01_q
-tag=${1:-r01_x}
+# usage: bash scripts/evidence.sh <tag>      e.g. r02_s        (one B200; ~10 minutes)
+tag=${1:-r02_x}
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/${tag}_gpu_tests.log
-python bench.py > gpurun_out/${tag}_bench_c2.jsonl 2> gpurun_out/bench.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_reference_arm.jsonl 2>> gpurun_out/bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_bench_c2.csv python bench.py --profile-only --steps 3 --warmup 3 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_telofind_scan -s 3 -c 1 -o gpurun_out/scan_full -f python bench.py --profile-only --steps 2 --warmup 3 > /dev/null 2>&1
+python bench.py --steps 100 --warmup 5 > gpurun_out/${tag}_bench_c2.jsonl 2> gpurun_out/${tag}_bench.err
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${tag}_bench_reference_arm.jsonl 2>> gpurun_out/${tag}_bench.err
+# launch list of the fused step (one host context, so that the six launches of a step are in order)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/${tag}_launches_bench_c2.csv python bench.py --profile-only --no-pipeline --steps 3 --warmup 3 > /dev/null 2>&1
+# full captures: the dominant kernel, and the three kernels of the two-phase sdust path
+ncu --set full --clock-control none --import-source on -k regex:k_telofind_scan -s 3 -c 1 -o gpurun_out/scan_full -f python bench.py --profile-only --no-pipeline --steps 2 --warmup 3 > /dev/null 2>&1
 ncu -i gpurun_out/scan_full.ncu-rep --page raw --csv > gpurun_out/scan_full_raw.csv 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:k_sdust_scan -c 1 -o gpurun_out/sdust_full -f python scripts/prof_sdust.py 1200 1 > /dev/null 2>&1
-ncu -i gpurun_out/sdust_full.ncu-rep --page raw --csv > gpurun_out/sdust_full_raw.csv 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:k_ing_copy -c 1 -o gpurun_out/ingest_full -f python scripts/prof_ingest.py 800 > /dev/null 2>&1
-ncu -i gpurun_out/ingest_full.ncu-rep --page raw --csv > gpurun_out/ingest_full_raw.csv 2>/dev/null
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches_ingest.csv python scripts/prof_ingest.py 800 > /dev/null 2>&1
-python scripts/cli_bench.py 3000 > gpurun_out/${tag}_cli_bench_fasta_3000Mb.json 2>> gpurun_out/bench.err
-python scripts/cli_bench_fastq.py 2000 > gpurun_out/${tag}_cli_bench_fastq_2000Mb.json 2>> gpurun_out/bench.err
-tail -c 400 gpurun_out/${tag}_bench_c2.jsonl; cat gpurun_out/${tag}_gpu_tests.log gpurun_out/${tag}_cli_bench_fasta_3000Mb.json gpurun_out/${tag}_cli_bench_fastq_2000Mb.json
+python scripts/ncu_summary.py gpurun_out/scan_full_raw.csv gpurun_out/${tag}_telofind_scan_ncu_full.json "ncu --set full --clock-control none, one launch of k_telofind_scan<6,TTAGGG> on the c2 workload (3.117 Gb resident)"
+for k in k_sdust_scout k_sdust_dense k_sdust_scan; do
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -o gpurun_out/sd_$k -f python scripts/prof_sdust.py 1200 2 > /dev/null 2>&1
+  ncu -i gpurun_out/sd_$k.ncu-rep --page raw --csv > gpurun_out/sd_${k}_raw.csv 2>/dev/null
+  python scripts/ncu_summary.py gpurun_out/sd_${k}_raw.csv gpurun_out/${tag}_${k}_ncu_full.json "ncu --set full --clock-control none, second launch of $k, sdust -w 64 -t 20 on a 1.2 Gb feature-rich batch"
+done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/${tag}_launches_sdust.csv python scripts/prof_sdust.py 1200 2 > /dev/null 2>&1
+CORNETTO_TRACE=1 python scripts/prof_sdust.py 3000 3 > gpurun_out/${tag}_prof_sdust.txt 2>&1
+CORNETTO_TRACE=1 python scripts/prof_sdust.py 3000 2 plain >> gpurun_out/${tag}_prof_sdust.txt 2>&1
+CORNETTO_SDUST_CLASSIC=1 python scripts/prof_sdust.py 3000 2 >> gpurun_out/${tag}_prof_sdust.txt 2>&1
+python scripts/cli_bench.py 3000 > gpurun_out/${tag}_cli_bench_fasta_3000Mb.json 2>> gpurun_out/${tag}_bench.err
+rm -f gpurun_out/*.ncu-rep
+tail -c 300 gpurun_out/${tag}_bench_c2.jsonl; cat gpurun_out/${tag}_gpu_tests.log gpurun_out/${tag}_prof_sdust.txt gpurun_out/${tag}_cli_bench_fasta_3000Mb.json
