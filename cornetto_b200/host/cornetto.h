@@ -132,6 +132,15 @@ uint64_t cornetto_next_batch_seq(void);
  * text: everything before *resume has been processed and written, and the caller continues with the
  * serial reader from byte offset *resume. */
 int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resume);
+/* ---- decompressed text of a .gz input in large blocks (gzsrc.c): BGZF members inflated on several threads, any other
+ * gzip file by one stream beside the GPU work.  gzsrc_read: up to n bytes at dst, *eof once the input has ended; -1 if
+ * the file is damaged. */
+typedef struct gzsrc gzsrc_t;
+gzsrc_t *gzsrc_open(const char *path);
+void     gzsrc_close(gzsrc_t *g);
+int      gzsrc_is_bgzf(const gzsrc_t *g);
+int64_t  gzsrc_read(gzsrc_t *g, uint8_t *dst, uint64_t n, int *eof);
+
 /* length of a record name starting at p: up to the first isspace() byte or max (src/kseq.h:195) */
 size_t cornetto_name_len(const uint8_t *p, size_t max);
 

@@ -73,7 +73,8 @@ fastx_t *fastx_open_at(const char *path, uint64_t offset)
 {
     fastx_t *fx = fastx_open(path);
     if (fx && offset) {
-        if (fx->fd < 0 || lseek(fx->fd, (off_t)offset, SEEK_SET) < 0) { fastx_close(fx); return NULL; }
+        /* plain file: seek; gzip: zlib inflates and discards up to the (decompressed) offset */
+        if (fx->fp ? gzseek(fx->fp, (z_off_t)offset, SEEK_SET) < 0 : lseek(fx->fd, (off_t)offset, SEEK_SET) < 0) { fastx_close(fx); return NULL; }
         fx->total = offset;                          /* (kseq_knows_eof: position in the file, not in this reader) */
     }
     return fx;

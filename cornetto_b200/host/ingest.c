@@ -210,12 +210,20 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
     if (fd < 0) return 0;
     struct stat sb;
     unsigned char magic[2] = { 0, 0 };
-    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size < 2 || pread(fd, magic, 2, 0) != 2 ||
-        (magic[0] == 0x1f && magic[1] == 0x8b) || (magic[0] != '>' && magic[0] != '@')) {
+    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size < 2 || pread(fd, magic, 2, 0) != 2) { close(fd); return 0; }
+    /* gzip input: the text comes from gzsrc.c (BGZF members inflated in parallel, other gzip files by one stream that
+     * runs beside the GPU work); its length is not known in advance.  $CORNETTO_GZ_INGEST=0: serial reader as before. */
+    gzsrc_t *gz = NULL;
+    if (magic[0] == 0x1f && magic[1] == 0x8b) {
+        const char *eg = getenv("CORNETTO_GZ_INGEST");
+        if (!(eg && atoi(eg) == 0)) gz = gzsrc_open(path);
+        if (!gz) { close(fd); return 0; }
+    } else if (magic[0] != '>' && magic[0] != '@') {
         close(fd);
         return 0;
     }
-    const uint64_t size = (uint64_t)sb.st_size;
+    const uint64_t size = gz ? (1ull << 62) : (uint64_t)sb.st_size;
+    int src_eof = 0;
 
     int n_gpus = 1;                        /* requested; clipped to the devices present once the driver is up */
     const char *e = getenv("CORNETTO_GPUS");
@@ -231,6 +239,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
     const char *eb = getenv("CORNETTO_BATCH_BYTES"), *em = getenv("CORNETTO_BATCH_MB");
     if (eb && atoll(eb) > 0) block = (uint64_t)atoll(eb);
     else if (em && atoll(em) > 0) block = (uint64_t)atoll(em) << 20;
+    if (gz && !(eb && atoll(eb) > 0) && !(em && atoll(em) > 0)) block = 1ull << 30;      /* text blocks of 1 GiB */
     if (block > size) block = size;
     if (block > max_block) block = max_block;
     if (block < 64) block = 64;
@@ -282,12 +291,19 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
             if (carry_len) memcpy(x->blk, carry, carry_len);
             fresh = want = ahead_bytes;
         } else {
-            if (ahead_for == dispatched) file_pos -= ahead_bytes;                /* tail too large: read again behind it */
+            if (ahead_for == dispatched) {                                       /* tail too large: read again behind it */
+                if (gz) { *resume = file_pos - ahead_bytes - carry_len; break; } /* (a stream cannot go back: the serial reader takes over) */
+                file_pos -= ahead_bytes;
+            }
             x->blk = x->text;
             if (carry_len) memcpy(x->blk, carry, carry_len);
             want = size - file_pos < block - carry_len ? size - file_pos : block - carry_len;
             const double t_rd = realtime();
-            fresh = read_block(fd, x->blk + carry_len, file_pos, want);
+            if (gz) {
+                const int64_t k = gzsrc_read(gz, x->blk + carry_len, want, &src_eof);
+                if (k < 0) { *resume = file_pos - carry_len; break; }             /* damaged: the serial reader reports it as gzread does */
+                fresh = (uint64_t)k;
+            } else fresh = read_block(fd, x->blk + carry_len, file_pos, want);
             die_if_read_failed(path);
             TRACE("[ingest] read %.1f MB in %.3f s\n", (double)fresh / 1e6, realtime() - t_rd);
             file_pos += fresh;
@@ -295,7 +311,8 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
         ahead_for = -1;
         const uint64_t block_off = file_pos - fresh - carry_len;
         x->n = carry_len + fresh;
-        x->final = (fresh < want || file_pos >= size);
+        x->final = gz ? src_eof : (fresh < want || file_pos >= size);
+        if (gz && x->final && x->n == 0) { complete = 1; break; }                /* the stream ended exactly at a block end */
         x->ingested = 0;
         x->seq = cornetto_next_batch_seq();
         pthread_mutex_lock(&x->mu);
@@ -326,7 +343,10 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
             }
             const uint64_t w2 = size - file_pos < block - reserve ? size - file_pos : block - reserve;
             const double t_rd = realtime();
-            ahead_bytes = read_block(fd, y->text + reserve, file_pos, w2);
+            if (gz) {
+                const int64_t k = gzsrc_read(gz, y->text + reserve, w2, &src_eof);
+                ahead_bytes = k < 0 ? 0 : (uint64_t)k;                            /* (a damaged stream shows up again at the next read) */
+            } else ahead_bytes = read_block(fd, y->text + reserve, file_pos, w2);
             die_if_read_failed(path);
             TRACE("[ingest] read ahead %.1f MB in %.3f s\n", (double)ahead_bytes / 1e6, realtime() - t_rd);
             file_pos += ahead_bytes;
@@ -361,6 +381,7 @@ int run_ingest_pipeline(const char *path, batch_fn fn, void *arg, uint64_t *resu
     fflush(cornetto_pipeline_out());
     free(w);
     close(fd);
+    if (gz) gzsrc_close(gz);
     TRACE("[ingest] pipeline done (complete %d)\n", complete);
     return complete;
 }

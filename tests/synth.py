@@ -113,6 +113,20 @@ def fastq_bytes(records, width: int = 0) -> bytes:
     return bytes(out)
 
 
+def bgzf_bytes(data: bytes, block: int = 65280) -> bytes:
+    """BGZF (bgzip) container of `data`: gzip members of <= 64 KiB with the 'BC' extra field, plus the empty end member."""
+    import struct
+    import zlib
+    out = []
+    for i in list(range(0, len(data), block)) + [None]:
+        chunk = data[i:i + block] if i is not None else b""
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = c.compress(chunk) + c.flush()
+        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                   struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    return b"".join(out)
+
+
 def _low_complexity(rng):
     kind = rng.integers(0, 3)
     if kind == 0:

@@ -300,6 +300,27 @@ def test_cli_telostats_matches_script(tmp_path, oracle_bin):
     assert rc == 1
 
 
+def test_cli_gzip_inputs_through_the_device_parser(tmp_path, oracle_bin):
+    """.gz inputs are inflated by host/gzsrc.c (BGZF members in parallel) and parsed on the device; results must equal the
+    oracle's, which reads through gzread: one member, several members, BGZF, small text blocks (carry-over between
+    blocks), FASTQ, and with the serial reader forced."""
+    import gzip
+    fa = synth.fasta_bytes(synth.assembly(19, [300_000, 120_000, 40_000, 7], n_gaps=1, telo=(60, 300)))
+    fq = synth.fastq_bytes(synth.reads(4, 20, n50=9_000, p_telo=0.4))
+    files = {"a.fa.gz": gzip.compress(fa), "b.fa.gz": synth.bgzf_bytes(fa), "c.fq.gz": synth.bgzf_bytes(fq),
+             "m.fa.gz": gzip.compress(fa[:100_000]) + gzip.compress(fa[100_000:])}
+    for name, data in files.items():
+        p = write(str(tmp_path / name), data)
+        want_t, _, _ = run([oracle_bin, "telofind", p])
+        want_s, _, _ = run([oracle_bin, "sdust", p])
+        assert len(want_t) > 500
+        for env in ({}, {"CORNETTO_BATCH_BYTES": "150000"}, {"CORNETTO_GZ_INGEST": "0"}):
+            out, _, _ = cornetto(["telofind", p], env=env)
+            assert out == want_t, (name, env)
+            out, _, _ = cornetto(["sdust", p], env=env)
+            assert out == want_s, (name, env)
+
+
 def test_sdust_library_api(capi):
     """sdust() / sdust_buf_init / sdust_core / sdust_buf_destroy with the reference's signatures and ownership rules
     (src/sdust/sdust.h:16-21): l_seq < 0 means strlen, sdust()'s result is free()d by the caller, sdust_core()'s

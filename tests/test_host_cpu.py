@@ -428,6 +428,27 @@ def test_sim_sdust_wide_windows(sim_wide_bin, oracle_bin, tmp_path):
             assert a == b, (opts, chunk)
 
 
+def test_gzip_text_source(tmp_path):
+    """host/gzsrc.c (the feeder of the device parser for .gz inputs): same bytes as gzip itself for one member, several
+    members, BGZF (members inflated in parallel) and trailing garbage, whatever the request size."""
+    import gzip
+    exe = str(tmp_path / "gz_dump")
+    subprocess.check_call(["gcc", "-O2", "-std=c99", "-D_GNU_SOURCE", "-I" + INC, "-o", exe, os.path.join(ROOT, "tests", "sim", "gz_dump.c"),
+                           os.path.join(ROOT, "cornetto_b200", "host", "gzsrc.c"), "-lz", "-lpthread"])
+    text = synth.fasta_bytes(synth.assembly(8, [400_000, 150_000, 70_000, 9], n_gaps=1))
+    files = {"plain.gz": gzip.compress(text), "bgzf.gz": synth.bgzf_bytes(text), "garbage.gz": gzip.compress(text) + b"\x00\x00junk",
+             "multi.gz": gzip.compress(text[:200_000]) + gzip.compress(text[200_000:500_001]) + gzip.compress(text[500_001:])}
+    for name, data in files.items():
+        p = write(str(tmp_path / name), data)
+        for req in ("70000", "1000003", "67108864"):
+            out, err, rc = run([exe, p, req])
+            assert rc == 0 and out == text, (name, req)
+            assert (b"bgzf=1" in err) == (name == "bgzf.gz")
+    p = write(str(tmp_path / "bad.gz"), synth.bgzf_bytes(text)[:100_000] + b"\x00" * 64)      # damaged BGZF member chain
+    _, _, rc = run([exe, p, "1000003"], check=False)
+    assert rc == 3
+
+
 def test_scan_commands_fail_loudly_without_gpu(built, tmp_path):
     import torch
     if torch.cuda.is_available():
