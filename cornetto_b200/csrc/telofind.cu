@@ -514,31 +514,40 @@ __global__ void __launch_bounds__(TP_THREADS) k_telofind_tile_prefix(const TileP
     uint4 wbase = make_uint4(0, 0, 0, 0), agg = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int w = 0; w < TP_THREADS / 32; ++w) { if (w < warp) wbase = add4(wbase, warp_tot[w]); agg = add4(agg, warp_tot[w]); }
-    // publish the aggregate, look back
-    if (threadIdx.x == 0) {
+    // publish the aggregate, then look back with one warp, 32 predecessors at a time (a single thread walking them one
+    // by one made the last of ~100 blocks wait for ~100 dependent global reads: 29 us for a 5 us job)
+    if (warp == 0) {
         uint4 excl = make_uint4(0, 0, 0, 0);
-        if (blockIdx.x == 0) {
-            P.blk_val[1] = agg;
-            __threadfence();
-            atomicExch(&P.blk_flag[0], 2u);
-        } else {
+        if (lane == 0) {
             P.blk_val[2 * blockIdx.x] = agg;
+            if (blockIdx.x == 0) P.blk_val[1] = agg;
             __threadfence();
-            atomicExch(&P.blk_flag[blockIdx.x], 1u);
-            for (int b = (int)blockIdx.x - 1; b >= 0; --b) {
-                uint32_t f;
-                while ((f = atomicAdd(&P.blk_flag[b], 0u)) == 0u) { }
-                __threadfence();
-                const volatile uint4 *pv = (const volatile uint4 *)&P.blk_val[2 * b + (f == 2u ? 1 : 0)];
-                excl = add4(excl, make_uint4(pv->x, pv->y, pv->z, pv->w));
-                if (f == 2u) break;
-            }
-            P.blk_val[2 * blockIdx.x + 1] = add4(excl, agg);
-            __threadfence();
-            atomicExch(&P.blk_flag[blockIdx.x], 2u);
+            atomicExch(&P.blk_flag[blockIdx.x], blockIdx.x == 0 ? 2u : 1u);
         }
-        blk_excl = excl;
-        if (blockIdx.x == gridDim.x - 1) *P.totals = add4(excl, agg);
+        for (int base = (int)blockIdx.x - 1; base >= 0; base -= 32) {
+            const int b = base - lane;                          // lane 0 looks at the nearest predecessor
+            uint32_t f = 2u;                                    // (in front of block 0: an empty prefix)
+            if (b >= 0) { while ((f = atomicAdd(&P.blk_flag[b], 0u)) == 0u) { } __threadfence(); }
+            const uint32_t pm = __ballot_sync(0xffffffffu, f == 2u);
+            const int stop = pm ? __ffs(pm) - 1 : 32;           // nearest predecessor that already knows its inclusive prefix
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (b >= 0 && lane <= stop) {
+                const volatile uint4 *pv = (const volatile uint4 *)&P.blk_val[2 * b + (lane == stop ? 1 : 0)];
+                v = make_uint4(pv->x, pv->y, pv->z, pv->w);
+            }
+            v.x = corn_warp_sum(v.x); v.y = corn_warp_sum(v.y); v.z = corn_warp_sum(v.z); v.w = corn_warp_sum(v.w);
+            excl = add4(excl, v);
+            if (pm) break;
+        }
+        if (lane == 0) {
+            if (blockIdx.x != 0) {
+                P.blk_val[2 * blockIdx.x + 1] = add4(excl, agg);
+                __threadfence();
+                atomicExch(&P.blk_flag[blockIdx.x], 2u);
+            }
+            blk_excl = excl;
+            if (blockIdx.x == gridDim.x - 1) *P.totals = add4(excl, agg);
+        }
     }
     __syncthreads();
     uint4 run = add4(blk_excl, add4(wbase, make_uint4(inc.x - sum.x, inc.y - sum.y, inc.z - sum.z, inc.w - sum.w)));
