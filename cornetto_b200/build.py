@@ -9,6 +9,10 @@ def lib_path() -> str:
     return os.path.join(HERE, "lib", "libcorn_gpu.so")
 
 
+def bench_lib_path() -> str:
+    return os.path.join(HERE, "lib", "libcorn_bench.so")
+
+
 def bin_path() -> str:
     return os.path.join(HERE, "bin", "cornetto")
 

@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .build import lib_path
+from .build import bench_lib_path, lib_path
 
 CORN_ALIGN = 32
 CORN_OK = 0
@@ -71,6 +71,7 @@ SYMBOLS = [
     "corn_shard_plan", "corn_shard_local_index", "corn_shard_merge_runs", "corn_shard_merge_intervals",
     "corn_bench_fill_random", "corn_bench_fill_random_rec", "corn_bench_apply_features", "corn_bench_download_all", "corn_bench_flush_l2",
 ]
+BENCH_SYMBOLS = [s for s in SYMBOLS if s.startswith("corn_bench_")]       # exported by libcorn_bench.so, not by the product library
 
 _lib = None
 
@@ -83,7 +84,13 @@ def load() -> C.CDLL:
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the CUDA library is the only implementation; there is no fallback)")
-    L = C.CDLL(path)
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    # the synthetic-input helpers (include/corn_bench.h) live in a library of their own; their entry points are
+    # attached to the same handle object so that callers keep writing L.corn_bench_*
+    if os.path.exists(bench_lib_path()):
+        B = C.CDLL(bench_lib_path())
+        for name in BENCH_SYMBOLS:
+            setattr(L, name, getattr(B, name))
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     L.corn_gpu_device_count.restype = i32
     L.corn_gpu_init.argtypes = [i32, C.POINTER(vp)]
