@@ -18,6 +18,7 @@ CORN_E_NOGPU = -1
 
 RUN_DTYPE = np.dtype([("rec", "<u4"), ("strand", "<u4"), ("start", "<u4"), ("end", "<u4")])
 WIN_DTYPE = np.dtype([("rec", "<u4"), ("start", "<u4"), ("end", "<u4"), ("car", "<u4")])
+DEPTHWIN_DTYPE = np.dtype([("ctg", "<u4"), ("st", "<u4"), ("end", "<u4"), ("depth", "<i4"), ("mq_depth", "<i4")])
 FEAT_DTYPE = np.dtype([("rec", "<u4"), ("start", "<u4"), ("len", "<u4"), ("kind", "<u4"), ("period", "<u4"),
                        ("seed", "<u4"), ("p_variant", "<f4"), ("unit", "u1", (8,)), ("_pad", "<u4")])
 
@@ -49,6 +50,20 @@ class Ingest(C.Structure):
                 ("consumed", C.c_uint64), ("irregular", C.c_int), ("_owner", C.c_void_p)]
 
 
+class DepthBatch(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("mq_depth", C.c_void_p), ("offset", C.c_void_p), ("length", C.c_void_p),
+                ("n_ctg", C.c_uint32), ("n_total", C.c_uint64)]
+
+
+class DepthParams(C.Structure):
+    _fields_ = [("window_size", C.c_int), ("window_inc", C.c_int), ("thresh_low_depth", C.c_int), ("thresh_high_depth", C.c_int),
+                ("low_mq_cov_thresh", C.c_float), ("edge_len", C.c_int), ("min_ctg_len", C.c_int), ("boring", C.c_int)]
+
+
+class DepthWindows(C.Structure):
+    _fields_ = [("win", C.c_void_p), ("n_win", C.c_uint64), ("_owner", C.c_void_p)]
+
+
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("scan_ms", C.c_float), ("post_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("launches", C.c_uint32), ("out_bytes", C.c_uint64)]
@@ -66,6 +81,7 @@ SYMBOLS = [
     "corn_gpu_telowin", "corn_gpu_windows_free",
     "corn_gpu_sdust", "corn_gpu_sdust_dev", "corn_gpu_intervals_free",
     "sdust", "sdust_buf_init", "sdust_buf_destroy", "sdust_core",
+    "corn_gpu_depthwin", "corn_gpu_depth_windows_free",
     "corn_gpu_ingest", "corn_gpu_ingest_free", "corn_gpu_host_register", "corn_gpu_host_unregister",
     "corn_gpu_last_timing", "corn_gpu_total_launches",
     "corn_shard_plan", "corn_shard_local_index", "corn_shard_merge_runs", "corn_shard_merge_intervals",
@@ -144,6 +160,9 @@ def load() -> C.CDLL:
     L.sdust_buf_destroy.restype = None
     L.sdust_core.argtypes = [C.c_char_p, i32, i32, i32, C.POINTER(i32), vp]
     L.sdust_core.restype = C.POINTER(C.c_uint64)
+    L.corn_gpu_depthwin.argtypes = [vp, C.POINTER(DepthBatch), C.POINTER(DepthParams), C.POINTER(DepthWindows)]
+    L.corn_gpu_depth_windows_free.argtypes = [C.POINTER(DepthWindows)]
+    L.corn_gpu_depth_windows_free.restype = None
     L.corn_gpu_ingest.argtypes = [vp, vp, u64, i32, C.POINTER(Ingest)]
     L.corn_gpu_ingest_free.argtypes = [C.POINTER(Ingest)]
     L.corn_gpu_ingest_free.restype = None
@@ -389,6 +408,20 @@ class Context:
         else:
             res["seq"] = []
         return res
+
+    def depthwin(self, depth_list, mq_list, window_size=2500, window_inc=50, lo=0, hi=1 << 30, mq_thr=0.4, edge_len=100000, min_ctg_len=1000000, boring=0):
+        """corn_gpu_depthwin on per-contig uint16 arrays -> structured array of the selected windows"""
+        d = np.ascontiguousarray(np.concatenate(depth_list), dtype=np.uint16)
+        q = np.ascontiguousarray(np.concatenate(mq_list), dtype=np.uint16)
+        lens = np.array([len(x) for x in depth_list], dtype=np.uint32)
+        off = np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.uint64)]).astype(np.uint64)
+        b = DepthBatch(d.ctypes.data, q.ctypes.data, off.ctypes.data, lens.ctypes.data, len(lens), len(d))
+        p = DepthParams(window_size, window_inc, lo, hi, mq_thr, edge_len, min_ctg_len, boring)
+        w = DepthWindows()
+        _check(self.ctx, self.L.corn_gpu_depthwin(self.ctx, C.byref(b), C.byref(p), C.byref(w)), "corn_gpu_depthwin")
+        out = _copy_struct_array(w.win, w.n_win, DEPTHWIN_DTYPE)
+        self.L.corn_gpu_depth_windows_free(C.byref(w))
+        return out
 
     def timing(self) -> dict:
         t = Timing()

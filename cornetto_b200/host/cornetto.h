@@ -34,6 +34,7 @@ int nx_main(int argc, char *argv[]);
 int report_main(int argc, char *argv[]);
 int seq_main(int argc, char *argv[]);
 int telostats_main(int argc, char *argv[]);
+int boringbits_main(int argc, char *argv[], int boring);
 
 /* misc.c */
 uint64_t cornetto_batch_capacity(const char *path, int n_parts);

@@ -11,6 +11,8 @@ static int print_usage(FILE *fp)
 {
     fprintf(fp, "Usage: cornetto <command> [options]\n\n");
     fprintf(fp, "commands (B200 build: the sequence-scan path):\n");
+    fprintf(fp, "   create panel:\n");
+    fprintf(fp, "       noboringbits    print no boring bits in an assembly\n");
     fprintf(fp, "   telo:\n");
     fprintf(fp, "       telowin         analyse telomere windows in a fasta file\n");
     fprintf(fp, "       telobreaks      find telomere breaks in a fasta file\n");
@@ -78,6 +80,8 @@ int main(int argc, char *argv[])
     else if (strcmp(argv[1], "telofind") == 0) ret = find_telomere_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "sdust") == 0) ret = sdust_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "telostats") == 0) ret = telostats_main(argc - 1, argv + 1);
+    else if (strcmp(argv[1], "noboringbits") == 0) ret = boringbits_main(argc - 1, argv + 1, 0);
+    else if (strcmp(argv[1], "boringbits") == 0) ret = boringbits_main(argc - 1, argv + 1, 1);      /* deprecated in the reference, kept like it */
     else if (strcmp(argv[1], "fa2bed") == 0) ret = assbed_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "nx") == 0) ret = nx_main(argc - 1, argv + 1);
     else if (strcmp(argv[1], "report") == 0) ret = report_main(argc - 1, argv + 1);

@@ -222,6 +222,42 @@ void corn_gpu_ingest_free(corn_ingest_t *ing);
 int  corn_gpu_host_register(void *p, uint64_t bytes);
 void corn_gpu_host_unregister(void *p);
 
+/* ---- depth windows: replaces get_regs() and the selection loops of print_fun_bits() / print_boring_bits(),
+ *      src/boringbits_main.c:315-372,425-485 (`cornetto noboringbits`, `boringbits`) ---------------------------
+ * depth / mq_depth: one uint16 per base (get_depths(), :179-293), contigs concatenated; offset[c] = first element of
+ * contig c.  Windows of window_size every window_inc bases, the last ones clipped to the contig (:340-347); per window
+ * the integer means of both arrays (C division, :357-358).  A window is returned when the reference prints it:
+ *   boring == 0  contigs of at least min_ctg_len:  depth < thresh_low_depth || depth > thresh_high_depth ||
+ *                mq_depth / (double)depth < low_mq_cov_thresh                                   (:436-441)
+ *   boring != 0  contigs longer than min_ctg_len, st > edge_len && end < length - edge_len, and none of the above  (:468-481)
+ * in (contig, start) order.  thresh_*_depth are round(factor * mean depth), computed by the caller as :524-525 does. */
+typedef struct corn_depth_batch {
+    const uint16_t *depth, *mq_depth;
+    const uint64_t *offset;     /* [n_ctg] */
+    const uint32_t *length;     /* [n_ctg], 1 .. 2^31-1 */
+    uint32_t        n_ctg;
+    uint64_t        n_total;    /* elements in depth / mq_depth */
+} corn_depth_batch_t;
+
+typedef struct corn_depth_params {
+    int   window_size, window_inc;              /* both >= 1 */
+    int   thresh_low_depth, thresh_high_depth;
+    float low_mq_cov_thresh;
+    int   edge_len, min_ctg_len;
+    int   boring;
+} corn_depth_params_t;
+
+typedef struct corn_depth_window { uint32_t ctg, st, end; int32_t depth, mq_depth; } corn_depth_window_t;
+
+typedef struct corn_depth_windows {
+    corn_depth_window_t *win;
+    uint64_t             n_win;
+    void                *_owner;
+} corn_depth_windows_t;
+
+int  corn_gpu_depthwin(corn_ctx_t *ctx, const corn_depth_batch_t *batch, const corn_depth_params_t *params, corn_depth_windows_t *out);
+void corn_gpu_depth_windows_free(corn_depth_windows_t *w);
+
 /* ---- several GPUs: record sharding (csrc/shard.cu; host arithmetic only, usable without a device) ----------
  * The reference is one thread in one address space (records scanned and printed in file order,
  * src/find_telomere.c:101-105).  Here the unit of distribution is the record: no scan looks across a record

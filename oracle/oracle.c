@@ -608,3 +608,84 @@ int orc_fa2bed_file(const char *path, FILE *out)
     orc_free_recs(recs, n);
     return 0;
 }
+
+
+/* ========================================================================================
+ * noboringbits / boringbits -- follows get_depths() src/boringbits_main.c:179-293, get_regs() :315-372,
+ * print_fun_bits() :425-446, print_boring_bits() :465-485, the_boring_bits() :487-539.
+ * ====================================================================================== */
+void orc_bits_defaults(orc_bits_opt_t *o)
+{   /* init_optp(), :543-559 */
+    o->window_size = 2500; o->window_inc = 50;
+    o->low_cov_thresh = 0.4f; o->high_cov_thresh = 2.5f; o->low_mq_cov_thresh = 0.4f;
+    o->min_ctg_len = 1000000; o->edge_len = 100000; o->boring = 1;
+}
+
+typedef struct { char *name; int len, cap; uint16_t *d, *q; } bits_ctg_t;
+
+int orc_bits_files(const char *cov_total, const char *cov_mq, const orc_bits_opt_t *o, FILE *out, FILE *err)
+{
+    FILE *f1 = fopen(cov_total, "r"), *f2 = fopen(cov_mq, "r");
+    if (!f1 || !f2) { if (err) fprintf(err, "cannot open input\n"); if (f1) fclose(f1); if (f2) fclose(f2); return 1; }
+    bits_ctg_t *c = NULL;
+    int n = 0, m = 0, rc = 0;
+    char b1[10000], b2[10000], prev[10000] = "";
+    int st1, st2, e1, e2, d1, d2, ret, prev_pos = 0;
+    double tot_len = 0, tot_d = 0, tot_q = 0;
+    for (;;) {                                                   /* :201-279 */
+        if ((ret = fscanf(f1, "%s\t%d\t%d\t%d\n", b1, &st1, &e1, &d1)) == EOF) break;
+        if (ret != 4) { if (err) fprintf(err, "The depth files should have 4 columns. Had %d.\n", ret); rc = 1; break; }
+        if ((ret = fscanf(f2, "%s\t%d\t%d\t%d\n", b2, &st2, &e2, &d2)) == EOF) { if (err) fprintf(err, "The two files are not in the same order\n"); rc = 1; break; }
+        if (ret != 4) { if (err) fprintf(err, "The depth files should have 4 columns. Had %d.\n", ret); rc = 1; break; }
+        if (strcmp(b1, b2) != 0 || st1 != st2 || e1 != e2) { if (err) fprintf(err, "The two files are not in the same order\n"); rc = 1; break; }
+        if (strcmp(b1, prev) != 0) {
+            strcpy(prev, b1);
+            if (n == m) { m = m ? m * 2 : 4; c = (bits_ctg_t *)realloc(c, (size_t)m * sizeof *c); }
+            c[n].name = strdup(b1); c[n].len = 0; c[n].cap = 100;
+            c[n].d = (uint16_t *)calloc(100, 2); c[n].q = (uint16_t *)calloc(100, 2);
+            ++n;
+            prev_pos = 0;                                        /* (the first line of a contig is not checked against 0) */
+        } else {
+            if (prev_pos + 1 != st1) { if (err) fprintf(err, "The depth files should be incremantal at one base resolution. Found %d to %d\n", prev_pos, st1); rc = 1; break; }
+            ++prev_pos;
+        }
+        if (st1 + 1 != e1) { if (err) fprintf(err, "The depth files should have end=start+1. Found %d to %d\n", st1, e1); rc = 1; break; }
+        if (d1 > 65535) d1 = 65535;                              /* (+ a WARNING on stderr) */
+        if (d2 > 65535) d2 = 65535;
+        bits_ctg_t *x = &c[n - 1];
+        if (x->len == x->cap) { x->cap *= 2; x->d = (uint16_t *)realloc(x->d, (size_t)x->cap * 2); x->q = (uint16_t *)realloc(x->q, (size_t)x->cap * 2); }
+        x->d[x->len] = (uint16_t)d1; x->q[x->len] = (uint16_t)d2; ++x->len;   /* (a negative depth wraps, as in the reference's store) */
+        tot_d += d1; tot_q += d2; tot_len++;
+    }
+    fclose(f1); fclose(f2);
+    if (!rc) {
+        const int mean_depth = (int)round(tot_d / tot_len);
+        const int w = o->window_size, inc = o->window_inc;
+        const int lo = (int)round(o->low_cov_thresh * mean_depth), hi = (int)round(o->high_cov_thresh * mean_depth);    /* :524-525 */
+        for (int i = 0; i < n; ++i) {
+            const bits_ctg_t *x = &c[i];
+            const int length = x->len;
+            int n_reg = (length - w + inc - 1) / inc + 1;        /* :331-332 */
+            if (n_reg < 1) n_reg = 1;
+            if (!o->boring) {                                    /* print_fun_bits, :425-446 */
+                if (length < o->min_ctg_len) { fprintf(out, "%s\t%d\t%d\t.\t.\n", x->name, 0, o->min_ctg_len); continue; }
+                fprintf(out, "%s\t%d\t%d\t.\t.\n", x->name, 0, o->edge_len);
+                fprintf(out, "%s\t%d\t%d\t.\t.\n", x->name, length - o->edge_len, length);
+            } else if (!(length > o->min_ctg_len)) continue;     /* print_boring_bits, :468 */
+            for (int j = 0; j < n_reg; ++j) {                    /* get_regs, :340-363 */
+                const int st = j * inc;
+                int end = st + w;
+                if (end > length) end = length;
+                int depth = 0, mq = 0;
+                for (int k = st; k < end; ++k) { depth += x->d[k]; mq += x->q[k]; }
+                depth /= (end - st); mq /= (end - st);
+                const int fun = depth < lo || depth > hi || (mq / (double)depth) < o->low_mq_cov_thresh;
+                if (!o->boring) { if (fun) fprintf(out, "%s\t%d\t%d\t%d\t%d\n", x->name, st, end, depth, mq); }
+                else if (st > o->edge_len && end < length - o->edge_len && !fun) fprintf(out, "%s\t%d\t%d\t%d\t%d\n", x->name, st, end, depth, mq);
+            }
+        }
+    }
+    for (int i = 0; i < n; ++i) { free(c[i].name); free(c[i].d); free(c[i].q); }
+    free(c);
+    return rc;
+}

@@ -74,6 +74,17 @@ int    orc_telobreaks_files(const char *lens, const char *sdust, const char *tel
 /* ---- fa2bed (src/assbed.c:97-100) -------------------------------------------------------- */
 int    orc_fa2bed_file(const char *path, FILE *out);
 
+/* ---- noboringbits / boringbits: windowed depth scan, src/boringbits_main.c:179-493 ---------------------- */
+typedef struct {
+    int window_size, window_inc;                 /* -w 2500, -i 50 */
+    float low_cov_thresh, high_cov_thresh, low_mq_cov_thresh;   /* -L 0.4, -H 2.5, -Q 0.4 */
+    int min_ctg_len, edge_len;                   /* -m 1000000, -e 100000 */
+    int boring;                                  /* 1: boringbits, 0: noboringbits */
+} orc_bits_opt_t;
+void orc_bits_defaults(orc_bits_opt_t *o);
+/* 0 ok; 1 = the reference would print an ERROR and exit(EXIT_FAILURE) (message in err, if not NULL) */
+int  orc_bits_files(const char *cov_total, const char *cov_mq, const orc_bits_opt_t *o, FILE *out, FILE *err);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,30 @@ int main(int argc, char **argv)
         if (argc < 3) return 1;
         return orc_fa2bed_file(argv[2], stdout) ? 1 : 0;
     }
+    if (!strcmp(cmd, "noboringbits") || !strcmp(cmd, "boringbits")) {
+        orc_bits_opt_t o;
+        orc_bits_defaults(&o);
+        o.boring = !strcmp(cmd, "boringbits");
+        const char *tot = NULL, *mq = NULL;
+        for (int i = 2; i < argc; ++i) {
+            if (argv[i][0] == '-' && argv[i][1] && i + 1 < argc) {
+                const char *v = argv[++i];
+                switch (argv[i - 1][1]) {
+                case 'q': mq = v; break;
+                case 'w': o.window_size = atoi(v); break;
+                case 'i': o.window_inc = atoi(v); break;
+                case 'L': o.low_cov_thresh = atof(v); break;
+                case 'H': o.high_cov_thresh = atof(v); break;
+                case 'Q': o.low_mq_cov_thresh = atof(v); break;
+                case 'm': o.min_ctg_len = atoi(v); break;
+                case 'e': o.edge_len = atoi(v); break;
+                default: break;
+                }
+            } else if (!tot) tot = argv[i];
+        }
+        if (!tot || !mq) return 1;
+        return orc_bits_files(tot, mq, &o, stdout, stderr);
+    }
     fprintf(stderr, "unknown command %s\n", cmd);
     return 1;
 }

@@ -66,10 +66,20 @@ def main():
             sf = os.path.join(td, name + ".sdust"); open(sf, "wb").write(base64.b64decode(c["sdust"][""]))
             c["telobreaks"] = b64(ref(["telobreaks", lf, sf, tf]))
             out[name] = c
+    # noboringbits / boringbits (src/boringbits_main.c): one pair of bedgraph files, several option sets
+    with tempfile.TemporaryDirectory() as td:
+        named = synth.depth_arrays(1, synth.BITS_LENGTHS)
+        t = os.path.join(td, "cov-total.bg"); open(t, "wb").write(synth.bedgraph_bytes(named, 1))
+        q = os.path.join(td, "cov-mq20.bg"); open(q, "wb").write(synth.bedgraph_bytes(named, 2))
+        bits = {}
+        for cmd in ("noboringbits", "boringbits"):
+            for a in synth.BITS_OPTS:
+                bits[cmd + " " + " ".join(a)] = b64(ref([cmd, t, "-q", q] + a))
+        out["__bits__"] = {"outputs": bits}
     blob = json.dumps(out, sort_keys=True).encode()
     with gzip.GzipFile(os.path.join(HERE, "golden.json.gz"), "wb", mtime=0) as f:
         f.write(blob)
-    n_out = sum(len(base64.b64decode(v)) for c in out.values() for k in ("telofind", "telowin", "sdust") for v in c[k].values())
+    n_out = sum(len(base64.b64decode(v)) for name, c in out.items() if name != "__bits__" for k in ("telofind", "telowin", "sdust") for v in c[k].values())
     print(f"{len(out)} cases, {n_out} bytes of reference output, fixture {os.path.getsize(os.path.join(HERE, 'golden.json.gz'))} bytes")
 
 

@@ -14,7 +14,7 @@ SDUST_WIDE = [["-w", "129"], ["-w", "200"], ["-w", "500", "-t", "30"]]
 SDUST_WIDE_CASES = ("q6_sdust.fa", "sdust_wide.fa")
 
 
-def load():
+def _load_all():
     with gzip.open(_PATH, "rb") as f:
         raw = json.load(f)
 
@@ -23,3 +23,13 @@ def load():
             return {k: dec(v) for k, v in x.items()}
         return base64.b64decode(x)
     return dec(raw)
+
+
+def load():
+    """the sequence cases (everything but the noboringbits fixture)"""
+    return {k: v for k, v in _load_all().items() if k != "__bits__"}
+
+
+def load_bits():
+    """{"noboringbits -m 10000 -e 1000": reference stdout, ...} for synth.depth_arrays(1, synth.BITS_LENGTHS)"""
+    return _load_all()["__bits__"]["outputs"]

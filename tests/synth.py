@@ -127,6 +127,43 @@ def bgzf_bytes(data: bytes, block: int = 65280) -> bytes:
     return b"".join(out)
 
 
+def depth_arrays(seed: int, lengths):
+    """per-contig (depth, mq_depth) integer arrays for noboringbits: Poisson coverage with low / high / zero stretches and
+    stretches of low mapq coverage; one value above 65535 (truncated by the reader, src/boringbits_main.c:252-259)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i, L in enumerate(lengths):
+        d = rng.poisson(30, size=L).astype(np.int64)
+        for _ in range(max(1, L // 4000)):
+            s0, n, k = int(rng.integers(0, L)), int(rng.integers(50, 900)), int(rng.integers(0, 4))
+            seg = d[s0:s0 + n]
+            if k == 0:
+                seg[:] = rng.poisson(5, size=len(seg))
+            elif k == 1:
+                seg[:] = rng.poisson(120, size=len(seg))
+            elif k == 2:
+                seg[:] = 0
+        q = (d * rng.uniform(0.2, 1.0, size=L)).astype(np.int64)
+        for _ in range(max(1, L // 6000)):
+            s0, n = int(rng.integers(0, L)), int(rng.integers(50, 900))
+            q[s0:s0 + n] //= 5
+        if i == 1 and L > 200:
+            d[100], q[100] = 70000, 66000
+        out.append((f"ctg{i + 1}", d, q))
+    return out
+
+
+def bedgraph_bytes(named, which: int) -> bytes:
+    """one line per base: name, pos, pos+1, depth (which = 1) or mq depth (which = 2)"""
+    return "".join("".join(f"{nm}\t{p}\t{p + 1}\t{v}\n" for p, v in enumerate(arr)) for nm, *arrs in named for arr in [arrs[which - 1]]).encode()
+
+
+BITS_OPTS = [[], ["-m", "10000", "-e", "1000"], ["-m", "2000", "-e", "100", "-w", "1000", "-i", "30"],
+             ["-m", "5000", "-e", "500", "-w", "777", "-i", "50", "-L", "0.6", "-H", "1.6", "-Q", "0.6"], ["-m", "2500", "-e", "0", "-w", "50", "-i", "50"],
+             ["-m", "2000", "-e", "10", "-w", "20000", "-i", "7"]]
+BITS_LENGTHS = [30000, 12000, 900, 2500, 2549, 7]
+
+
 def _low_complexity(rng):
     kind = rng.integers(0, 3)
     if kind == 0:

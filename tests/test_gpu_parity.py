@@ -321,6 +321,58 @@ def test_cli_gzip_inputs_through_the_device_parser(tmp_path, oracle_bin):
             assert out == want_s, (name, env)
 
 
+def test_cli_noboringbits_matches_golden(tmp_path):
+    """`cornetto noboringbits` / `boringbits` through the binary against the reference's outputs (golden), every option set."""
+    named = synth.depth_arrays(1, synth.BITS_LENGTHS)
+    t = write(str(tmp_path / "cov-total.bg"), synth.bedgraph_bytes(named, 1))
+    q = write(str(tmp_path / "cov-mq20.bg"), synth.bedgraph_bytes(named, 2))
+    for key, exp in golden_util.load_bits().items():
+        out, err, _ = cornetto(key.split()[:1] + [t, "-q", q] + key.split()[1:])
+        assert out == exp, key
+        assert b"Number of contigs: 6" in err and b"truncated to 65535" in err
+    # argument and input errors as in the reference: usage on stderr, exit 1; files in a different order
+    _, err, rc = cornetto(["noboringbits", t], check=False)
+    assert rc == 1 and err.startswith(b"Usage: cornetto boringbits cov-total.bg -q cov-mq20.bg")
+    out, _, rc = cornetto(["noboringbits", "-h"], check=False)
+    assert rc == 0 and out.startswith(b"Usage: cornetto boringbits")
+    bad = write(str(tmp_path / "bad.bg"), synth.bedgraph_bytes(named[1:], 2))
+    _, err, rc = cornetto(["noboringbits", t, "-q", bad], check=False)
+    assert rc == 1 and b"The two files are not in the same order" in err
+
+
+def test_abi_depthwin(ctx, capi):
+    """corn_gpu_depthwin against a direct numpy restatement of get_regs() + the selection rules: random depths with zeros
+    (division by zero in the mapq ratio), windows that are / are not multiples of the increment, windows spanning
+    thousands of increments (the direct kernel), contigs shorter than a window, many tiles per contig."""
+    rng = np.random.default_rng(77)
+    lens = [200_000, 33_333, 2500, 2499, 51, 1, 1_300_000]
+    d = [rng.poisson(20, size=L).astype(np.uint16) for L in lens]
+    q = [(x * rng.uniform(0, 1, size=len(x))).astype(np.uint16) for x in d]
+    d[0][5000:9000] = 0
+    q[0][5000:7000] = 0
+    d[6][400_000:400_100] = 65535
+    for (w, inc, lo, hi, thr, edge, minlen, boring) in ((2500, 50, 8, 50, 0.4, 1000, 30000, 0), (2500, 50, 8, 50, 0.4, 1000, 30000, 1),
+                                                        (777, 50, 12, 30, 0.6, 0, 0, 0), (100, 7, 15, 25, 0.5, 10, 50, 1), (20000, 7, 10, 40, 0.5, 0, 2000, 0),
+                                                        (50, 50, 19, 21, 0.45, 100, 2500, 0)):
+        got = ctx.depthwin(d, q, w, inc, lo, hi, thr, edge, minlen, boring)
+        want = []
+        for c, (dd, qq) in enumerate(zip(d, q)):
+            L = len(dd)
+            n_reg = max(1, int((L - w + inc - 1) / inc) + 1)          # C division truncates toward zero
+            cd = np.concatenate([[0], np.cumsum(dd, dtype=np.int64)]); cq = np.concatenate([[0], np.cumsum(qq, dtype=np.int64)])
+            st = np.arange(n_reg, dtype=np.int64) * inc
+            en = np.minimum(st + w, L)
+            dep = (cd[en] - cd[st]) // (en - st); mq = (cq[en] - cq[st]) // (en - st)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                fun = (dep < lo) | (dep > hi) | ((mq / dep.astype(np.float64)) < np.float64(np.float32(thr)))
+            sel = (fun & (L >= minlen)) if not boring else ((L > minlen) & (st > edge) & (en < L - edge) & ~fun)
+            for k in np.flatnonzero(sel):
+                want.append((c, int(st[k]), int(en[k]), int(dep[k]), int(mq[k])))
+        assert [tuple(int(x) for x in r) for r in got] == want, (w, inc, boring)
+    with pytest.raises(capi.CornError):
+        ctx.depthwin(d, q, 0, 50)
+
+
 def test_sdust_library_api(capi):
     """sdust() / sdust_buf_init / sdust_core / sdust_buf_destroy with the reference's signatures and ownership rules
     (src/sdust/sdust.h:16-21): l_seq < 0 means strlen, sdust()'s result is free()d by the caller, sdust_core()'s

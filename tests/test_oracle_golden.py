@@ -34,3 +34,18 @@ def test_oracle_matches_golden(oracle_bin, tmp_path):
     assert sum(len(c["sdust"][""]) for c in g.values()) > 1500
     assert sum(len(c["telobreaks"]) for c in g.values()) > 100
     assert sum(len(c["telowin"]["99.9 0.4"]) for c in g.values()) > 500
+
+
+def test_oracle_bits_match_golden(oracle_bin, tmp_path):
+    """noboringbits / boringbits (src/boringbits_main.c): the oracle's restatement against the reference's outputs for
+    several window / threshold / contig-length settings, incl. a window that is not a multiple of the increment, a
+    window longer than every contig and a depth above 65535."""
+    import synth
+    named = synth.depth_arrays(1, synth.BITS_LENGTHS)
+    t = write(str(tmp_path / "cov-total.bg"), synth.bedgraph_bytes(named, 1))
+    q = write(str(tmp_path / "cov-mq20.bg"), synth.bedgraph_bytes(named, 2))
+    want = golden_util.load_bits()
+    assert len(want) == 2 * len(synth.BITS_OPTS) and sum(len(v) for v in want.values()) > 50_000
+    for key, exp in want.items():
+        out, _, _ = run([oracle_bin] + key.split()[:1] + [t, "-q", q] + key.split()[1:])
+        assert out == exp, key
