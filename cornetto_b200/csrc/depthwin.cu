@@ -48,8 +48,8 @@ __device__ __forceinline__ bool selected(const DepthParams &P, int ctg_len, int 
 
 __global__ void __launch_bounds__(DW_THREADS) k_depth_windows(const DepthParams P)
 {
-    extern __shared__ unsigned long long sm[];          // prefix of depth bins | prefix of mq bins, n_bins + 1 entries each
-    __shared__ unsigned long long wsum[2][DW_THREADS / 32];
+    extern __shared__ uint32_t sm[];                    // prefix of depth bins | prefix of mq bins, n_bins + 1 entries each
+    __shared__ uint32_t wsum[2][DW_THREADS / 32];
     const uint32_t tile = blockIdx.x;
     const uint32_t c = corn_upper_bound(P.tile_base, P.n_ctg, tile) - 1;
     const int len = (int)P.ctg_len[c];
@@ -61,15 +61,19 @@ __global__ void __launch_bounds__(DW_THREADS) k_depth_windows(const DepthParams 
     int b1 = (int)j1 - 1 + fw + 1;                       // bins [b0, b1) cover every window of the tile (the partial tail is read directly)
     if (b1 > nb_ctg) b1 = nb_ctg;
     const int n_bins = b1 - b0;
-    unsigned long long *Pd = sm, *Pq = sm + (DW_TILE + DW_MAX_SPAN + 2);
+    // All sums are kept modulo 2^32: the reference accumulates a window in an int (:353-359), so only the low 32 bits
+    // of a sum reach its division, and differences of prefixes modulo 2^32 are those bits.
+    uint32_t *Pd = sm, *Pq = sm + (DW_TILE + DW_MAX_SPAN + 2);
     const uint16_t *d = P.depth + P.ctg_off[c], *q = P.mq + P.ctg_off[c];
 
     // ---- bin sums with coalesced loads.  The tile's bases [lo, hi) are walked by the warps in steps of 256 values: a
     // lane takes 8 consecutive values of each array with one 16-byte load (aligned on the ARRAY, whatever the contig's
-    // offset; values outside [lo, hi) are masked), splits them over the at most two bins they fall into (window_inc >= 8;
-    // smaller increments take one value at a time), and the warp reduces per bin before one lane adds the total to the
-    // bin in shared memory.  (One thread per bin walking its 50 values gave 8 % of the HBM roofline: 32 lanes x 2 bytes
-    // per request, 100 bytes apart.)
+    // offset; values outside [lo, hi) are masked) and splits them over the at most two bins they fall into (window_inc
+    // >= 8; smaller increments take one value at a time).  The part that belongs to the lane's second bin moves one
+    // lane up -- with window_inc >= 8 that lane starts in exactly that bin -- and a segmented scan over the lanes (bin
+    // numbers rise with the lane) leaves each bin's total in the last lane that touches it: one shared-memory add per
+    // bin and warp step.  (One thread per bin walking its 50 values gave 8 % of the HBM roofline -- 32 lanes x 2 bytes
+    // per request, 100 bytes apart; a warp reduction per bin with 64-bit shared atomics 19 %.)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i <= n_bins; i += DW_THREADS) { Pd[i] = 0; Pq[i] = 0; }
     __syncthreads();
@@ -77,43 +81,50 @@ __global__ void __launch_bounds__(DW_THREADS) k_depth_windows(const DepthParams 
         const long long lo = (long long)b0 * P.inc, hi = min((long long)len, (long long)b1 * P.inc);
         const unsigned long long g0 = P.ctg_off[c];                       // element index of the contig's first value
         const long long first = (long long)((g0 + (unsigned long long)lo) & ~7ull) - (long long)g0;   // 8-aligned on the array, may be < lo
+        const uint32_t uinc = (uint32_t)P.inc;
         for (long long base = first + (long long)warp * 256; base < hi; base += (long long)(DW_THREADS / 32) * 256) {
             const long long k0 = base + lane * 8;                          // contig-relative index of this lane's first value
             uint32_t vd[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, vq[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
             if (k0 + 8 > lo && k0 < hi) {
                 const uint4 a = __ldg((const uint4 *)(P.depth + g0 + k0)), e = __ldg((const uint4 *)(P.mq + g0 + k0));
                 const uint32_t wa[4] = { a.x, a.y, a.z, a.w }, we[4] = { e.x, e.y, e.z, e.w };
+                const bool whole = k0 >= lo && k0 + 8 <= hi;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    const bool in = k0 + t >= lo && k0 + t < hi;
+                    const bool in = whole || (k0 + t >= lo && k0 + t < hi);
                     vd[t] = in ? (wa[t >> 1] >> (16 * (t & 1))) & 0xFFFFu : 0u;
                     vq[t] = in ? (we[t >> 1] >> (16 * (t & 1))) & 0xFFFFu : 0u;
                 }
             }
-            // bins of the first and of the last value of this lane (relative to b0); with window_inc >= 8 there is at most one boundary between them
-            const long long kk = k0 < lo ? lo : k0;
-            const int ba = (int)(kk / P.inc) - b0;
-            const long long split = (long long)(ba + b0 + 1) * P.inc;      // first value of the next bin
-            uint32_t sa_d = 0, sb_d = 0, sa_q = 0, sb_q = 0;
             if (P.inc >= 8) {
+                // bin of the lane's first value (relative to b0; contig positions are below 2^31) and how many of the
+                // eight values stay in it
+                const long long kk = k0 < lo ? lo : k0;
+                const int ba = (int)((uint32_t)kk / uinc) - b0;
+                const long long split = (long long)(ba + b0 + 1) * P.inc;  // first value of the next bin
+                const int keep = split - k0 >= 8 ? 8 : (int)(split - k0);
+                uint32_t xd = 0, nd = 0, xq = 0, nq = 0;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) { const bool nx = k0 + t >= split; sa_d += nx ? 0u : vd[t]; sb_d += nx ? vd[t] : 0u; sa_q += nx ? 0u : vq[t]; sb_q += nx ? vq[t] : 0u; }
-                // the warp's 256 values span bins [w_lo, w_hi]: reduce each over the lanes, one shared-memory add per bin
-                const long long wk0 = base < lo ? lo : base, wk1 = (base + 255 < hi - 1 ? base + 255 : hi - 1);
-                if (wk0 <= wk1) {
-                    const int w_lo = (int)(wk0 / P.inc) - b0, w_hi = (int)(wk1 / P.inc) - b0;
-                    for (int bb = w_lo; bb <= w_hi; ++bb) {
-                        uint32_t xd = (ba == bb ? sa_d : 0u) + (ba + 1 == bb ? sb_d : 0u), xq = (ba == bb ? sa_q : 0u) + (ba + 1 == bb ? sb_q : 0u);
-                        xd = corn_warp_sum(xd); xq = corn_warp_sum(xq);
-                        if (lane == 0 && bb >= 0 && bb < n_bins) { atomicAdd(&Pd[bb + 1], (unsigned long long)xd); atomicAdd(&Pq[bb + 1], (unsigned long long)xq); }
-                    }
+                for (int t = 0; t < 8; ++t) { const bool nx = t >= keep; xd += nx ? 0u : vd[t]; nd += nx ? vd[t] : 0u; xq += nx ? 0u : vq[t]; nq += nx ? vq[t] : 0u; }
+                const uint32_t ud = __shfl_up_sync(0xffffffffu, nd, 1), uq = __shfl_up_sync(0xffffffffu, nq, 1);
+                const int prev = __shfl_up_sync(0xffffffffu, ba, 1);
+                if (lane) { xd += ud; xq += uq; }
+                const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != ba);
+                const int dist = lane - (31 - __clz((int)(heads & (0xffffffffu >> (31 - lane)))));   // lanes since the head of my bin
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t yd = __shfl_up_sync(0xffffffffu, xd, o), yq = __shfl_up_sync(0xffffffffu, xq, o);
+                    if (dist >= o) { xd += yd; xq += yq; }
                 }
+                const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+                if (tail && ba >= 0 && ba < n_bins) { atomicAdd(&Pd[ba + 1], xd); atomicAdd(&Pq[ba + 1], xq); }
+                if (lane == 31 && keep < 8 && ba + 1 < n_bins) { atomicAdd(&Pd[ba + 2], nd); atomicAdd(&Pq[ba + 2], nq); }
             } else {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     if (k0 + t >= lo && k0 + t < hi) {
-                        const int bb = (int)((k0 + t) / P.inc) - b0;
-                        atomicAdd(&Pd[bb + 1], (unsigned long long)vd[t]); atomicAdd(&Pq[bb + 1], (unsigned long long)vq[t]);
+                        const int bb = (int)((uint32_t)(k0 + t) / uinc) - b0;
+                        atomicAdd(&Pd[bb + 1], vd[t]); atomicAdd(&Pq[bb + 1], vq[t]);
                     }
                 }
             }
@@ -121,19 +132,18 @@ __global__ void __launch_bounds__(DW_THREADS) k_depth_windows(const DepthParams 
     }
     __syncthreads();
     // inclusive prefix over the bin sums (block scan in rounds of DW_THREADS); Pd[0] = Pq[0] = 0
-    unsigned long long carry_d = 0, carry_q = 0;
+    uint32_t carry_d = 0, carry_q = 0;
     for (int base = 0; base < n_bins; base += DW_THREADS) {
         const int b = base + (int)threadIdx.x;
-        const unsigned long long sd = b < n_bins ? Pd[b + 1] : 0ull, sq = b < n_bins ? Pq[b + 1] : 0ull;
-        unsigned long long xd = sd, xq = sq;
+        uint32_t xd = b < n_bins ? Pd[b + 1] : 0u, xq = b < n_bins ? Pq[b + 1] : 0u;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long yd = __shfl_up_sync(0xffffffffu, xd, o), yq = __shfl_up_sync(0xffffffffu, xq, o);
+            const uint32_t yd = __shfl_up_sync(0xffffffffu, xd, o), yq = __shfl_up_sync(0xffffffffu, xq, o);
             if (lane >= o) { xd += yd; xq += yq; }
         }
         if (lane == 31) { wsum[0][warp] = xd; wsum[1][warp] = xq; }
         __syncthreads();
-        unsigned long long od = carry_d, oq = carry_q, td = 0, tq = 0;
+        uint32_t od = carry_d, oq = carry_q, td = 0, tq = 0;
         for (int w2 = 0; w2 < DW_THREADS / 32; ++w2) { if (w2 < warp) { od += wsum[0][w2]; oq += wsum[1][w2]; } td += wsum[0][w2]; tq += wsum[1][w2]; }
         if (b < n_bins) { Pd[b + 1] = od + xd; Pq[b + 1] = oq + xq; }
         carry_d += td; carry_q += tq;
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(DW_THREADS) k_depth_windows(const DepthParams 
     for (uint32_t j = j0 + threadIdx.x; j < j1; j += DW_THREADS) {
         const int st = (int)j * P.inc;
         int end = st + P.w;
-        unsigned long long sd, sq;
+        uint32_t sd, sq;
         const int r = (int)(j - j0);                     // first bin of the window, relative to b0
         if (end >= len) {                                // clipped window: all bins to the end of the contig
             end = len;
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(DW_THREADS) k_depth_windows(const DepthParams 
             for (int k = st + fw * P.inc; k < end; ++k) { sd += __ldg(d + k); sq += __ldg(q + k); }
         }
         // the reference accumulates in int: same low 32 bits, then C division by the window length (:357-358)
-        const int depth = (int)(uint32_t)sd / (end - st), mq = (int)(uint32_t)sq / (end - st);
+        const int depth = (int)sd / (end - st), mq = (int)sq / (end - st);
         P.out_depth[wb + j] = depth; P.out_mq[wb + j] = mq;
         P.flag[wb + j] = selected(P, len, st, end, depth, mq) ? 1u : 0u;
     }
@@ -254,7 +264,7 @@ extern "C" int corn_gpu_depthwin(corn_ctx_t *ctx, const corn_depth_batch_t *b, c
     P.flag = d_flag; P.out_depth = d_od; P.out_mq = d_oq;
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     if ((prm->window_size + prm->window_inc - 1) / prm->window_inc + 1 <= DW_MAX_SPAN) {
-        const size_t smem = 2 * (size_t)(DW_TILE + DW_MAX_SPAN + 2) * sizeof(unsigned long long);
+        const size_t smem = 2 * (size_t)(DW_TILE + DW_MAX_SPAN + 2) * sizeof(uint32_t);
         CORN_CUDA(ctx, cudaFuncSetAttribute(k_depth_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_depth_windows<<<(unsigned)tiles, DW_THREADS, smem, st>>>(P);
     } else {
