@@ -38,6 +38,19 @@ __device__ __forceinline__ uint32_t nreg_of(int length, int w, int inc)
     return n < 1 ? 1u : (uint32_t)n;
 }
 
+// mask of the 16-bit halves of word i (values 2i and 2i + 1 of a lane's eight) whose value index is below cnt
+__device__ __forceinline__ uint32_t below_mask(int cnt, int i)
+{
+    const int r = cnt - 2 * i;
+    return r >= 2 ? 0xFFFFFFFFu : (r == 1 ? 0x0000FFFFu : 0u);
+}
+
+// sum of the eight uint16 values packed in four words (IDP.2A: both halves of a word times 1, accumulated)
+__device__ __forceinline__ uint32_t sum16x8(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
+{
+    return __dp2a_lo(w3, 0x0101u, __dp2a_lo(w2, 0x0101u, __dp2a_lo(w1, 0x0101u, __dp2a_lo(w0, 0x0101u, 0u))));
+}
+
 // is window [st, end) with these means printed?  (:436-441 for noboringbits, :474-481 for boringbits)
 __device__ __forceinline__ bool selected(const DepthParams &P, int ctg_len, int st, int end, int depth, int mq)
 {
@@ -46,7 +59,7 @@ __device__ __forceinline__ bool selected(const DepthParams &P, int ctg_len, int 
     return ctg_len > P.min_ctg_len && st > P.edge_len && end < ctg_len - P.edge_len && !fun;
 }
 
-__global__ void __launch_bounds__(DW_THREADS) k_depth_windows(const DepthParams P)
+__global__ void __launch_bounds__(DW_THREADS, 6) k_depth_windows(const DepthParams P)
 {
     extern __shared__ uint32_t sm[];                    // prefix of depth bins | prefix of mq bins, n_bins + 1 entries each
     __shared__ uint32_t wsum[2][DW_THREADS / 32];
@@ -80,32 +93,39 @@ __global__ void __launch_bounds__(DW_THREADS) k_depth_windows(const DepthParams 
     {
         const long long lo = (long long)b0 * P.inc, hi = min((long long)len, (long long)b1 * P.inc);
         const unsigned long long g0 = P.ctg_off[c];                       // element index of the contig's first value
-        const long long first = (long long)((g0 + (unsigned long long)lo) & ~7ull) - (long long)g0;   // 8-aligned on the array, may be < lo
-        const uint32_t uinc = (uint32_t)P.inc;
-        for (long long base = first + (long long)warp * 256; base < hi; base += (long long)(DW_THREADS / 32) * 256) {
-            const long long k0 = base + lane * 8;                          // contig-relative index of this lane's first value
-            uint32_t vd[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, vq[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-            if (k0 + 8 > lo && k0 < hi) {
-                const uint4 a = __ldg((const uint4 *)(P.depth + g0 + k0)), e = __ldg((const uint4 *)(P.mq + g0 + k0));
-                const uint32_t wa[4] = { a.x, a.y, a.z, a.w }, we[4] = { e.x, e.y, e.z, e.w };
-                const bool whole = k0 >= lo && k0 + 8 <= hi;
+        const unsigned long long first = (g0 + (unsigned long long)lo) & ~7ull;   // 8-aligned on the array, may lie before lo
+        // 32-bit positions u relative to `first`: the tile's values are [lo_u, hi_u), value u lies in bin (u - lo_u) / inc
+        const uint32_t lo_u = (uint32_t)(g0 + (unsigned long long)lo - first), hi_u = lo_u + (uint32_t)(hi - lo);
+        const uint16_t *pd = P.depth + first, *pq = P.mq + first;
+        const uint32_t uinc = (uint32_t)P.inc, stride = (DW_THREADS / 32) * 256;
+        // the loads of the warp's next step are issued before this step's values are reduced
+        uint4 a = make_uint4(0, 0, 0, 0), e = a, a_nx = a, e_nx = a;
+        uint32_t u0 = (uint32_t)warp * 256 + (uint32_t)lane * 8;          // this lane's first value
+        if (u0 + 8 > lo_u && u0 < hi_u) { a = __ldg((const uint4 *)(pd + u0)); e = __ldg((const uint4 *)(pq + u0)); }
+        for (; u0 - (uint32_t)lane * 8 < hi_u; u0 += stride, a = a_nx, e = e_nx) {
+            { const uint32_t k = u0 + stride; if (k + 8 > lo_u && k < hi_u) { a_nx = __ldg((const uint4 *)(pd + k)); e_nx = __ldg((const uint4 *)(pq + k)); } }
+            // the eight values of each array stay packed two to a word; masks blank what lies outside [lo_u, hi_u)
+            const bool has = u0 + 8 > lo_u && u0 < hi_u;
+            uint32_t wa[4] = { has ? a.x : 0u, has ? a.y : 0u, has ? a.z : 0u, has ? a.w : 0u };
+            uint32_t we[4] = { has ? e.x : 0u, has ? e.y : 0u, has ? e.z : 0u, has ? e.w : 0u };
+            if (has && !(u0 >= lo_u && u0 + 8 <= hi_u)) {
+                const int t_lo = lo_u > u0 ? (int)(lo_u - u0) : 0, t_hi = hi_u - u0 >= 8u ? 8 : (int)(hi_u - u0);
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const bool in = whole || (k0 + t >= lo && k0 + t < hi);
-                    vd[t] = in ? (wa[t >> 1] >> (16 * (t & 1))) & 0xFFFFu : 0u;
-                    vq[t] = in ? (we[t >> 1] >> (16 * (t & 1))) & 0xFFFFu : 0u;
-                }
+                for (int i = 0; i < 4; ++i) { const uint32_t m = below_mask(t_hi, i) & ~below_mask(t_lo, i); wa[i] &= m; we[i] &= m; }
             }
             if (P.inc >= 8) {
-                // bin of the lane's first value (relative to b0; contig positions are below 2^31) and how many of the
-                // eight values stay in it
-                const long long kk = k0 < lo ? lo : k0;
-                const int ba = (int)((uint32_t)kk / uinc) - b0;
-                const long long split = (long long)(ba + b0 + 1) * P.inc;  // first value of the next bin
-                const int keep = split - k0 >= 8 ? 8 : (int)(split - k0);
-                uint32_t xd = 0, nd = 0, xq = 0, nq = 0;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) { const bool nx = t >= keep; xd += nx ? 0u : vd[t]; nd += nx ? vd[t] : 0u; xq += nx ? 0u : vq[t]; nq += nx ? vq[t] : 0u; }
+                // bin of the lane's first value and how many of the eight values stay in it
+                const uint32_t uu = u0 < lo_u ? lo_u : u0;
+                const int ba = (int)((uu - lo_u) / uinc);
+                const uint32_t split = lo_u + ((uint32_t)ba + 1u) * uinc;  // first value of the next bin (> uu)
+                const int keep = split - u0 >= 8u ? 8 : (int)(split - u0);
+                const uint32_t td = sum16x8(wa[0], wa[1], wa[2], wa[3]), tq = sum16x8(we[0], we[1], we[2], we[3]);
+                uint32_t xd = td, xq = tq;
+                if (keep < 8) {
+                    xd = sum16x8(wa[0] & below_mask(keep, 0), wa[1] & below_mask(keep, 1), wa[2] & below_mask(keep, 2), wa[3] & below_mask(keep, 3));
+                    xq = sum16x8(we[0] & below_mask(keep, 0), we[1] & below_mask(keep, 1), we[2] & below_mask(keep, 2), we[3] & below_mask(keep, 3));
+                }
+                const uint32_t nd = td - xd, nq = tq - xq;                 // what belongs to the next bin
                 const uint32_t ud = __shfl_up_sync(0xffffffffu, nd, 1), uq = __shfl_up_sync(0xffffffffu, nq, 1);
                 const int prev = __shfl_up_sync(0xffffffffu, ba, 1);
                 if (lane) { xd += ud; xq += uq; }
@@ -117,14 +137,14 @@ __global__ void __launch_bounds__(DW_THREADS) k_depth_windows(const DepthParams 
                     if (dist >= o) { xd += yd; xq += yq; }
                 }
                 const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-                if (tail && ba >= 0 && ba < n_bins) { atomicAdd(&Pd[ba + 1], xd); atomicAdd(&Pq[ba + 1], xq); }
+                if (tail && ba < n_bins) { atomicAdd(&Pd[ba + 1], xd); atomicAdd(&Pq[ba + 1], xq); }
                 if (lane == 31 && keep < 8 && ba + 1 < n_bins) { atomicAdd(&Pd[ba + 2], nd); atomicAdd(&Pq[ba + 2], nq); }
             } else {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    if (k0 + t >= lo && k0 + t < hi) {
-                        const int bb = (int)((uint32_t)(k0 + t) / uinc) - b0;
-                        atomicAdd(&Pd[bb + 1], vd[t]); atomicAdd(&Pq[bb + 1], vq[t]);
+                    if (u0 + t >= lo_u && u0 + t < hi_u) {
+                        const int bb = (int)((u0 + t - lo_u) / uinc);
+                        atomicAdd(&Pd[bb + 1], (wa[t >> 1] >> (16 * (t & 1))) & 0xFFFFu); atomicAdd(&Pq[bb + 1], (we[t >> 1] >> (16 * (t & 1))) & 0xFFFFu);
                     }
                 }
             }
