@@ -45,12 +45,6 @@ __device__ __forceinline__ uint32_t below_mask(int cnt, int i)
     return r >= 2 ? 0xFFFFFFFFu : (r == 1 ? 0x0000FFFFu : 0u);
 }
 
-// sum of the eight uint16 values packed in four words (IDP.2A: both halves of a word times 1, accumulated)
-__device__ __forceinline__ uint32_t sum16x8(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
-{
-    return __dp2a_lo(w3, 0x0101u, __dp2a_lo(w2, 0x0101u, __dp2a_lo(w1, 0x0101u, __dp2a_lo(w0, 0x0101u, 0u))));
-}
-
 // is window [st, end) with these means printed?  (:436-441 for noboringbits, :474-481 for boringbits)
 __device__ __forceinline__ bool selected(const DepthParams &P, int ctg_len, int st, int end, int depth, int mq)
 {
@@ -59,7 +53,8 @@ __device__ __forceinline__ bool selected(const DepthParams &P, int ctg_len, int 
     return ctg_len > P.min_ctg_len && st > P.edge_len && end < ctg_len - P.edge_len && !fun;
 }
 
-__global__ void __launch_bounds__(DW_THREADS, 6) k_depth_windows(const DepthParams P)
+template <int VPL>
+__global__ void __launch_bounds__(DW_THREADS, VPL == 8 ? 6 : 4) k_depth_windows(const DepthParams P)
 {
     extern __shared__ uint32_t sm[];                    // prefix of depth bins | prefix of mq bins, n_bins + 1 entries each
     __shared__ uint32_t wsum[2][DW_THREADS / 32];
@@ -79,51 +74,77 @@ __global__ void __launch_bounds__(DW_THREADS, 6) k_depth_windows(const DepthPara
     uint32_t *Pd = sm, *Pq = sm + (DW_TILE + DW_MAX_SPAN + 2);
     const uint16_t *d = P.depth + P.ctg_off[c], *q = P.mq + P.ctg_off[c];
 
-    // ---- bin sums with coalesced loads.  The tile's bases [lo, hi) are walked by the warps in steps of 256 values: a
-    // lane takes 8 consecutive values of each array with one 16-byte load (aligned on the ARRAY, whatever the contig's
-    // offset; values outside [lo, hi) are masked) and splits them over the at most two bins they fall into (window_inc
-    // >= 8; smaller increments take one value at a time).  The part that belongs to the lane's second bin moves one
-    // lane up -- with window_inc >= 8 that lane starts in exactly that bin -- and a segmented scan over the lanes (bin
-    // numbers rise with the lane) leaves each bin's total in the last lane that touches it: one shared-memory add per
-    // bin and warp step.  (One thread per bin walking its 50 values gave 8 % of the HBM roofline -- 32 lanes x 2 bytes
-    // per request, 100 bytes apart; a warp reduction per bin with 64-bit shared atomics 19 %.)
+    // ---- bin sums with coalesced loads.  The tile's bases [lo, hi) are walked by the warps in steps of 32 x VPL values:
+    // a lane takes VPL (8 or 16) consecutive values of each array with 16-byte loads (aligned on the ARRAY, whatever the
+    // contig's offset; values outside [lo, hi) are masked) and splits them over the at most two bins they fall into
+    // (window_inc >= VPL; increments below 8 take one value at a time).  The part that belongs to the lane's second bin
+    // moves one lane up -- with window_inc >= VPL that lane starts in exactly that bin -- and a segmented scan over the
+    // lanes (bin numbers rise with the lane) leaves each bin's total in the last lane that touches it: one
+    // shared-memory add per bin and warp step.  The kernel is bound by instruction issue, not by the loads, which is
+    // why the per-step work (bin number, scan, adds) is spread over 16 values where the increment allows.
+    // (One thread per bin walking its 50 values gave 8 % of the HBM roofline -- 32 lanes x 2 bytes per request, 100
+    // bytes apart; a warp reduction per bin with 64-bit shared atomics 19 %; 8 values per lane 54 %.)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i <= n_bins; i += DW_THREADS) { Pd[i] = 0; Pq[i] = 0; }
     __syncthreads();
     {
+        constexpr int NW = VPL / 2, NL = VPL / 8;                         // words / 16-byte loads per lane and array
         const long long lo = (long long)b0 * P.inc, hi = min((long long)len, (long long)b1 * P.inc);
         const unsigned long long g0 = P.ctg_off[c];                       // element index of the contig's first value
         const unsigned long long first = (g0 + (unsigned long long)lo) & ~7ull;   // 8-aligned on the array, may lie before lo
         // 32-bit positions u relative to `first`: the tile's values are [lo_u, hi_u), value u lies in bin (u - lo_u) / inc
         const uint32_t lo_u = (uint32_t)(g0 + (unsigned long long)lo - first), hi_u = lo_u + (uint32_t)(hi - lo);
         const uint16_t *pd = P.depth + first, *pq = P.mq + first;
-        const uint32_t uinc = (uint32_t)P.inc, stride = (DW_THREADS / 32) * 256;
-        // the loads of the warp's next step are issued before this step's values are reduced
-        uint4 a = make_uint4(0, 0, 0, 0), e = a, a_nx = a, e_nx = a;
-        uint32_t u0 = (uint32_t)warp * 256 + (uint32_t)lane * 8;          // this lane's first value
-        if (u0 + 8 > lo_u && u0 < hi_u) { a = __ldg((const uint4 *)(pd + u0)); e = __ldg((const uint4 *)(pq + u0)); }
-        for (; u0 - (uint32_t)lane * 8 < hi_u; u0 += stride, a = a_nx, e = e_nx) {
-            { const uint32_t k = u0 + stride; if (k + 8 > lo_u && k < hi_u) { a_nx = __ldg((const uint4 *)(pd + k)); e_nx = __ldg((const uint4 *)(pq + k)); } }
-            // the eight values of each array stay packed two to a word; masks blank what lies outside [lo_u, hi_u)
-            const bool has = u0 + 8 > lo_u && u0 < hi_u;
-            uint32_t wa[4] = { has ? a.x : 0u, has ? a.y : 0u, has ? a.z : 0u, has ? a.w : 0u };
-            uint32_t we[4] = { has ? e.x : 0u, has ? e.y : 0u, has ? e.z : 0u, has ? e.w : 0u };
-            if (has && !(u0 >= lo_u && u0 + 8 <= hi_u)) {
-                const int t_lo = lo_u > u0 ? (int)(lo_u - u0) : 0, t_hi = hi_u - u0 >= 8u ? 8 : (int)(hi_u - u0);
+        const uint32_t uinc = (uint32_t)P.inc, stride = (DW_THREADS / 32) * 32 * VPL;
+        const uint32_t inc_magic = 0xFFFFFFFFu / uinc;                    // x / inc = umulhi(x, magic) or one more
+        const int max_seg = (P.inc - 1 + VPL - 1) / VPL + 1;              // lanes one bin can spread over
+        // the loads of the warp's next step are issued before this step's values are reduced; a 16-byte piece that lies
+        // wholly outside [lo_u, hi_u) is not read and stays zero
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        uint4 a[NL], e[NL], a_nx[NL], e_nx[NL];
+        uint32_t u0 = (uint32_t)warp * 32 * VPL + (uint32_t)lane * VPL;   // this lane's first value
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { const uint32_t m = below_mask(t_hi, i) & ~below_mask(t_lo, i); wa[i] &= m; we[i] &= m; }
+        for (int l = 0; l < NL; ++l) {
+            const uint32_t k = u0 + 8 * l;
+            a[l] = zero4; e[l] = zero4;
+            if (k + 8 > lo_u && k < hi_u) { a[l] = __ldg((const uint4 *)(pd + k)); e[l] = __ldg((const uint4 *)(pq + k)); }
+        }
+#pragma unroll 2
+        for (; u0 - (uint32_t)lane * VPL < hi_u; u0 += stride) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                const uint32_t k = u0 + stride + 8 * l;
+                a_nx[l] = zero4; e_nx[l] = zero4;
+                if (k + 8 > lo_u && k < hi_u) { a_nx[l] = __ldg((const uint4 *)(pd + k)); e_nx[l] = __ldg((const uint4 *)(pq + k)); }
             }
-            if (P.inc >= 8) {
-                // bin of the lane's first value and how many of the eight values stay in it
+            // the values of each array stay packed two to a word; masks blank what lies outside [lo_u, hi_u)
+            uint32_t wa[NW], we[NW];
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                wa[4 * l] = a[l].x; wa[4 * l + 1] = a[l].y; wa[4 * l + 2] = a[l].z; wa[4 * l + 3] = a[l].w;
+                we[4 * l] = e[l].x; we[4 * l + 1] = e[l].y; we[4 * l + 2] = e[l].z; we[4 * l + 3] = e[l].w;
+            }
+            if (u0 + VPL > lo_u && u0 < hi_u && !(u0 >= lo_u && u0 + VPL <= hi_u)) {
+                const int t_lo = lo_u > u0 ? (int)(lo_u - u0) : 0, t_hi = hi_u - u0 >= (uint32_t)VPL ? VPL : (int)(hi_u - u0);
+#pragma unroll
+                for (int i = 0; i < NW; ++i) { const uint32_t m = below_mask(t_hi, i) & ~below_mask(t_lo, i); wa[i] &= m; we[i] &= m; }
+            }
+            if (VPL > 8 || P.inc >= 8) {
+                // bin of the lane's first value and how many of its values stay in it
                 const uint32_t uu = u0 < lo_u ? lo_u : u0;
-                const int ba = (int)((uu - lo_u) / uinc);
+                uint32_t qb = __umulhi(uu - lo_u, inc_magic);
+                if (uu - lo_u - qb * uinc >= uinc) ++qb;
+                const int ba = (int)qb;
                 const uint32_t split = lo_u + ((uint32_t)ba + 1u) * uinc;  // first value of the next bin (> uu)
-                const int keep = split - u0 >= 8u ? 8 : (int)(split - u0);
-                const uint32_t td = sum16x8(wa[0], wa[1], wa[2], wa[3]), tq = sum16x8(we[0], we[1], we[2], we[3]);
+                const int keep = split - u0 >= (uint32_t)VPL ? VPL : (int)(split - u0);
+                uint32_t td = 0, tq = 0;
+#pragma unroll
+                for (int i = 0; i < NW; ++i) { td = __dp2a_lo(wa[i], 0x0101u, td); tq = __dp2a_lo(we[i], 0x0101u, tq); }   // IDP.2A: both halves of a word times 1
                 uint32_t xd = td, xq = tq;
-                if (keep < 8) {
-                    xd = sum16x8(wa[0] & below_mask(keep, 0), wa[1] & below_mask(keep, 1), wa[2] & below_mask(keep, 2), wa[3] & below_mask(keep, 3));
-                    xq = sum16x8(we[0] & below_mask(keep, 0), we[1] & below_mask(keep, 1), we[2] & below_mask(keep, 2), we[3] & below_mask(keep, 3));
+                if (keep < VPL) {
+                    xd = 0; xq = 0;
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) { const uint32_t m = below_mask(keep, i); xd = __dp2a_lo(wa[i] & m, 0x0101u, xd); xq = __dp2a_lo(we[i] & m, 0x0101u, xq); }
                 }
                 const uint32_t nd = td - xd, nq = tq - xq;                 // what belongs to the next bin
                 const uint32_t ud = __shfl_up_sync(0xffffffffu, nd, 1), uq = __shfl_up_sync(0xffffffffu, nq, 1);
@@ -133,21 +154,25 @@ __global__ void __launch_bounds__(DW_THREADS, 6) k_depth_windows(const DepthPara
                 const int dist = lane - (31 - __clz((int)(heads & (0xffffffffu >> (31 - lane)))));   // lanes since the head of my bin
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t yd = __shfl_up_sync(0xffffffffu, xd, o), yq = __shfl_up_sync(0xffffffffu, xq, o);
-                    if (dist >= o) { xd += yd; xq += yq; }
+                    if (o < max_seg) {                                     // (same for the whole grid)
+                        const uint32_t yd = __shfl_up_sync(0xffffffffu, xd, o), yq = __shfl_up_sync(0xffffffffu, xq, o);
+                        if (dist >= o) { xd += yd; xq += yq; }
+                    }
                 }
                 const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
                 if (tail && ba < n_bins) { atomicAdd(&Pd[ba + 1], xd); atomicAdd(&Pq[ba + 1], xq); }
-                if (lane == 31 && keep < 8 && ba + 1 < n_bins) { atomicAdd(&Pd[ba + 2], nd); atomicAdd(&Pq[ba + 2], nq); }
+                if (lane == 31 && keep < VPL && ba + 1 < n_bins) { atomicAdd(&Pd[ba + 2], nd); atomicAdd(&Pq[ba + 2], nq); }
             } else {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
+                for (int t = 0; t < VPL; ++t) {
                     if (u0 + t >= lo_u && u0 + t < hi_u) {
                         const int bb = (int)((u0 + t - lo_u) / uinc);
                         atomicAdd(&Pd[bb + 1], (wa[t >> 1] >> (16 * (t & 1))) & 0xFFFFu); atomicAdd(&Pq[bb + 1], (we[t >> 1] >> (16 * (t & 1))) & 0xFFFFu);
                     }
                 }
             }
+#pragma unroll
+            for (int l = 0; l < NL; ++l) { a[l] = a_nx[l]; e[l] = e_nx[l]; }
         }
     }
     __syncthreads();
@@ -285,8 +310,8 @@ extern "C" int corn_gpu_depthwin(corn_ctx_t *ctx, const corn_depth_batch_t *b, c
     CORN_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     if ((prm->window_size + prm->window_inc - 1) / prm->window_inc + 1 <= DW_MAX_SPAN) {
         const size_t smem = 2 * (size_t)(DW_TILE + DW_MAX_SPAN + 2) * sizeof(uint32_t);
-        CORN_CUDA(ctx, cudaFuncSetAttribute(k_depth_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_depth_windows<<<(unsigned)tiles, DW_THREADS, smem, st>>>(P);
+        if (prm->window_inc >= 16) k_depth_windows<16><<<(unsigned)tiles, DW_THREADS, smem, st>>>(P);
+        else k_depth_windows<8><<<(unsigned)tiles, DW_THREADS, smem, st>>>(P);
     } else {
         k_depth_windows_direct<<<(n_win + 255) / 256, 256, 0, st>>>(P, n_win);
     }

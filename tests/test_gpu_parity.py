@@ -353,7 +353,8 @@ def test_abi_depthwin(ctx, capi):
     d[6][400_000:400_100] = 65535
     for (w, inc, lo, hi, thr, edge, minlen, boring) in ((2500, 50, 8, 50, 0.4, 1000, 30000, 0), (2500, 50, 8, 50, 0.4, 1000, 30000, 1),
                                                         (777, 50, 12, 30, 0.6, 0, 0, 0), (100, 7, 15, 25, 0.5, 10, 50, 1), (20000, 7, 10, 40, 0.5, 0, 2000, 0),
-                                                        (50, 50, 19, 21, 0.45, 100, 2500, 0), (64, 8, 18, 22, 0.5, 0, 0, 0), (2501, 13, 19, 21, 0.5, 50, 60, 1)):
+                                                        (50, 50, 19, 21, 0.45, 100, 2500, 0), (64, 8, 18, 22, 0.5, 0, 0, 0), (2501, 13, 19, 21, 0.5, 50, 60, 1),
+                                                        (333, 16, 19, 21, 0.5, 0, 0, 0), (1000, 17, 18, 22, 0.45, 20, 40, 1)):
         got = ctx.depthwin(d, q, w, inc, lo, hi, thr, edge, minlen, boring)
         want = []
         for c, (dd, qq) in enumerate(zip(d, q)):
