@@ -47,52 +47,6 @@ static void bits_help(FILE *fp, const bits_opt_t *o)
     fprintf(fp, "   --verbose INT              verbosity level [%d]\n", o->verbose);
 }
 
-/* ---- the two files, token by token: fscanf("%s\t%d\t%d\t%d\n") reads whitespace-separated tokens, whatever the line
- * structure (:202,211).  A memory map and a hand-written integer reader instead of fscanf: the files hold one line
- * per BASE (tens of GB for a human assembly). */
-typedef struct { const char *p, *e; void *map; size_t size; } tok_t;
-
-static void tok_open(tok_t *t, const char *path)
-{
-    const int fd = open(path, O_RDONLY);
-    struct stat sb;
-    if (fd < 0 || fstat(fd, &sb) != 0) { CORN_ERROR("Could not to open file %s: %s", path, strerror(errno)); exit(EXIT_FAILURE); }
-    t->size = (size_t)sb.st_size;
-    t->map = t->size ? mmap(NULL, t->size, PROT_READ, MAP_PRIVATE, fd, 0) : NULL;
-    if (t->size && t->map == MAP_FAILED) { CORN_ERROR("Could not to open file %s: %s", path, strerror(errno)); exit(EXIT_FAILURE); }
-    if (t->size) madvise(t->map, t->size, MADV_SEQUENTIAL);
-    close(fd);
-    t->p = (const char *)t->map; t->e = t->p + t->size;
-}
-
-static int is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
-
-/* one record: 4 = all fields converted, EOF = nothing left, else the number of fields converted (what fscanf returns) */
-static int tok_record(tok_t *t, const char **name, size_t *name_len, int *st, int *end, int *depth)
-{
-    while (t->p < t->e && is_ws(*t->p)) ++t->p;
-    if (t->p >= t->e) return EOF;
-    *name = t->p;
-    while (t->p < t->e && !is_ws(*t->p)) ++t->p;
-    *name_len = (size_t)(t->p - *name);
-    int *dst[3] = { st, end, depth };
-    for (int k = 0; k < 3; ++k) {
-        while (t->p < t->e && is_ws(*t->p)) ++t->p;
-        if (t->p >= t->e) return 1 + k;                       /* (fscanf: input failure after k + 1 conversions) */
-        const char *q = t->p;
-        int neg = 0;
-        if (*q == '-' || *q == '+') { neg = *q == '-'; ++q; }
-        if (q >= t->e || *q < '0' || *q > '9') return 1 + k;  /* matching failure */
-        long long v = 0;
-        while (q < t->e && *q >= '0' && *q <= '9') { v = v * 10 + (*q - '0'); if (v > 0x7fffffffLL) v = 0x7fffffffLL; ++q; }
-        *dst[k] = (int)(neg ? -v : v);
-        t->p = q;
-    }
-    return 4;
-}
-
-typedef struct { char *name; uint64_t off; uint32_t len; } ctg_t;
-
 int boringbits_main(int argc, char *argv[], int boring)
 {
     bits_opt_t o;
@@ -100,6 +54,7 @@ int boringbits_main(int argc, char *argv[], int boring)
     o.low_cov_thresh = 0.4f; o.high_cov_thresh = 2.5f; o.low_mq_cov_thresh = 0.4f;
     o.min_ctg_len = 1000000; o.edge_len = 100000; o.verbose = 4;
     const char *covmq = NULL;
+    int threads = 0;                                         /* -t: the reference parses it and never uses it; here: text reader threads */
     FILE *fp_help = stderr;
     int c, longindex = 0;
     optind = 1;
@@ -117,7 +72,10 @@ int boringbits_main(int argc, char *argv[], int boring)
         else if (c == 'e') o.edge_len = atoi(optarg);
         else if (c == 'B' && atof(optarg) <= 0) { CORN_ERROR("%s", "Maximum number of bytes should be larger than 0."); exit(EXIT_FAILURE); }
         else if (c == 'K' && atoi(optarg) < 1) { CORN_ERROR("Batch size should larger than 0. You entered %d", atoi(optarg)); exit(EXIT_FAILURE); }
-        else if (c == 't' && atoi(optarg) < 1) { CORN_ERROR("Number of threads should larger than 0. You entered %d", atoi(optarg)); exit(EXIT_FAILURE); }
+        else if (c == 't') {
+            threads = atoi(optarg);
+            if (threads < 1) { CORN_ERROR("Number of threads should larger than 0. You entered %d", threads); exit(EXIT_FAILURE); }
+        }
     }
     if (argc - optind != 1 || fp_help == stdout || covmq == NULL) {
         bits_help(fp_help, &o);
@@ -130,60 +88,24 @@ int boringbits_main(int argc, char *argv[], int boring)
     }
     cornetto_gpu_prefetch();                                 /* the driver starts while the text is parsed */
 
-    /* ---- get_depths(), :179-293 ---- */
-    tok_t t1, t2;
-    tok_open(&t1, covtotal);
-    tok_open(&t2, covmq);
-    ctg_t *ctg = NULL;
-    size_t n_ctg = 0, m_ctg = 0;
-    uint64_t n_tot = 0, cap = 1u << 20;
-    uint16_t *depth = (uint16_t *)malloc(cap * sizeof(uint16_t)), *mq = (uint16_t *)malloc(cap * sizeof(uint16_t));
-    CORN_MALLOC_CHK(depth); CORN_MALLOC_CHK(mq);
-    const char *prev = NULL;
-    size_t prev_len = 0;
-    int prev_pos = 0;
-    double tot_depth = 0, tot_mq = 0, tot_len = 0;
-    for (;;) {
-        const char *n1, *n2;
-        size_t l1, l2;
-        int st1, st2, e1, e2, d1, d2;
-        int ret = tok_record(&t1, &n1, &l1, &st1, &e1, &d1);
-        if (ret == EOF) break;
-        if (ret != 4) { CORN_ERROR("The depth files should have 4 columns. Had %d.", ret); exit(EXIT_FAILURE); }
-        ret = tok_record(&t2, &n2, &l2, &st2, &e2, &d2);
-        if (ret == EOF) { CORN_ERROR("%s", "The two files are not in the same order"); exit(EXIT_FAILURE); }
-        if (ret != 4) { CORN_ERROR("The depth files should have 4 columns. Had %d.", ret); exit(EXIT_FAILURE); }
-        if (l1 != l2 || memcmp(n1, n2, l1) != 0 || st1 != st2 || e1 != e2) { CORN_ERROR("%s", "The two files are not in the same order"); exit(EXIT_FAILURE); }
-        if (!prev || l1 != prev_len || memcmp(n1, prev, l1) != 0) {
-            prev = n1; prev_len = l1;
-            if (n_ctg == m_ctg) { m_ctg = m_ctg ? m_ctg * 2 : 16; ctg = (ctg_t *)realloc(ctg, m_ctg * sizeof(ctg_t)); CORN_MALLOC_CHK(ctg); }
-            ctg[n_ctg].name = strndup(n1, l1); CORN_MALLOC_CHK(ctg[n_ctg].name);
-            ctg[n_ctg].off = n_tot; ctg[n_ctg].len = 0;
-            ++n_ctg;
-            prev_pos = 0;
-        } else {
-            if (prev_pos + 1 != st1) { CORN_ERROR("The depth files should be incremantal at one base resolution. Found %d to %d", prev_pos, st1); exit(EXIT_FAILURE); }
-            ++prev_pos;
-        }
-        if (st1 + 1 != e1) { CORN_ERROR("The depth files should have end=start+1. Found %d to %d", st1, e1); exit(EXIT_FAILURE); }
-        if (d1 > 65535) {
-            fprintf(stderr, "[%s::WARNING]\033[1;33m The depth at %.*s:%d-%d was truncated to 65535. Found %d\033[0m At %s:%d\n", "get_depths", (int)l1, n1, st1, e1, d1, __FILE__, __LINE__);
-            d1 = 65535;
-        }
-        if (d2 > 65535) {
-            fprintf(stderr, "[%s::WARNING]\033[1;33m The depth at %.*s:%d-%d was truncated to 65535. Found %d\033[0m At %s:%d\n", "get_depths", (int)l2, n2, st2, e2, d2, __FILE__, __LINE__);
-            d2 = 65535;
-        }
-        if (n_tot == cap) {
-            cap *= 2;
-            depth = (uint16_t *)realloc(depth, cap * sizeof(uint16_t)); mq = (uint16_t *)realloc(mq, cap * sizeof(uint16_t));
-            CORN_MALLOC_CHK(depth); CORN_MALLOC_CHK(mq);
-        }
-        if (ctg[n_ctg - 1].len == 0x7fffffffu) { CORN_ERROR("contig %s is too long", ctg[n_ctg - 1].name); exit(EXIT_FAILURE); }
-        depth[n_tot] = (uint16_t)d1; mq[n_tot] = (uint16_t)d2;
-        ++n_tot; ++ctg[n_ctg - 1].len;
-        tot_depth += d1; tot_mq += d2; tot_len++;
+    /* ---- get_depths(), :179-293: blocks of both files on several threads when the text is plain (depthtxt.c), else --
+     * and for small files -- the one-pass reader that reports what the reference reports ---- */
+    depth_text_t t1, t2;
+    depthtxt_open(&t1, covtotal);
+    depthtxt_open(&t2, covmq);
+    depth_table_t T;
+    {
+        const char *e_min = getenv("CORNETTO_DEPTH_PAR_MIN"), *e_blk = getenv("CORNETTO_DEPTH_BLOCK");
+        const size_t par_min = e_min ? (size_t)strtoull(e_min, NULL, 10) : ((size_t)8 << 20);
+        const size_t block = e_blk ? (size_t)strtoull(e_blk, NULL, 10) : ((size_t)16 << 20);
+        if (threads == 0) { const long nc = sysconf(_SC_NPROCESSORS_ONLN); threads = nc < 1 ? 1 : (nc > 16 ? 16 : (int)nc); }
+        if (t1.size < par_min || depthtxt_load_parallel(&t1, &t2, threads, block, &T) != 0) depthtxt_load_serial(&t1, &t2, &T);
     }
+    const size_t n_ctg = T.n_ctg;
+    const depth_ctg_t *ctg = T.ctg;
+    const uint64_t n_tot = T.n_tot;
+    uint16_t *depth = T.depth, *mq = T.mq;
+    const double tot_depth = T.tot_depth, tot_mq = T.tot_mq, tot_len = (double)T.n_tot;
     const int mean_depth = (int)round(tot_depth / tot_len), mean_mq_depth = (int)round(tot_mq / tot_len);
 
     /* the_boring_bits(), :504-513 */
@@ -246,10 +168,8 @@ int boringbits_main(int argc, char *argv[], int boring)
     outbuf_free(&ob);
     corn_gpu_depth_windows_free(&w);
     if (!cornetto_fast_exit()) {
-        for (size_t i = 0; i < n_ctg; ++i) free(ctg[i].name);
-        free(ctg); free(depth); free(mq);
-        if (t1.size) munmap(t1.map, t1.size);
-        if (t2.size) munmap(t2.map, t2.size);
+        depth_table_free(&T);
+        depthtxt_close(&t1); depthtxt_close(&t2);
     }
     return 0;
 }

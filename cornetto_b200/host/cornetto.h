@@ -142,6 +142,18 @@ void     gzsrc_close(gzsrc_t *g);
 int      gzsrc_is_bgzf(const gzsrc_t *g);
 int64_t  gzsrc_read(gzsrc_t *g, uint8_t *dst, uint64_t n, int *eof);
 
+/* ---- the two per-base depth tables of noboringbits / boringbits (depthtxt.c; get_depths(), src/boringbits_main.c:179-293).
+ * depthtxt_load_parallel returns -1, with nothing printed, for any input the serial reader would not accept silently;
+ * the caller then runs depthtxt_load_serial, which reports and exits as the reference does. */
+typedef struct { const char *p, *e; void *map; size_t size; } depth_text_t;
+typedef struct { char *name; uint64_t off; uint32_t len; } depth_ctg_t;
+typedef struct { depth_ctg_t *ctg; size_t n_ctg; uint16_t *depth, *mq; uint64_t n_tot; double tot_depth, tot_mq; } depth_table_t;
+void depthtxt_open(depth_text_t *t, const char *path);
+void depthtxt_close(depth_text_t *t);
+void depthtxt_load_serial(depth_text_t *t1, depth_text_t *t2, depth_table_t *T);
+int  depthtxt_load_parallel(const depth_text_t *t1, const depth_text_t *t2, int threads, size_t block_bytes, depth_table_t *T);
+void depth_table_free(depth_table_t *T);
+
 /* length of a record name starting at p: up to the first isspace() byte or max (src/kseq.h:195) */
 size_t cornetto_name_len(const uint8_t *p, size_t max);
 

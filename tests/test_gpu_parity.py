@@ -338,6 +338,29 @@ def test_cli_noboringbits_matches_golden(tmp_path):
     bad = write(str(tmp_path / "bad.bg"), synth.bedgraph_bytes(named[1:], 2))
     _, err, rc = cornetto(["noboringbits", t, "-q", bad], check=False)
     assert rc == 1 and b"The two files are not in the same order" in err
+    # the block-parallel text reader (host/depthtxt.c) declines these files (one depth above 65535) and the one-pass
+    # reader takes over: same output, same warning
+    par = {"CORNETTO_DEPTH_PAR_MIN": "0", "CORNETTO_DEPTH_BLOCK": "3000"}
+    key, exp = next(iter(golden_util.load_bits().items()))
+    out, err, _ = cornetto(key.split()[:1] + [t, "-q", q] + key.split()[1:], env=par)
+    assert out == exp and b"truncated to 65535" in err
+    _, err, rc = cornetto(["noboringbits", t, "-q", bad], check=False, env=par)
+    assert rc == 1 and b"The two files are not in the same order" in err
+
+
+def test_cli_noboringbits_parallel_reader(tmp_path, oracle_bin):
+    """Plain depth tables go through the block-parallel reader (forced here for small files, blocks of 3000 bytes and of
+    1 MB, 1 and 5 threads): stdout identical to the oracle's for every option set, both commands."""
+    named = [(nm, np.minimum(d, 65535), np.minimum(m, 65535)) for nm, d, m in synth.depth_arrays(21, [40000, 12000, 900, 2500, 2549, 7, 25000])]
+    t = write(str(tmp_path / "cov-total.bg"), synth.bedgraph_bytes(named, 1))
+    q = write(str(tmp_path / "cov-mq20.bg"), synth.bedgraph_bytes(named, 2))
+    for cmd in ("noboringbits", "boringbits"):
+        for k, opts in enumerate(synth.BITS_OPTS):
+            want, _, _ = run([oracle_bin, cmd, t, "-q", q] + opts)
+            block, threads = ("3000", "5") if k % 2 == 0 else ("1048576", "1")
+            out, err, _ = cornetto([cmd, t, "-q", q, "-t", threads] + opts, env={"CORNETTO_DEPTH_PAR_MIN": "0", "CORNETTO_DEPTH_BLOCK": block})
+            assert out == want, (cmd, opts)
+            assert b"Number of contigs: 7" in err and b"truncated" not in err
 
 
 def test_abi_depthwin(ctx, capi):

@@ -464,3 +464,57 @@ def test_scan_commands_fail_loudly_without_gpu(built, tmp_path):
     assert rc == 1 and err.startswith(b"Usage: sdust [-w 64] [-t 20] <in.fa>")
     _, err, rc = run([BIN, "telobreaks", "a", "b"], check=False)
     assert rc == 1 and b"Usage: telobreaks" in err
+
+
+def test_depth_text_readers(tmp_path):
+    """host/depthtxt.c: the parallel reader of noboringbits' two depth tables returns exactly what the one-pass reader
+    (the restatement of get_depths(), src/boringbits_main.c:179-293) returns, whatever the block size and thread count --
+    or declines (exit 3) for every input the reference would reject, warn about, or tokenise across lines."""
+    exe = str(tmp_path / "depthtxt_dump")
+    subprocess.check_call(["gcc", "-O2", "-std=c99", "-D_GNU_SOURCE", "-I" + INC, "-o", exe, os.path.join(ROOT, "tests", "sim", "depthtxt_dump.c"),
+                           os.path.join(ROOT, "cornetto_b200", "host", "depthtxt.c"), "-lpthread"])
+    named = [(nm, np.minimum(d, 65535), np.minimum(q, 65535)) for nm, d, q in synth.depth_arrays(5, [30000, 1, 12000, 900, 7])]
+    named.append((named[0][0], named[3][1], named[3][2]))                  # the first name again: a new contig (names are compared with the previous record only)
+    f1, f2 = synth.bedgraph_bytes(named, 1), synth.bedgraph_bytes(named, 2)
+    p1, p2 = write(str(tmp_path / "a1.bg"), f1), write(str(tmp_path / "a2.bg"), f2)
+    want, _, _ = run([exe, p1, p2, "serial"])
+    head, _, body = want.partition(b"\n")
+    n_tot = sum(len(d) for _, d, _ in named)
+    assert head == f"n_ctg {len(named)} n_tot {n_tot} tot_depth {sum(int(d.sum()) for _, d, _ in named)} tot_mq {sum(int(q.sum()) for _, _, q in named)}".encode()
+    arrays = want[len(want) - 4 * n_tot:]
+    assert arrays == np.concatenate([d for _, d, _ in named]).astype("<u2").tobytes() + np.concatenate([q for _, _, q in named]).astype("<u2").tobytes()
+    for threads, block in (("1", "64"), ("3", "100"), ("8", "1000"), ("4", "4096"), ("5", "65537"), ("2", "100000000")):
+        got, _, rc = run([exe, p1, p2, "parallel", threads, block], check=False)
+        assert rc == 0 and got == want, (threads, block)
+    # accepted variants of the same table: CRLF line ends, blank lines, spaces for tabs, no newline at the end
+    for k, (g1, g2) in enumerate(((f1.replace(b"\n", b"\r\n"), f2), (f1.replace(b"\n", b"\n\n", 50), f2.replace(b"\t", b"  ")), (f1[:-1], f2[:-1] + b"\n \n"))):
+        q1, q2 = write(str(tmp_path / f"v{k}_1.bg"), g1), write(str(tmp_path / f"v{k}_2.bg"), g2)
+        for block in ("77", "5000"):
+            got, _, rc = run([exe, q1, q2, "parallel", "4", block], check=False)
+            assert rc == 0 and got == want, (k, block)
+    # declined: everything the one-pass reader reports (or reads differently from a line-by-line parse)
+    lines1 = f1.split(b"\n")
+    def edited(i, new):
+        return b"\n".join(lines1[:i] + [new] + lines1[i + 1:])
+    bad = {
+        "big": (edited(200, b"ctg1\t200\t201\t70000"), f2),
+        "five": (edited(200, b"ctg1\t200\t201\t30\t9"), f2),
+        "three": (edited(200, b"ctg1\t200\t201"), f2),
+        "split": (edited(200, b"ctg1\t200\n201\t30"), f2),
+        "sign": (edited(200, b"ctg1\t200\t201\t+30"), f2),
+        "gap": (edited(200, b"ctg1\t201\t202\t30"), f2),
+        "end": (edited(200, b"ctg1\t200\t202\t30"), f2),
+        "start": (edited(30000, b"ctg2\t5\t6\t30") + b"ctg2\t6\t7\t30\n", f2),
+        "names": (f1, f2.replace(b"ctg3\t", b"ctgX\t")),
+        "longer": (f1, f2 + b"zz\t0\t1\t3\n"),
+        "shorter": (f1 + b"zz\t0\t1\t3\n", f2),
+    }
+    for k, (g1, g2) in bad.items():
+        q1, q2 = write(str(tmp_path / f"b{k}_1.bg"), g1), write(str(tmp_path / f"b{k}_2.bg"), g2)
+        for block in ("90", "100000"):
+            _, _, rc = run([exe, q1, q2, "parallel", "4", block], check=False)
+            assert rc == 3, (k, block)
+    # empty inputs
+    e = write(str(tmp_path / "empty.bg"), b"")
+    got, _, rc = run([exe, e, e, "parallel"], check=False)
+    assert rc == 0 and got == b"n_ctg 0 n_tot 0 tot_depth 0 tot_mq 0\n"
