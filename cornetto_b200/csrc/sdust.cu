@@ -614,8 +614,8 @@ struct ItemParams {
     const uint32_t *total;          // number of items (device)
     uint32_t cap_items;
     uint32_t *it_rec, *it_c0, *it_c1, *it_flags;
-    uint32_t *it_list, *n_lists;    // item numbers by class: dense ones from the front, sparse ones from the back of
-                                    // it_list[0 .. *total); n_lists[0] / [1] = sparse / dense items placed so far
+    uint32_t dense_pct;             // an item is dense when at least this share (%) of its positions are trigger positions
+    uint32_t *it_dense;             // [n_items] 1 = dense item (k_sdust_items); scanned to the item's rank in its class
 };
 
 __device__ __forceinline__ bool item_starts_at(const uint8_t *__restrict__ active, uint32_t j, uint32_t first_blk_of_rec)
@@ -637,25 +637,6 @@ __global__ void __launch_bounds__(256) k_sdust_item_starts(const ItemParams P)
     P.start[j] = v;
 }
 
-// places item number `it` into its class's end of it_list: one atomic per warp and class, not one per item (a few
-// million atomics on two addresses were 0.9 ms of a 1.2 Gb batch)
-__device__ __forceinline__ void place_item(const ItemParams &P, bool have, bool dense, uint32_t it)
-{
-    const uint32_t FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const uint32_t md = __ballot_sync(FULL, have && dense), ms = __ballot_sync(FULL, have && !dense);
-    uint32_t bd = 0, bs = 0;
-    if (lane == 0) {
-        if (md) bd = atomicAdd(&P.n_lists[1], (uint32_t)__popc(md));
-        if (ms) bs = atomicAdd(&P.n_lists[0], (uint32_t)__popc(ms));
-    }
-    bd = __shfl_sync(FULL, bd, 0); bs = __shfl_sync(FULL, bs, 0);
-    if (!have) return;
-    const uint32_t below = corn_lanemask_lt();
-    if (dense) P.it_list[bd + __popc(md & below)] = it;
-    else P.it_list[*P.total - 1u - (bs + __popc(ms & below))] = it;
-}
-
 __global__ void __launch_bounds__(256) k_sdust_items(const ItemParams P, const uint32_t *__restrict__ item_no)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -667,9 +648,8 @@ __global__ void __launch_bounds__(256) k_sdust_items(const ItemParams P, const u
         have = item_starts_at(P.active, j, b0);
     }
     if (have) { it = item_no[j]; have = it < P.cap_items; }            // (beyond the tables: host grows them and repeats)
-    if (!__any_sync(0xffffffffu, have)) return;
+    if (!have) return;
     bool dense = false;
-    if (have) {
     const uint32_t len = P.rec_len[rec], k = j - b0, nb = (len + SD_BLK - 1) / SD_BLK;
     uint32_t e = k + 1;                                                // the item runs to the next cut or to the end of the active run
     while (e < nb && P.active[b0 + e] && (e % (SD_ITEM_MAX / SD_BLK)) != 0) ++e;
@@ -684,12 +664,23 @@ __global__ void __launch_bounds__(256) k_sdust_items(const ItemParams P, const u
     // warp, one per lane, with the cooperative routines serving whichever lane needs them (k_sdust_scan<2, true>).
     uint32_t trig = 0;
     for (uint32_t b = k; b < e; ++b) trig += P.tcnt[b0 + b];
-    dense = trig * 4u >= (e - k) * SD_BLK;
+    dense = trig * 100u >= (e - k) * SD_BLK * P.dense_pct;
     // the dense kernel only takes items without a non-ACGT byte from their warm start (at most 3W + 2 = 194 bases, i.e.
     // four blocks, before c0) to their end
     for (uint32_t b = k >= 4u ? k - 4u : 0u; dense && b < e; ++b) dense = P.nflag[b0 + b] == 0;
-    }
-    place_item(P, have, dense, it);                                    // (all lanes of the warp: one call site)
+    P.it_dense[it] = dense ? 1u : 0u;
+}
+
+// item numbers by class, each class in position order: dense items are it_list[0 .. *n_dense), sparse ones follow.
+// rank = exclusive scan of it_dense.  (Placing them with one atomicAdd per warp and class on two counters cost 2.2 ms of a
+// 3 Gb batch: ~1.5 M returning atomics on two addresses.)
+__global__ void __launch_bounds__(256) k_sdust_item_lists(const uint32_t *__restrict__ it_dense, const uint32_t *__restrict__ rank,
+                                                           uint32_t n_items, const uint32_t *__restrict__ n_dense, uint32_t *__restrict__ it_list)
+{
+    const uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const uint32_t r = rank[it];
+    it_list[it_dense[it] ? r : *n_dense + (it - r)] = it;
 }
 
 struct ItemGatherParams {
@@ -934,7 +925,7 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     const uint32_t n_chunks = (uint32_t)n_chunks64, n_blk = (uint32_t)n_blk64;
 
     CORN_TRY(corn_dbuf_reserve(ctx, &ctx->misc, 4096));
-    uint32_t *d_tot = (uint32_t *)((uint8_t *)ctx->misc.p + 2048);   // [0] intervals, [1] items, [4] overflow errors, [8] task counter, [10..11] list counters
+    uint32_t *d_tot = (uint32_t *)((uint8_t *)ctx->misc.p + 2048);   // [0] intervals, [1] items, [4] overflow errors, [8] task counter, [11] dense items, [12] dense task counter
     uint32_t *d_err = d_tot + 4;
     CORN_CUDA(ctx, cudaMemsetAsync(d_tot, 0, 64, st));
 
@@ -970,6 +961,8 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     memset(&ip, 0, sizeof ip);
     ip.active = active; ip.tcnt = tcnt; ip.nflag = nflag; ip.blk_base = blk_base; ip.rec_len = db->d_rec_len; ip.n_rec = n_rec; ip.n_blk = n_blk;
     ip.start = item_no; ip.total = d_tot + 1;
+    ip.dense_pct = 25;
+    if (const char *e = getenv("CORNETTO_SDUST_DENSE_PCT")) { const int v = atoi(e); if (v >= 1 && v <= 1000) ip.dense_pct = (uint32_t)v; }
     k_sdust_item_starts<<<(n_blk + 255) / 256, 256, 0, st>>>(ip);
     corn_count_launch(ctx);
     CORN_LAUNCH_CHECK(ctx);
@@ -1004,8 +997,12 @@ static int sdust_run_fast(corn_ctx *ctx, const corn_dbatch *db, int T, int W, co
     uint32_t *gslots = (uint32_t *)((uint8_t *)ctx->sd_slots.p + iv_bytes);
     CORN_CUDA(ctx, cudaMemsetAsync(gslots, 0, (size_t)n_items * slot_words * sizeof(uint32_t), st));
     ip.cap_items = n_items;
-    ip.it_rec = it_rec; ip.it_c0 = it_c0; ip.it_c1 = it_c1; ip.it_flags = it_flags; ip.it_list = it_list; ip.n_lists = d_tot + 10;
+    ip.it_rec = it_rec; ip.it_c0 = it_c0; ip.it_c1 = it_c1; ip.it_flags = it_flags; ip.it_dense = out_cnt;          // (out_cnt / out_off are free until the gather)
     k_sdust_items<<<(n_blk + 255) / 256, 256, 0, st>>>(ip, item_no);
+    corn_count_launch(ctx);
+    CORN_LAUNCH_CHECK(ctx);
+    CORN_TRY(corn_scan_u32(ctx, out_cnt, out_off, n_items, d_tot + 11));
+    k_sdust_item_lists<<<(n_items + 255) / 256, 256, 0, st>>>(out_cnt, out_off, n_items, d_tot + 11, it_list);
     k_sdust_item_off<<<(n_items + 255) / 256, 256, 0, st>>>(it_off, n_items, cap);
     corn_count_launch(ctx, 2);
     CORN_LAUNCH_CHECK(ctx);
