@@ -875,35 +875,74 @@ def main():
     texts = [fasta_text(b) for b in blocks]
     for t in texts:
         Lc.corn_gpu_host_register(t.ctypes.data, len(t))
-    hits = capi.Hits()
-
-    def e2e_step():
+    def e2e_step(c):
+        hits = capi.Hits()
         nrun = nwin = 0
         for t in texts:
-            ing = ctx.ingest(t, final=True, keep_db=True)
-            capi._check(ctx.ctx, Lc.corn_gpu_telofind_dev(ctx.ctx, ing["db"], b"TTAGGG", C.byref(hits)), "corn_gpu_telofind_dev")
+            ing = c.ingest(t, final=True, keep_db=True)
+            capi._check(c.ctx, Lc.corn_gpu_telofind_dev(c.ctx, ing["db"], b"TTAGGG", C.byref(hits)), "corn_gpu_telofind_dev")
             nrun += hits.n_run
             Lc.corn_gpu_hits_free(C.byref(hits))
-            nwin += len(ctx.telowin(THR))
-            ctx.free(ing["db"])
+            nwin += len(c.telowin(THR))
+            c.free(ing["db"])
         return nrun, nwin
 
-    e2e_step()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record(stream)
-    for _ in range(args.e2e_steps):
-        nrun, nwin = e2e_step()
-    ev1.record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    e2e_ms = allmax(ev0.elapsed_time(ev1))                 # device time, max over ranks (the host wall clock is reported beside it)
+    def e2e_run(steps, use):
+        """`steps` complete passes.  With two host contexts, two host threads take the steps alternately (every ABI call
+        is synchronous, ctypes releases the GIL): while one step's text is parsed and scanned, the next step's text is
+        already crossing PCIe -- the same double buffering as the resident loop above, and what the drop-in binary's
+        two workers per device do with file blocks."""
+        if len(use) == 1:
+            res = [e2e_step(use[0]) for _ in range(steps)]
+            return res[-1]
+        import threading
+        nxt, res, errs, mu = [0], [None] * steps, [], threading.Lock()
+
+        def worker(c):
+            try:
+                while True:
+                    with mu:
+                        i = nxt[0]; nxt[0] += 1
+                    if i >= steps:
+                        return
+                    res[i] = e2e_step(c)
+            except BaseException as e:          # noqa: BLE001 (re-raised on the main thread)
+                errs.append(e)
+        th = [threading.Thread(target=worker, args=(c,)) for c in use]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        return res[-1]
+
+    def e2e_timed(steps, use):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        nrun, nwin = e2e_run(steps, use)
+        ev1.record(stream)                      # (every step ended with a host sync: the device is idle here)
+        barrier()
+        t_wall = time.perf_counter() - t0
+        return allmax(ev0.elapsed_time(ev1)), allmax(t_wall * 1e3), nrun, nwin
+
+    for c in ctxs:
+        e2e_step(c)                             # warm-up: buffers of both contexts sized
+    one_ms, one_wall, nrun, nwin = e2e_timed(args.e2e_steps, ctxs[:1])
+    e2e_ms, e2e_wall, e2e_steps = one_ms, one_wall, args.e2e_steps
+    if len(ctxs) > 1:
+        e2e_steps = 2 * args.e2e_steps
+        e2e_ms, e2e_wall, nrun, nwin = e2e_timed(e2e_steps, ctxs)
     text_bytes = int(sum(len(t) for t in texts))
-    line["e2e"] = {"value": float(n_bases_total) * args.e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+    line["e2e"] = {"value": float(n_bases_total) * e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
                    "h2d_bytes_per_step": int(allsum(text_bytes)), "d2h_bytes_per_step": int(allsum(int(nrun) * 16 + int(nwin) * 16)),
-                   "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps, "host_wall_ms_per_step": allmax(t_wall * 1e3) / args.e2e_steps,
-                   "what": "FASTA text (60 columns) in page-locked host memory -> corn_gpu_ingest (PCIe + device parse) -> corn_gpu_telofind_dev -> corn_gpu_telowin -> runs + windows on the host",
+                   "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "host_wall_ms_per_step": e2e_wall / e2e_steps,
+                   "host_contexts": len(ctxs),
+                   "one_context": {"value": float(n_bases_total) * args.e2e_steps / (one_ms * 1e-3) / 1e9, "ms_per_step": one_ms / args.e2e_steps, "steps": args.e2e_steps},
+                   "what": "FASTA text (60 columns) in page-locked host memory -> corn_gpu_ingest (PCIe + device parse) -> corn_gpu_telofind_dev -> corn_gpu_telowin -> runs + windows on the host"
+                           + ("; two host contexts take the steps alternately (the next step's H2D copy overlaps this step's parse + scan)" if len(ctxs) > 1 else ""),
                    "bound": "PCIe: the H2D copy of the text (1.02 bytes per base) dominates; parse + scan run ~30x faster"}
     for t in texts:
         Lc.corn_gpu_host_unregister(t.ctypes.data)
