@@ -47,6 +47,22 @@ static void bits_help(FILE *fp, const bits_opt_t *o)
     fprintf(fp, "   --verbose INT              verbosity level [%d]\n", o->verbose);
 }
 
+/* the selected windows of one contig as text: name \t st \t end \t depth \t mq_depth */
+typedef struct { const corn_depth_window_t *win; const char *name; size_t nl; } fmt_bits_t;
+
+static void fmt_bits(outbuf_t *ob, uint64_t begin, uint64_t end, void *arg)
+{
+    const fmt_bits_t *a = (const fmt_bits_t *)arg;
+    for (uint64_t k = begin; k < end; ++k) {
+        outbuf_str(ob, a->name, a->nl);
+        outbuf_chr(ob, '\t'); outbuf_i32(ob, (int)a->win[k].st);
+        outbuf_chr(ob, '\t'); outbuf_i32(ob, (int)a->win[k].end);
+        outbuf_chr(ob, '\t'); outbuf_i32(ob, a->win[k].depth);
+        outbuf_chr(ob, '\t'); outbuf_i32(ob, a->win[k].mq_depth);
+        outbuf_chr(ob, '\n');
+    }
+}
+
 int boringbits_main(int argc, char *argv[], int boring)
 {
     bits_opt_t o;
@@ -155,14 +171,11 @@ int boringbits_main(int argc, char *argv[], int boring)
                 outbuf_str(&ob, name, nl); outbuf_chr(&ob, '\t'); outbuf_i32(&ob, (int)ctg[i].len - o.edge_len); outbuf_chr(&ob, '\t'); outbuf_i32(&ob, (int)ctg[i].len); outbuf_str(&ob, "\t.\t.\n", 5);
             }
         }
-        for (; k < w.n_win && w.win[k].ctg == i; ++k) {
-            outbuf_str(&ob, name, nl);
-            outbuf_chr(&ob, '\t'); outbuf_i32(&ob, (int)w.win[k].st);
-            outbuf_chr(&ob, '\t'); outbuf_i32(&ob, (int)w.win[k].end);
-            outbuf_chr(&ob, '\t'); outbuf_i32(&ob, w.win[k].depth);
-            outbuf_chr(&ob, '\t'); outbuf_i32(&ob, w.win[k].mq_depth);
-            outbuf_chr(&ob, '\n');
-        }
+        uint64_t k1 = k;
+        while (k1 < w.n_win && w.win[k1].ctg == i) ++k1;
+        fmt_bits_t fa = { w.win + k, name, nl };
+        outbuf_format_parallel(&ob, k1 - k, fmt_bits, &fa);                       /* (threads from 200 k lines on) */
+        k = k1;
     }
     outbuf_flush(&ob);
     outbuf_free(&ob);
