@@ -71,6 +71,8 @@ def workload_lengths(name: str):
         return [max(1000, L // 64) for L in CHM13]
     if name == "small3":
         return [max(1000, L // 64) for L in workload_lengths("c3")]
+    if name == "c2q":                        # quarter scale (0.78 Gb): the size of one GPU's shard in the 8-GPU c3 run
+        return [L // 4 for L in CHM13]
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -555,7 +557,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CORN_BENCH_WORKLOAD", ""),
-                    help="c2 (default at N=1), c3 (default at N>1), small, small3")
+                    help="c2 (default at N=1), c3 (default at N>1), small, small3, c2q")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sdust", action="store_true")
