@@ -150,6 +150,8 @@ template <int NB>
 __device__ __forceinline__ void pop_coop(int leader, int lane, sd_state &s, int my_t, uint32_t *smem, const SdLayout &lay, int W)   // (does not touch the slots)
 {
     const uint32_t FULL = 0xffffffffu;
+    __syncwarp();                                     // the leader's own writes to its ring and counts (its last steps) are
+                                                      // visible to the lanes that now read them (shuffles order nothing)
     const int wn = __shfl_sync(FULL, s.wn, leader), whead = __shfl_sync(FULL, s.whead, leader);
     const int L = __shfl_sync(FULL, s.L, leader), t = __shfl_sync(FULL, my_t, leader);
     const sd_mem m = sd_mem_of(smem, lay, (threadIdx.x & ~31) + leader, NULL);
