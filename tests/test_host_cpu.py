@@ -518,3 +518,47 @@ def test_depth_text_readers(tmp_path):
     e = write(str(tmp_path / "empty.bg"), b"")
     got, _, rc = run([exe, e, e, "parallel"], check=False)
     assert rc == 0 and got == b"n_ctg 0 n_tot 0 tot_depth 0 tot_mq 0\n"
+
+
+def test_depth_text_readers_fuzz(tmp_path):
+    """Mutated depth tables (bytes deleted, replaced, duplicated, lines swapped / cut, whitespace injected): whenever the
+    parallel reader accepts a pair of files, the one-pass reader accepts it too, silently, with the same result."""
+    exe = str(tmp_path / "depthtxt_dump")
+    subprocess.check_call(["gcc", "-O2", "-std=c99", "-D_GNU_SOURCE", "-I" + INC, "-o", exe, os.path.join(ROOT, "tests", "sim", "depthtxt_dump.c"),
+                           os.path.join(ROOT, "cornetto_b200", "host", "depthtxt.c"), "-lpthread"])
+    rng = np.random.default_rng(2024)
+    named = [(nm, np.minimum(d, 65535), np.minimum(q, 65535)) for nm, d, q in synth.depth_arrays(9, [300, 1, 120, 45])]
+    f1, f2 = synth.bedgraph_bytes(named, 1), synth.bedgraph_bytes(named, 2)
+    alphabet = np.frombuffer(b"0123456789\t\n \r-+cx", dtype=np.uint8)
+    accepted = 0
+    for case in range(160):
+        g = [bytearray(f1), bytearray(f2)]
+        for _ in range(int(rng.integers(1, 4))):
+            b = g[int(rng.integers(0, 2))]
+            pos = int(rng.integers(0, len(b)))
+            kind = int(rng.integers(0, 6))
+            if kind == 0:
+                del b[pos]
+            elif kind == 1:
+                b[pos] = int(alphabet[rng.integers(0, len(alphabet))])
+            elif kind == 2:
+                b.insert(pos, int(alphabet[rng.integers(0, len(alphabet))]))
+            elif kind == 3:                                   # cut the file
+                del b[pos:]
+            elif kind == 4:                                   # duplicate a line
+                a = b.rfind(b"\n", 0, pos) + 1
+                e = b.find(b"\n", pos) + 1 or len(b)
+                b[a:a] = b[a:e]
+            else:                                             # the same edit in both files (still a consistent pair)
+                for bb in g:
+                    p2 = min(pos, len(bb) - 1)
+                    if bb[p2:p2 + 1].isdigit():
+                        bb[p2] = ord("1")
+        p1, p2 = write(str(tmp_path / "z1.bg"), bytes(g[0])), write(str(tmp_path / "z2.bg"), bytes(g[1]))
+        got, _, rc = run([exe, p1, p2, "parallel", str(int(rng.integers(1, 6))), str(int(rng.choice([64, 97, 500, 4096, 1 << 20])))], check=False)
+        assert rc in (0, 3), case
+        if rc == 0:
+            accepted += 1
+            want, err, rc2 = run([exe, p1, p2, "serial"], check=False)
+            assert rc2 == 0 and err == b"" and got == want, case
+    assert accepted >= 10          # (consistent edits and harmless whitespace do get through)
